@@ -1,0 +1,226 @@
+// oracle/ref_harness.cpp — TEST INFRASTRUCTURE, not product code.
+//
+// A thin C-callable harness around the UNMODIFIED reference implementation
+// (/root/reference/source/FX8010.cpp + helpers.cpp, compiled where they lie by oracle/Makefile
+// into oracle/_ref/libfx8010_ref.so).  It lets tests/ and bench.py's cpu_baseline / --impl
+// reference legs drive Klangraum::FX8010 exactly as source/main.cpp:103-122 does (one process()
+// call per sample) and read back its private state for differential checks.
+//
+// Nothing under fx8010-emulator-core_b200/ may link or load this library.
+//
+// Build notes: -O2 -ffp-contract=off; objects are calloc'ed and
+// placement-new'ed so the TRAM arrays (include/FX8010.h:210-211, uninitialised in the
+// reference) start at zero; std::cout is silenced while the constructor runs
+// (source/FX8010.cpp:18-24,48,61,121).
+
+#include <stdio.h>
+#include <vector>
+#include <string>
+#include <iostream>
+#include <chrono>
+#include <math.h>
+#include <fstream>
+#include <iomanip>
+#include <sstream>
+#include <regex>
+#include <map>
+#include <array>
+#include <unordered_map>
+#include <thread>
+#include <atomic>
+#include <cstring>
+#include <cstdlib>
+#include <new>
+
+// Test-only access to the private state of the reference class (after all std headers).
+#define private public
+#include FX8010_REF_HEADER      // -DFX8010_REF_HEADER='"<reference>/include/FX8010.h"' (see Makefile)
+#undef private
+
+using Klangraum::FX8010;
+
+namespace {
+struct CoutSilencer {
+    std::streambuf* old;
+    std::ostringstream sink;
+    CoutSilencer() : old(std::cout.rdbuf(sink.rdbuf())) {}
+    ~CoutSilencer() { std::cout.rdbuf(old); }
+};
+
+FX8010* make_object(int channels) {
+    void* mem = calloc(1, sizeof(FX8010));
+    if (!mem) return nullptr;
+    CoutSilencer s;
+    return new (mem) FX8010(channels);
+}
+void free_object(FX8010* fx) {
+    if (!fx) return;
+    fx->~FX8010();
+    free(fx);
+}
+}  // namespace
+
+extern "C" {
+
+void* ref_create(int channels) { return make_object(channels); }
+void ref_destroy(void* h) { free_object(static_cast<FX8010*>(h)); }
+size_t ref_sizeof(void) { return sizeof(FX8010); }
+
+int ref_load_file(void* h, const char* path) {
+    CoutSilencer s;
+    return static_cast<FX8010*>(h)->loadFile(path) ? 1 : 0;
+}
+
+// in/out: [n_samples][channels] (the per-sample vectors of source/main.cpp:116-122, back to back)
+void ref_process(void* h, const float* in, float* out, int n_samples) {
+    FX8010* fx = static_cast<FX8010*>(h);
+    const int c = fx->getChannels();
+    std::vector<float> ibuf(c), obuf;
+    for (int s = 0; s < n_samples; ++s) {
+        for (int j = 0; j < c; ++j) ibuf[j] = in ? in[(size_t)s * c + j] : 0.0f;
+        obuf = fx->process(ibuf);
+        for (int j = 0; j < c; ++j) out[(size_t)s * c + j] = obuf[j];
+    }
+}
+
+int ref_set_register(void* h, const char* name, float v) { return static_cast<FX8010*>(h)->setRegisterValue(name, v); }
+float ref_get_register(void* h, const char* name) { return static_cast<FX8010*>(h)->getRegisterValue(name); }
+int ref_get_instruction_counter(void* h) { return static_cast<FX8010*>(h)->getInstructionCounter(); }
+int ref_get_ready(void* h) { return static_cast<FX8010*>(h)->getReadyStatus() ? 1 : 0; }
+int ref_get_channels(void* h) { return static_cast<FX8010*>(h)->getChannels(); }
+
+// ---- decoded image / private state ---------------------------------------------------------
+int ref_num_registers(void* h) { return (int)static_cast<FX8010*>(h)->registers.size(); }
+int ref_num_instructions(void* h) { return (int)static_cast<FX8010*>(h)->instructions.size(); }
+
+// type, io_index -> ints; value -> float; name copied (truncated) into name_buf
+void ref_register_info(void* h, int i, int* type, float* value, int* io_index, char* name_buf, int name_cap) {
+    const auto& r = static_cast<FX8010*>(h)->registers[i];
+    *type = r.registerType; *value = r.registerValue; *io_index = r.IOIndex;
+    if (name_buf && name_cap > 0) { strncpy(name_buf, r.registerName.c_str(), name_cap - 1); name_buf[name_cap - 1] = 0; }
+}
+void ref_register_values(void* h, float* out) {
+    const auto& regs = static_cast<FX8010*>(h)->registers;
+    for (size_t i = 0; i < regs.size(); ++i) out[i] = regs[i].registerValue;
+}
+void ref_set_register_index(void* h, int i, float v) { static_cast<FX8010*>(h)->registers[i].registerValue = v; }
+
+// fields[8] = opcode, R, A, X, Y, hasInput, hasOutput, hasNoise
+void ref_instruction_info(void* h, int i, int* fields) {
+    const auto& in = static_cast<FX8010*>(h)->instructions[i];
+    fields[0] = in.opcode; fields[1] = in.operand1; fields[2] = in.operand2; fields[3] = in.operand3;
+    fields[4] = in.operand4; fields[5] = in.hasInput; fields[6] = in.hasOutput; fields[7] = in.hasNoise;
+}
+
+int ref_itram_size(void* h) { return static_cast<FX8010*>(h)->iTRAMSize; }
+int ref_xtram_size(void* h) { return static_cast<FX8010*>(h)->xTRAMSize; }
+// ptrs[4] = iTRAM write, iTRAM read, xTRAM write, xTRAM read (include/FX8010.h:214-217)
+void ref_tram_pointers(void* h, int* ptrs) {
+    FX8010* fx = static_cast<FX8010*>(h);
+    ptrs[0] = fx->smallDelayWritePos; ptrs[1] = fx->smallDelayReadPos;
+    ptrs[2] = fx->largeDelayWritePos; ptrs[3] = fx->largeDelayReadPos;
+}
+// which 0 = iTRAM, 1 = xTRAM; copies n floats from ring position 0.  Reading past
+// MAX_IDELAY_SIZE on which==0 deliberately follows the reference's adjacent-member layout
+//  so oversize itramsize programs can still be diffed.
+void ref_tram_read(void* h, int which, float* out, int n) {
+    FX8010* fx = static_cast<FX8010*>(h);
+    const float* src = which == 0 ? fx->smallDelayBuffer : fx->largeDelayBuffer;
+    memcpy(out, src, (size_t)n * sizeof(float));
+}
+double ref_accumulator(void* h) { return static_cast<FX8010*>(h)->accumulator; }
+void ref_lfsr(void* h, unsigned int* x) {
+    FX8010* fx = static_cast<FX8010*>(h);
+    x[0] = (unsigned int)fx->g_x1; x[1] = (unsigned int)fx->g_x2;
+}
+// out: [2][32][64] doubles, LOG tables then EXP tables (source/FX8010.cpp:73-105)
+void ref_tables(void* h, double* out) {
+    FX8010* fx = static_cast<FX8010*>(h);
+    for (int t = 0; t < 32; ++t)
+        for (int i = 0; i < 64; ++i) {
+            out[t * 64 + i] = fx->lookupTablesLog[t][i];
+            out[2048 + t * 64 + i] = fx->lookupTablesExp[t][i];
+        }
+}
+
+int ref_num_errors(void* h) { return (int)static_cast<FX8010*>(h)->getErrorList().size(); }
+int ref_error_info(void* h, int i, char* buf, int cap) {
+    auto l = static_cast<FX8010*>(h)->getErrorList();
+    strncpy(buf, l[i].errorDescription.c_str(), cap - 1); buf[cap - 1] = 0;
+    return l[i].errorRow;
+}
+int ref_num_controls(void* h) { return (int)static_cast<FX8010*>(h)->getControlRegisters().size(); }
+void ref_control_name(void* h, int i, char* buf, int cap) {
+    auto l = static_cast<FX8010*>(h)->getControlRegisters();
+    strncpy(buf, l[i].c_str(), cap - 1); buf[cap - 1] = 0;
+}
+// metadata value for key; returns 1 when present
+int ref_metadata(void* h, const char* key, char* buf, int cap) {
+    auto m = static_cast<FX8010*>(h)->getMetaData();
+    auto it = m.find(key);
+    if (it == m.end()) { if (cap > 0) buf[0] = 0; return 0; }
+    strncpy(buf, it->second.c_str(), cap - 1); buf[cap - 1] = 0;
+    return 1;
+}
+
+// ---- CPU baseline: one reference object per thread -------------------------
+// Each of n_threads threads owns one object loaded from `path` and runs n_samples process()
+// calls over its own input column: in is [n_threads][n_samples][channels] (or NULL = zeros);
+// controls (optional): names[n_ctl], values [n_threads][n_ctl] applied before the run.
+// If out != NULL it receives [n_threads][n_samples][channels].  Returns wall seconds of the
+// timed region (all threads started together, joined at the end); *instr_total gets the sum of
+// the per-object instruction-counter deltas (32-bit counters are sampled every 4096 samples).
+double ref_bench(const char* path, int channels, int n_threads, int n_samples, const float* in,
+                 int n_ctl, const char** ctl_names, const float* ctl_values, float* out,
+                 unsigned long long* instr_total, int* load_ok) {
+    std::vector<FX8010*> objs(n_threads, nullptr);
+    *load_ok = 1;
+    for (int t = 0; t < n_threads; ++t) {
+        objs[t] = make_object(channels);
+        CoutSilencer s;
+        if (!objs[t] || !objs[t]->loadFile(path)) *load_ok = 0;
+        for (int k = 0; k < n_ctl && objs[t]; ++k)
+            objs[t]->setRegisterValue(ctl_names[k], ctl_values[(size_t)t * n_ctl + k]);
+    }
+    if (!*load_ok) { for (auto* o : objs) free_object(o); return -1.0; }
+    std::atomic<int> ready{0};
+    std::atomic<bool> go{false};
+    std::vector<unsigned long long> counts(n_threads, 0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) {
+        th.emplace_back([&, t]() {
+            FX8010* fx = objs[t];
+            std::vector<float> ibuf(channels, 0.0f), obuf;
+            const float* my_in = in ? in + (size_t)t * n_samples * channels : nullptr;
+            float* my_out = out ? out + (size_t)t * n_samples * channels : nullptr;
+            unsigned long long total = 0;
+            unsigned int last = (unsigned int)fx->getInstructionCounter();
+            ready.fetch_add(1);
+            while (!go.load(std::memory_order_acquire)) {}
+            for (int s = 0; s < n_samples; ++s) {
+                if (my_in) for (int j = 0; j < channels; ++j) ibuf[j] = my_in[(size_t)s * channels + j];
+                obuf = fx->process(ibuf);
+                if (my_out) for (int j = 0; j < channels; ++j) my_out[(size_t)s * channels + j] = obuf[j];
+                if ((s & 4095) == 4095) {
+                    unsigned int now = (unsigned int)fx->getInstructionCounter();
+                    total += (unsigned int)(now - last); last = now;
+                }
+            }
+            unsigned int now = (unsigned int)fx->getInstructionCounter();
+            total += (unsigned int)(now - last);
+            counts[t] = total;
+        });
+    }
+    while (ready.load() < n_threads) {}
+    auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
+    for (auto& x : th) x.join();
+    auto t1 = std::chrono::steady_clock::now();
+    unsigned long long sum = 0;
+    for (auto c : counts) sum += c;
+    *instr_total = sum;
+    for (auto* o : objs) free_object(o);
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
