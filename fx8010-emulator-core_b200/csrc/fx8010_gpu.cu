@@ -1,0 +1,801 @@
+// fx8010_gpu.cu — the C ABI of include/fx8010_gpu.h: handle, program analysis + encoding, device
+// state, kernel launches and the pipelined host-buffer path.  There is NO CPU fallback in this
+// file: every compute entry point needs a CUDA device and fails with FX8010_ERR_CUDA otherwise.
+//
+// What the reference does per object and per sample (reference source/FX8010.cpp:1023-1249,
+// one FX8010 object = one DSP instance) happens here per handle and per block of samples for
+// N instances at once.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fx8010_kernel.cuh"
+
+using namespace fxk;
+
+namespace {
+
+constexpr int MAX_DEVICES = 64;
+constexpr int HOST_PIPE_BUFS = 3;
+std::mutex g_mutex;
+bool g_slot_used[MAX_DEVICES][PROG_SLOTS];
+thread_local std::string g_create_error;
+
+struct Launch { int K, B, n_seg, seg_len, grid_x; size_t smem; };
+
+}  // namespace
+
+struct fx8010_gpu {
+    int device = 0, N = 0, C = 0;
+    int num_sms = 148;
+    size_t smem_optin = 227 * 1024;
+    bool loaded = false;
+    int slot = -1;
+    // program image (host copies)
+    std::vector<fx8010_instr> instrs;
+    std::vector<fx8010_reg> regs;
+    int itram_size = 0, xtram_size = 0;          // ring sizes actually allocated (0 = unused)
+    std::vector<TableEntry> h_tabs;
+    // analysis
+    std::vector<uint8_t> written;                // program may write the register
+    std::vector<uint8_t> reg_uniform;            // every instance holds reg_value (host knowledge)
+    std::vector<float> reg_value;
+    std::vector<uint32_t> wb;
+    bool has_skip = false, has_ext = false, stateless = false;
+    bool encode_dirty = true;
+    int n_smem_tabs = 0;
+    int smem_tab_id[MAX_SMEM_TABLES] = {0, 0};
+    uint4* h_prog = nullptr;                     // pinned, MAX_INSTR + 1 words
+    // device state
+    float* d_gpr = nullptr; double* d_acc = nullptr; uint32_t* d_lfsr = nullptr; float* d_latch = nullptr;
+    int32_t* d_ptrs = nullptr; float* d_itram = nullptr; float* d_xtram = nullptr;
+    unsigned long long* d_counts = nullptr; unsigned int* d_flags = nullptr; uint32_t* d_wb = nullptr;
+    TableEntry* d_tabs = nullptr;
+    // streams
+    cudaStream_t last_stream = nullptr;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[HOST_PIPE_BUFS] = {}, ev_comp[HOST_PIPE_BUFS] = {}, ev_d2h[HOST_PIPE_BUFS] = {};
+    float* d_stage_in[HOST_PIPE_BUFS] = {}; float* d_stage_out[HOST_PIPE_BUFS] = {};
+    size_t stage_floats = 0;
+    // tuning overrides (0 = heuristic)
+    int tune_K = 0, tune_B = 0, tune_seg = 0, tune_sub = 0;
+    std::string err;
+    fx8010_launch_info info = {};
+};
+
+namespace {
+
+int fail(fx8010_gpu* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+#define FX_CUDA(h, call)                                                                             \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(h, FX8010_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
+    } while (0)
+
+int env_int(const char* name) { const char* s = getenv(name); return s ? atoi(s) : 0; }
+
+// static_cast<int32_t>(float) with x86-64 semantics (same rule as the kernel's cvt_x86)
+int32_t cvt_x86_host(float f) {
+    if (!(f < 2147483648.0f) || f < -2147483648.0f) return INT32_MIN;
+    return (int32_t)f;
+}
+
+Uop uop_of(const fx8010_gpu* h, const fx8010_instr& in) {
+    switch (in.opcode) {
+    case FX_MACS: case FX_MACINTS: return U_MACS;     // MACINTS == MACS in the reference (:1095-1103)
+    case FX_MACSN: return U_MACSN;
+    case FX_MACW: return U_MACW;
+    case FX_MACWN: return U_MACWN;
+    case FX_MACINTW: return U_MACINTW;
+    case FX_ACC3: return U_ACC3;
+    case FX_MACMV: return U_MACMV;
+    case FX_ANDXOR: return U_ANDXOR;
+    case FX_TSTNEG: return U_TSTNEG;
+    case FX_LIMIT: return U_LIMIT;
+    case FX_LIMITN: return U_LIMITN;
+    case FX_LOG: return U_LOG;
+    case FX_EXP: return U_EXP;
+    case FX_INTERP: return U_INTERP;
+    case FX_SKIP: return U_SKIP;
+    case FX_IDELAY: {
+        const int t = h->regs[in.r].type;
+        return t == FX_REG_READ ? U_IREAD : (t == FX_REG_WRITE ? U_IWRITE : U_NOP);
+    }
+    case FX_XDELAY: {
+        const int t = h->regs[in.r].type;
+        return t == FX_REG_READ ? U_XREAD : (t == FX_REG_WRITE ? U_XWRITE : U_NOP);
+    }
+    case FX_END: return U_END;
+    default: return U_NOP;
+    }
+}
+bool writes_r(Uop u) { return u <= U_INTERP; }   // every one of these also runs setCCR
+
+// Which operands of the instruction are preloaded from the input block / which register gets noise.
+void pre_targets(const fx8010_gpu* h, const fx8010_instr& in, bool& pa, bool& px, bool& py, int& noise_reg) {
+    pa = px = py = false; noise_reg = -1;
+    if (in.has_input) {                                         // source/FX8010.cpp:1053-1061
+        pa = h->regs[in.a].type == FX_REG_INPUT;
+        px = h->regs[in.x].type == FX_REG_INPUT;
+        py = h->regs[in.y].type == FX_REG_INPUT;
+    }
+    if (in.has_noise) {                                         // :1063-1071 (first match only)
+        if (h->regs[in.a].is_noise) noise_reg = in.a;
+        else if (h->regs[in.x].is_noise) noise_reg = in.x;
+        else if (h->regs[in.y].is_noise) noise_reg = in.y;
+    }
+}
+
+// Load-time analysis: written set, feature flags, statelessness.
+void analyse(fx8010_gpu* h) {
+    const int n = (int)h->instrs.size(), nr = (int)h->regs.size();
+    h->written.assign(nr, 0);
+    h->has_skip = false; h->has_ext = false;
+    bool any_ccr_writer = false;
+    for (int i = 0; i < n; ++i) {
+        const fx8010_instr& in = h->instrs[i];
+        const Uop u = uop_of(h, in);
+        bool pa, px, py; int nz;
+        pre_targets(h, in, pa, px, py, nz);
+        if (pa) h->written[in.a] = 1;
+        if (px) h->written[in.x] = 1;
+        if (py) h->written[in.y] = 1;
+        if (nz >= 0) { h->written[nz] = 1; h->has_ext = true; }
+        if (writes_r(u)) { h->written[in.r] = 1; any_ccr_writer = true; }
+        if (u == U_IREAD || u == U_XREAD) { h->written[in.a] = 1; h->has_ext = true; }
+        if (u == U_IWRITE || u == U_XWRITE) h->has_ext = true;
+        if (u == U_MACMV) h->has_ext = true;
+        if (u == U_SKIP) h->has_skip = true;
+    }
+    if (any_ccr_writer) h->written[0] = 1;
+    h->wb.clear();
+    for (int r = 0; r < nr; ++r) if (h->written[r]) h->wb.push_back((uint32_t)r);
+
+    // Stateless = no sample period reads anything an earlier period wrote: then the time axis can
+    // be cut into independent segments.  Conservative: SKIP / TRAM / noise / MACMV rule it out.
+    h->stateless = !h->has_skip && !h->has_ext;
+    if (h->stateless) {
+        std::vector<uint8_t> defined(nr, 0);
+        for (int i = 0; i < n && h->stateless; ++i) {
+            const fx8010_instr& in = h->instrs[i];
+            const Uop u = uop_of(h, in);
+            if (u == U_END || u == U_NOP) continue;
+            bool pa, px, py; int nz;
+            pre_targets(h, in, pa, px, py, nz);
+            if (pa) defined[in.a] = 1;
+            if (px) defined[in.x] = 1;
+            if (py) defined[in.y] = 1;
+            const int ops[3] = {in.a, in.x, in.y};
+            for (int o : ops)
+                if (h->written[o] && !defined[o]) h->stateless = false;
+            if (writes_r(u)) { defined[in.r] = 1; defined[0] = 1; }
+        }
+    }
+}
+
+// Encodes the program for the kernel: micro-ops, flags, CCR liveness, table placement.
+void encode(fx8010_gpu* h) {
+    const int n = (int)h->instrs.size();
+    std::vector<Uop> uops(n);
+    for (int i = 0; i < n; ++i) uops[i] = uop_of(h, h->instrs[i]);
+    auto is_const = [&](int r) { return !h->written[r] && h->reg_uniform[r]; };
+
+    // instructions a SKIP may jump over
+    std::vector<uint8_t> maybe_skipped(n, 0);
+    for (int k = 0; k < n; ++k) {
+        if (uops[k] != U_SKIP) continue;
+        long reach = n;
+        const int yr = h->instrs[k].y;
+        if (is_const(yr)) {
+            const int32_t c = cvt_x86_host(h->reg_value[yr]);
+            reach = c > 0 ? c : (c < 0 ? 1 : 0);
+        }
+        for (long d = 1; d <= std::min<long>(reach, n); ++d) maybe_skipped[(k + d) % n] = 1;
+    }
+    // CCR liveness: a setCCR result matters only if a SKIP or a `ccr` operand can see it before the
+    // next unconditional setCCR (the batch-final value is forced by the kernel on the last sample).
+    std::vector<uint8_t> ccr_live(n, 0);
+    auto reads_ccr = [&](int j) {
+        const Uop u = uops[j];
+        if (u == U_END || u == U_NOP) return false;
+        if (u == U_SKIP) return true;
+        const fx8010_instr& in = h->instrs[j];
+        return in.a == 0 || in.x == 0 || in.y == 0;
+    };
+    for (int i = 0; i < n; ++i) {
+        if (!writes_r(uops[i])) continue;
+        if (h->instrs[i].r == 0) { ccr_live[i] = 1; continue; }   // R is ccr itself: the store order matters
+        bool live = true;                                         // nothing kills it within one lap: keep
+        for (int d = 1; d <= n; ++d) {
+            const int j = (i + d) % n;
+            if (reads_ccr(j)) { live = true; break; }
+            if (writes_r(uops[j]) && !maybe_skipped[j]) { live = false; break; }
+        }
+        ccr_live[i] = live;
+    }
+
+    // LOG/EXP with a literal selector: most frequent tables go to shared memory
+    int freq[2 * FX8010_TABLE_COUNT] = {0};
+    std::vector<int> tab_of(n, -1);
+    for (int i = 0; i < n; ++i) {
+        if (uops[i] != U_LOG && uops[i] != U_EXP) continue;
+        const int xr = h->instrs[i].x;
+        if (!is_const(xr)) continue;
+        const int32_t sel = cvt_x86_host(h->reg_value[xr]);
+        if (sel < 0 || sel >= FX8010_TABLE_COUNT) continue;      // out of range: dynamic path raises the flag
+        tab_of[i] = (uops[i] == U_EXP ? FX8010_TABLE_COUNT : 0) + sel;
+        freq[tab_of[i]]++;
+    }
+    h->n_smem_tabs = 0;
+    for (int t = 0; t < MAX_SMEM_TABLES; ++t) {
+        int best = -1;
+        for (int id = 0; id < 2 * FX8010_TABLE_COUNT; ++id)
+            if (freq[id] > 0 && (best < 0 || freq[id] > freq[best])) best = id;
+        if (best < 0) break;
+        h->smem_tab_id[h->n_smem_tabs++] = best;
+        freq[best] = -1;
+    }
+
+    for (int i = 0; i < n; ++i) {
+        const fx8010_instr& in = h->instrs[i];
+        bool pa, px, py; int nz;
+        pre_targets(h, in, pa, px, py, nz);
+        uint32_t w0 = (uint32_t)uops[i];
+        if (pa) w0 |= F_PRE_A;
+        if (px) w0 |= F_PRE_X;
+        if (py) w0 |= F_PRE_Y;
+        if (pa || px || py) w0 |= (uint32_t)(h->regs[in.a].io_index & 0xff) << 16;   // X and Y use A's IOIndex (:1057-1060)
+        uint32_t aux = 0;
+        if (nz >= 0) { w0 |= F_NOISE; aux = (uint32_t)nz; }
+        if (h->regs[in.r].type == FX_REG_OUTPUT && uops[i] != U_END) {           // :1229-1233
+            w0 |= F_OUT | ((uint32_t)(h->regs[in.r].io_index & 0xff) << 24);
+        }
+        if (ccr_live[i]) w0 |= F_CCR;
+        if (tab_of[i] >= 0) {
+            int slot = -1;
+            for (int t = 0; t < h->n_smem_tabs; ++t) if (h->smem_tab_id[t] == tab_of[i]) slot = t;
+            if (slot >= 0) { w0 |= F_TAB_SMEM; aux = (uint32_t)slot; }
+            else { w0 |= F_TAB_IMM; aux = (uint32_t)tab_of[i]; }
+        }
+        h->h_prog[i] = make_uint4(w0, (uint32_t)in.r | ((uint32_t)in.a << 16), (uint32_t)in.x | ((uint32_t)in.y << 16), aux);
+    }
+    h->h_prog[n] = make_uint4((uint32_t)U_END, 0, 0, 0);          // pad: the kernel prefetches pc + 1
+}
+
+void free_state(fx8010_gpu* h) {
+    cudaFree(h->d_gpr); cudaFree(h->d_acc); cudaFree(h->d_lfsr); cudaFree(h->d_latch); cudaFree(h->d_ptrs);
+    cudaFree(h->d_itram); cudaFree(h->d_xtram); cudaFree(h->d_counts); cudaFree(h->d_wb);
+    h->d_gpr = nullptr; h->d_acc = nullptr; h->d_lfsr = nullptr; h->d_latch = nullptr; h->d_ptrs = nullptr;
+    h->d_itram = nullptr; h->d_xtram = nullptr; h->d_counts = nullptr; h->d_wb = nullptr;
+}
+
+typedef void (*KernelFn)(const Params);
+template <int K> KernelFn pick_kernel(bool skip, bool ext) {
+    if (skip) return ext ? fx_interp_kernel<K, true, true> : fx_interp_kernel<K, true, false>;
+    return ext ? fx_interp_kernel<K, false, true> : fx_interp_kernel<K, false, false>;
+}
+KernelFn pick_kernel(int K, bool skip, bool ext) {
+    return K == 4 ? pick_kernel<4>(skip, ext) : (K == 2 ? pick_kernel<2>(skip, ext) : pick_kernel<1>(skip, ext));
+}
+
+// Geometry of one launch: contexts per thread, block size, time split.
+int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_cs, size_t out_cs, int n_samples, Launch& L) {
+    const int N = h->N, C = h->C, nr = (int)h->regs.size();
+    auto aligned = [&](int K) {
+        const size_t a = (size_t)K * 4;
+        return N % K == 0 && ((uintptr_t)d_in % a) == 0 && ((uintptr_t)d_out % a) == 0 &&
+               (in_cs * 4) % a == 0 && (out_cs * 4) % a == 0;
+    };
+    const int min_seg = CHUNK;
+    const long max_seg = h->stateless ? std::max(1, n_samples / min_seg) : 1;
+    const long want_threads = (long)h->num_sms * 512;
+    int K = 4;
+    while (K > 1 && (!aligned(K) || ((long)(N / K) * max_seg < want_threads && N / K < h->num_sms * 128))) K >>= 1;
+    if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
+    // block size: spread small jobs over the SMs, keep several blocks per SM resident
+    int B = 128;
+    auto fits = [&](int b, int k) { return smem_bytes(nr, C, b, k, h->n_smem_tabs) <= h->smem_optin; };
+    while (B > 32 && ((long)((N / K + B - 1) / B) * max_seg < 2L * h->num_sms || smem_bytes(nr, C, B, K, h->n_smem_tabs) > 56 * 1024)) B >>= 1;
+    if (h->tune_B) B = h->tune_B;
+    while (!fits(B, K) && K > 1) K >>= 1;
+    while (!fits(B, K) && B > 32) B >>= 1;
+    if (!fits(B, K)) return fail(h, FX8010_ERR_CAPACITY, "register file does not fit in shared memory");
+    L.K = K; L.B = B;
+    L.smem = smem_bytes(nr, C, B, K, h->n_smem_tabs);
+    L.grid_x = (N / K + B - 1) / B;
+    L.n_seg = 1; L.seg_len = n_samples;
+    if (h->stateless && n_samples > min_seg) {
+        KernelFn fn = pick_kernel(K, h->has_skip, h->has_ext);
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, B, L.smem);
+        occ = std::max(occ, 1);
+        long slots = (long)h->num_sms * occ;
+        long n_seg = std::max(1L, slots / L.grid_x);
+        if (h->tune_seg) n_seg = h->tune_seg;
+        n_seg = std::min(n_seg, max_seg);
+        int seg_len = (int)((n_samples + n_seg - 1) / n_seg);
+        seg_len = (seg_len + CHUNK - 1) / CHUNK * CHUNK;
+        L.seg_len = seg_len;
+        L.n_seg = (n_samples + seg_len - 1) / seg_len;
+    }
+    return FX8010_OK;
+}
+
+int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, size_t out_cs, int n_samples, cudaStream_t st) {
+    if (n_samples == 0) return FX8010_OK;
+    if (h->encode_dirty) {
+        encode(h);
+        FX_CUDA(h, cudaMemcpyToSymbolAsync(c_prog, h->h_prog, sizeof(uint4) * (h->instrs.size() + 1),
+                                           sizeof(uint4) * (size_t)(MAX_INSTR + 1) * h->slot, cudaMemcpyHostToDevice, st));
+        // h_prog is reused by the next encode: make sure the copy has left the pinned buffer
+        FX_CUDA(h, cudaStreamSynchronize(st));
+        h->encode_dirty = false;
+    }
+    // per-launch executed-instruction counters are 32-bit: split very long batches
+    const long long per_sample = (long long)h->instrs.size() * FX8010_MAX_PASSES;
+    const int max_samples = (int)std::max<long long>(1, std::min<long long>(0x7fffffffLL, 0xffffffffLL / per_sample));
+    for (int s0 = 0; s0 < n_samples; s0 += max_samples) {
+        const int ns = std::min(max_samples, n_samples - s0);
+        Launch L;
+        const float* in = d_in ? d_in + (size_t)s0 * h->N : nullptr;
+        float* out = d_out + (size_t)s0 * h->N;
+        const int rc = plan_launch(h, in, out, in_cs, out_cs, ns, L);
+        if (rc) return rc;
+        Params p = {};
+        p.gpr = h->d_gpr; p.acc = h->d_acc; p.lfsr = h->d_lfsr; p.latch = h->d_latch; p.ptrs = h->d_ptrs;
+        p.itram = h->d_itram; p.xtram = h->d_xtram; p.counts = h->d_counts; p.rt_flags = h->d_flags;
+        p.wb_regs = h->d_wb; p.tabs = h->d_tabs;
+        p.in = in; p.out = out; p.in_cstride = in_cs; p.out_cstride = out_cs;
+        p.n_samples = ns; p.seg_len = L.seg_len; p.n_seg = L.n_seg;
+        p.N = h->N; p.C = h->C; p.n_regs = (int)h->regs.size(); p.n_instrs = (int)h->instrs.size();
+        p.n_wb = (int)h->wb.size(); p.slot = h->slot;
+        p.itram_size = h->itram_size; p.xtram_size = h->xtram_size;
+        p.n_smem_tabs = h->n_smem_tabs;
+        for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
+        KernelFn fn = pick_kernel(L.K, h->has_skip, h->has_ext);
+        FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        fn<<<dim3(L.grid_x, L.n_seg), L.B, L.smem, st>>>(p);
+        FX_CUDA(h, cudaGetLastError());
+        h->info.kernel_launches++;
+        h->info.last_grid = L.grid_x * L.n_seg; h->info.last_block = L.B; h->info.last_time_split = L.n_seg;
+        h->info.last_smem_bytes = (int)L.smem;
+        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.K << 8);
+    }
+    h->last_stream = st;
+    return FX8010_OK;
+}
+
+int sync_all(fx8010_gpu* h) {
+    FX_CUDA(h, cudaSetDevice(h->device));
+    if (h->last_stream) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));
+    FX_CUDA(h, cudaStreamSynchronize(h->s_comp));
+    FX_CUDA(h, cudaStreamSynchronize(h->s_h2d));
+    FX_CUDA(h, cudaStreamSynchronize(h->s_d2h));
+    FX_CUDA(h, cudaStreamSynchronize(nullptr));
+    return FX8010_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** out) {
+    if (!out) return fail(nullptr, FX8010_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n_instances <= 0 || n_channels <= 0 || n_channels > 255 || device < 0 || device >= MAX_DEVICES)
+        return fail(nullptr, FX8010_ERR_ARG, "n_instances and n_channels (<= 255) must be positive, device in range");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, FX8010_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device >= count) return fail(nullptr, FX8010_ERR_ARG, "device ordinal out of range");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, FX8010_ERR_CUDA, cudaGetErrorString(e));
+    fx8010_gpu* h = new fx8010_gpu();
+    h->device = device; h->N = n_instances; h->C = n_channels;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        h->num_sms = prop.multiProcessorCount;
+        h->smem_optin = prop.sharedMemPerBlockOptin;
+    }
+    bool ok = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < HOST_PIPE_BUFS && ok; ++i)
+        ok = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMallocHost(&h->h_prog, sizeof(uint4) * (MAX_INSTR + 1)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_flags, sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_tabs, sizeof(TableEntry) * 2 * FX8010_TABLE_COUNT * FX8010_TABLE_ENTRIES) == cudaSuccess;
+    if (!ok) {
+        const std::string msg = std::string("CUDA resource creation failed: ") + cudaGetErrorString(cudaGetLastError());
+        fx8010_gpu_destroy(h);
+        return fail(nullptr, FX8010_ERR_CUDA, msg);
+    }
+    h->tune_K = env_int("FX8010_TUNE_K"); h->tune_B = env_int("FX8010_TUNE_B");
+    h->tune_seg = env_int("FX8010_TUNE_SEG"); h->tune_sub = env_int("FX8010_TUNE_SUB");
+    if (h->tune_K != 1 && h->tune_K != 2 && h->tune_K != 4) h->tune_K = 0;
+    if (h->tune_B != 32 && h->tune_B != 64 && h->tune_B != 128) h->tune_B = 0;
+    *out = h;
+    return FX8010_OK;
+}
+
+void fx8010_gpu_destroy(fx8010_gpu* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    sync_all(h);
+    free_state(h);
+    cudaFree(h->d_flags); cudaFree(h->d_tabs);
+    for (int i = 0; i < HOST_PIPE_BUFS; ++i) {
+        cudaFree(h->d_stage_in[i]); cudaFree(h->d_stage_out[i]);
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+        if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+    }
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    if (h->h_prog) cudaFreeHost(h->h_prog);
+    if (h->slot >= 0) {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        g_slot_used[h->device][h->slot] = false;
+    }
+    delete h;
+}
+
+int fx8010_gpu_load_program(fx8010_gpu* h, const fx8010_program_image* im) {
+    if (!h) return FX8010_ERR_ARG;
+    if (!im || !im->instrs || !im->regs || !im->log_tables || !im->exp_tables) return fail(h, FX8010_ERR_ARG, "image or one of its arrays is NULL");
+    if (im->n_instrs <= 0 || im->n_regs <= 0) return fail(h, FX8010_ERR_PROGRAM, "empty program (the reference would spin forever, SURVEY U10)");
+    if (im->n_instrs > MAX_INSTR) return fail(h, FX8010_ERR_CAPACITY, "more than FX8010_MAX_INSTRUCTIONS instructions");
+    if (im->n_regs > 65535) return fail(h, FX8010_ERR_CAPACITY, "more than 65535 registers");
+    bool has_end = false, use_i = false, use_x = false;
+    for (int i = 0; i < im->n_instrs; ++i) {
+        const fx8010_instr& in = im->instrs[i];
+        if (in.opcode < 0 || in.opcode >= FX_NUM_OPCODES) return fail(h, FX8010_ERR_PROGRAM, "opcode out of range");
+        if (in.r < 0 || in.r >= im->n_regs || in.a < 0 || in.a >= im->n_regs || in.x < 0 || in.x >= im->n_regs ||
+            in.y < 0 || in.y >= im->n_regs) return fail(h, FX8010_ERR_PROGRAM, "operand register index out of range");
+        if (in.opcode == FX_END) has_end = true;
+        const int t = im->regs[in.r].type;
+        if (in.opcode == FX_IDELAY && (t == FX_REG_READ || t == FX_REG_WRITE)) use_i = true;
+        if (in.opcode == FX_XDELAY && (t == FX_REG_READ || t == FX_REG_WRITE)) use_x = true;
+    }
+    if (!has_end) return fail(h, FX8010_ERR_PROGRAM, "program has no END (the reference would spin forever)");
+    for (int r = 0; r < im->n_regs; ++r)
+        if (im->regs[r].io_index < 0 || im->regs[r].io_index >= h->C) return fail(h, FX8010_ERR_PROGRAM, "I/O index outside the channel count");
+    if ((use_i && im->itram_size <= 0) || (use_x && im->xtram_size <= 0))
+        return fail(h, FX8010_ERR_PROGRAM, "IDELAY/XDELAY without a declared TRAM size (SURVEY U4)");
+    if (im->itram_size > (1 << 24) || im->xtram_size > (1 << 24)) return fail(h, FX8010_ERR_CAPACITY, "TRAM size above 2^24");
+
+    FX_CUDA(h, cudaSetDevice(h->device));
+    const int rc = sync_all(h);
+    if (rc) return rc;
+    if (h->slot < 0) {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        for (int s = 0; s < PROG_SLOTS && h->slot < 0; ++s)
+            if (!g_slot_used[h->device][s]) { g_slot_used[h->device][s] = true; h->slot = s; }
+    }
+    if (h->slot < 0) return fail(h, FX8010_ERR_CAPACITY, "all constant-memory program slots of this device are in use (destroy a handle)");
+
+    h->loaded = false;
+    free_state(h);
+    h->instrs.assign(im->instrs, im->instrs + im->n_instrs);
+    h->regs.assign(im->regs, im->regs + im->n_regs);
+    h->itram_size = use_i ? im->itram_size : 0;
+    h->xtram_size = use_x ? im->xtram_size : 0;
+    const size_t N = (size_t)h->N, nr = (size_t)im->n_regs;
+
+    // LOG/EXP tables: T[i] and the interpolation quotient (T[i+1]-T[i])/(x2-x1), evaluated here with
+    // the same IEEE double operations as linearInterpolate (source/FX8010.cpp:285-293); T[64] = 0 (U5).
+    h->h_tabs.resize((size_t)2 * FX8010_TABLE_COUNT * FX8010_TABLE_ENTRIES);
+    const double x_min = -1.0, x_max = 1.0;
+    const double step = (x_max - x_min) / (double)(FX8010_TABLE_ENTRIES - 1);
+    for (int op = 0; op < 2; ++op)
+        for (int t = 0; t < FX8010_TABLE_COUNT; ++t) {
+            const double* T = (op == 0 ? im->log_tables : im->exp_tables) + (size_t)t * FX8010_TABLE_ENTRIES;
+            for (int i = 0; i < FX8010_TABLE_ENTRIES; ++i) {
+                const volatile double x1 = x_min + i * step;
+                const volatile double x2 = x_min + (i + 1) * step;
+                const volatile double y1 = T[i];
+                const volatile double y2 = (i + 1 < FX8010_TABLE_ENTRIES) ? T[i + 1] : 0.0;
+                const volatile double num = y2 - y1, den = x2 - x1;
+                TableEntry e; e.y1 = y1; e.slope = num / den;
+                h->h_tabs[((size_t)op * FX8010_TABLE_COUNT + t) * FX8010_TABLE_ENTRIES + i] = e;
+            }
+        }
+    FX_CUDA(h, cudaMemcpy(h->d_tabs, h->h_tabs.data(), sizeof(TableEntry) * h->h_tabs.size(), cudaMemcpyHostToDevice));
+
+    // capacity check before allocating the rings
+    size_t free_b = 0, total_b = 0;
+    FX_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+    const size_t need = N * (4 * nr + 8 + 8 + 4 * (size_t)h->C + 16 + 8) + 4 * N * ((size_t)h->itram_size + (size_t)h->xtram_size);
+    if (need + (64u << 20) > free_b) return fail(h, FX8010_ERR_CAPACITY, "per-instance state (registers + TRAM rings) does not fit in device memory");
+
+    FX_CUDA(h, cudaMalloc(&h->d_gpr, sizeof(float) * nr * N));
+    FX_CUDA(h, cudaMalloc(&h->d_acc, sizeof(double) * N));
+    FX_CUDA(h, cudaMalloc(&h->d_lfsr, sizeof(uint32_t) * 2 * N));
+    FX_CUDA(h, cudaMalloc(&h->d_latch, sizeof(float) * (size_t)h->C * N));
+    FX_CUDA(h, cudaMalloc(&h->d_ptrs, sizeof(int32_t) * 4 * N));
+    FX_CUDA(h, cudaMalloc(&h->d_counts, sizeof(unsigned long long) * N));
+    if (h->itram_size) { FX_CUDA(h, cudaMalloc(&h->d_itram, sizeof(float) * (size_t)h->itram_size * N)); FX_CUDA(h, cudaMemset(h->d_itram, 0, sizeof(float) * (size_t)h->itram_size * N)); }
+    if (h->xtram_size) { FX_CUDA(h, cudaMalloc(&h->d_xtram, sizeof(float) * (size_t)h->xtram_size * N)); FX_CUDA(h, cudaMemset(h->d_xtram, 0, sizeof(float) * (size_t)h->xtram_size * N)); }
+    // state of a freshly constructed + loaded reference object
+    for (size_t r = 0; r < nr; ++r) {
+        fx_fill_kernel<<<(unsigned)((N + 255) / 256), 256>>>(h->d_gpr + r * N, im->regs[r].init_value, (int)N);
+        h->info.kernel_launches++;
+    }
+    FX_CUDA(h, cudaGetLastError());
+    FX_CUDA(h, cudaMemset(h->d_acc, 0, sizeof(double) * N));
+    FX_CUDA(h, cudaMemset(h->d_latch, 0, sizeof(float) * (size_t)h->C * N));
+    FX_CUDA(h, cudaMemset(h->d_ptrs, 0, sizeof(int32_t) * 4 * N));
+    FX_CUDA(h, cudaMemset(h->d_counts, 0, sizeof(unsigned long long) * N));
+    FX_CUDA(h, cudaMemset(h->d_flags, 0, sizeof(unsigned int)));
+    {
+        std::vector<uint32_t> seeds(2 * N);
+        for (size_t i = 0; i < N; ++i) { seeds[i] = FX8010_LFSR_SEED1; seeds[N + i] = FX8010_LFSR_SEED2; }
+        FX_CUDA(h, cudaMemcpy(h->d_lfsr, seeds.data(), sizeof(uint32_t) * 2 * N, cudaMemcpyHostToDevice));
+    }
+    h->reg_uniform.assign(nr, 1);
+    h->reg_value.resize(nr);
+    for (size_t r = 0; r < nr; ++r) h->reg_value[r] = im->regs[r].init_value;
+    analyse(h);
+    FX_CUDA(h, cudaMalloc(&h->d_wb, sizeof(uint32_t) * std::max<size_t>(1, h->wb.size())));
+    if (!h->wb.empty()) FX_CUDA(h, cudaMemcpy(h->d_wb, h->wb.data(), sizeof(uint32_t) * h->wb.size(), cudaMemcpyHostToDevice));
+    FX_CUDA(h, cudaDeviceSynchronize());
+    h->encode_dirty = true;
+    h->loaded = true;
+    return FX8010_OK;
+}
+
+#define FX_NEED_PROGRAM(h)                                                                  \
+    if (!h) return FX8010_ERR_ARG;                                                         \
+    if (!h->loaded) return fail(h, FX8010_ERR_NO_PROGRAM, "no program loaded (SURVEY U10)"); \
+    FX_CUDA(h, cudaSetDevice(h->device));
+
+int fx8010_gpu_set_controls(fx8010_gpu* h, int reg, const float* values, int broadcast) {
+    FX_NEED_PROGRAM(h);
+    if (!values || reg < 0 || reg >= (int)h->regs.size()) return fail(h, FX8010_ERR_ARG, "bad register index or NULL values");
+    const int rc = sync_all(h);
+    if (rc) return rc;
+    float* dst = h->d_gpr + (size_t)reg * h->N;
+    if (broadcast) {
+        fx_fill_kernel<<<(h->N + 255) / 256, 256>>>(dst, values[0], h->N);
+        h->info.kernel_launches++;
+        FX_CUDA(h, cudaGetLastError());
+        FX_CUDA(h, cudaStreamSynchronize(nullptr));
+        h->reg_uniform[reg] = 1; h->reg_value[reg] = values[0];
+    } else {
+        FX_CUDA(h, cudaMemcpy(dst, values, sizeof(float) * h->N, cudaMemcpyHostToDevice));
+        h->reg_uniform[reg] = 0;
+    }
+    h->encode_dirty = true;
+    return FX8010_OK;
+}
+
+int fx8010_gpu_set_controls_device(fx8010_gpu* h, int reg, const float* d_values, void* stream) {
+    FX_NEED_PROGRAM(h);
+    if (!d_values || reg < 0 || reg >= (int)h->regs.size()) return fail(h, FX8010_ERR_ARG, "bad register index or NULL values");
+    cudaStream_t st = (cudaStream_t)stream;
+    FX_CUDA(h, cudaMemcpyAsync(h->d_gpr + (size_t)reg * h->N, d_values, sizeof(float) * h->N, cudaMemcpyDeviceToDevice, st));
+    h->reg_uniform[reg] = 0;
+    h->encode_dirty = true;
+    h->last_stream = st;
+    return FX8010_OK;
+}
+
+int fx8010_gpu_get_register(fx8010_gpu* h, int reg, float* out) {
+    FX_NEED_PROGRAM(h);
+    if (!out || reg < 0 || reg >= (int)h->regs.size()) return fail(h, FX8010_ERR_ARG, "bad register index or NULL out");
+    const int rc = sync_all(h);
+    if (rc) return rc;
+    FX_CUDA(h, cudaMemcpy(out, h->d_gpr + (size_t)reg * h->N, sizeof(float) * h->N, cudaMemcpyDeviceToHost));
+    return FX8010_OK;
+}
+
+int fx8010_gpu_process_batch(fx8010_gpu* h, const float* d_in, float* d_out, int n_samples, void* stream) {
+    FX_NEED_PROGRAM(h);
+    if (!d_out || n_samples < 0) return fail(h, FX8010_ERR_ARG, "d_out is NULL or n_samples negative");
+    const size_t cs = (size_t)n_samples * h->N;
+    return launch_block(h, d_in, d_out, cs, cs, n_samples, (cudaStream_t)stream);
+}
+
+int fx8010_gpu_process_batch_host(fx8010_gpu* h, const float* in, float* out, int n_samples) {
+    FX_NEED_PROGRAM(h);
+    if (!out || n_samples < 0) return fail(h, FX8010_ERR_ARG, "out is NULL or n_samples negative");
+    if (n_samples == 0) return FX8010_OK;
+    const size_t N = (size_t)h->N, C = (size_t)h->C;
+    // sub-block: ~8 MiB of samples per channel set, a multiple of the cp.async chunk
+    long sub = h->tune_sub ? h->tune_sub : (long)((8u << 20) / (4 * N * C));
+    sub = std::max<long>(CHUNK, sub / CHUNK * CHUNK);
+    sub = std::min<long>(sub, n_samples);
+    const size_t need = C * (size_t)sub * N;
+    if (need > h->stage_floats) {
+        const int rc = sync_all(h);
+        if (rc) return rc;
+        for (int i = 0; i < HOST_PIPE_BUFS; ++i) {
+            cudaFree(h->d_stage_in[i]); cudaFree(h->d_stage_out[i]);
+            h->d_stage_in[i] = h->d_stage_out[i] = nullptr;
+        }
+        h->stage_floats = 0;
+        for (int i = 0; i < HOST_PIPE_BUFS; ++i) {
+            FX_CUDA(h, cudaMalloc(&h->d_stage_in[i], sizeof(float) * need));
+            FX_CUDA(h, cudaMalloc(&h->d_stage_out[i], sizeof(float) * need));
+        }
+        h->stage_floats = need;
+    }
+    if (h->last_stream) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));   // earlier device-side batches come first
+    int b = 0;
+    for (long s0 = 0; s0 < n_samples; s0 += sub, ++b) {
+        const int buf = b % HOST_PIPE_BUFS;
+        const long len = std::min<long>(sub, n_samples - s0);
+        if (b >= HOST_PIPE_BUFS) FX_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_comp[buf], 0));     // stage_in[buf] consumed
+        if (in)
+            for (size_t c = 0; c < C; ++c)
+                FX_CUDA(h, cudaMemcpyAsync(h->d_stage_in[buf] + c * (size_t)sub * N, in + (c * (size_t)n_samples + s0) * N,
+                                           sizeof(float) * len * N, cudaMemcpyHostToDevice, h->s_h2d));
+        FX_CUDA(h, cudaEventRecord(h->ev_h2d[buf], h->s_h2d));
+        FX_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_h2d[buf], 0));
+        if (b >= HOST_PIPE_BUFS) FX_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_d2h[buf], 0));    // stage_out[buf] drained
+        const cudaStream_t keep = h->last_stream;
+        const int rc = launch_block(h, in ? h->d_stage_in[buf] : nullptr, h->d_stage_out[buf], (size_t)sub * N, (size_t)sub * N, (int)len, h->s_comp);
+        h->last_stream = keep;
+        if (rc) return rc;
+        FX_CUDA(h, cudaEventRecord(h->ev_comp[buf], h->s_comp));
+        FX_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[buf], 0));
+        for (size_t c = 0; c < C; ++c)
+            FX_CUDA(h, cudaMemcpyAsync(out + (c * (size_t)n_samples + s0) * N, h->d_stage_out[buf] + c * (size_t)sub * N,
+                                       sizeof(float) * len * N, cudaMemcpyDeviceToHost, h->s_d2h));
+        FX_CUDA(h, cudaEventRecord(h->ev_d2h[buf], h->s_d2h));
+    }
+    FX_CUDA(h, cudaStreamSynchronize(h->s_d2h));
+    return FX8010_OK;
+}
+
+int fx8010_gpu_synchronize(fx8010_gpu* h, void* stream) {
+    if (!h) return FX8010_ERR_ARG;
+    FX_CUDA(h, cudaSetDevice(h->device));
+    if (stream) FX_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+    return sync_all(h);
+}
+
+void* fx8010_gpu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void fx8010_gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int fx8010_gpu_get_instruction_counts(fx8010_gpu* h, unsigned long long* out) {
+    FX_NEED_PROGRAM(h);
+    if (!out) return fail(h, FX8010_ERR_ARG, "out is NULL");
+    const int rc = sync_all(h);
+    if (rc) return rc;
+    FX_CUDA(h, cudaMemcpy(out, h->d_counts, sizeof(unsigned long long) * h->N, cudaMemcpyDeviceToHost));
+    return FX8010_OK;
+}
+
+int fx8010_gpu_get_instruction_count(fx8010_gpu* h, unsigned long long* total) {
+    FX_NEED_PROGRAM(h);
+    if (!total) return fail(h, FX8010_ERR_ARG, "total is NULL");
+    std::vector<unsigned long long> c(h->N);
+    const int rc = fx8010_gpu_get_instruction_counts(h, c.data());
+    if (rc) return rc;
+    unsigned long long s = 0;
+    for (unsigned long long v : c) s += v;
+    *total = s;
+    return FX8010_OK;
+}
+
+int fx8010_gpu_get_dims(fx8010_gpu* h, fx8010_state_dims* out) {
+    if (!h || !out) return FX8010_ERR_ARG;
+    out->n_instances = h->N; out->n_channels = h->C;
+    out->n_regs = (int)h->regs.size(); out->n_instrs = (int)h->instrs.size();
+    out->itram_size = h->itram_size; out->xtram_size = h->xtram_size;
+    out->itram_alloc = h->itram_size; out->xtram_alloc = h->xtram_size;
+    return FX8010_OK;
+}
+
+int fx8010_gpu_get_registers(fx8010_gpu* h, float* out) {
+    FX_NEED_PROGRAM(h);
+    if (!out) return fail(h, FX8010_ERR_ARG, "out is NULL");
+    const int rc = sync_all(h);
+    if (rc) return rc;
+    FX_CUDA(h, cudaMemcpy(out, h->d_gpr, sizeof(float) * h->regs.size() * h->N, cudaMemcpyDeviceToHost));
+    return FX8010_OK;
+}
+
+int fx8010_gpu_set_registers(fx8010_gpu* h, const float* in) {
+    FX_NEED_PROGRAM(h);
+    if (!in) return fail(h, FX8010_ERR_ARG, "in is NULL");
+    const int rc = sync_all(h);
+    if (rc) return rc;
+    FX_CUDA(h, cudaMemcpy(h->d_gpr, in, sizeof(float) * h->regs.size() * h->N, cudaMemcpyHostToDevice));
+    std::fill(h->reg_uniform.begin(), h->reg_uniform.end(), 0);
+    h->encode_dirty = true;
+    return FX8010_OK;
+}
+
+int fx8010_gpu_get_scalars(fx8010_gpu* h, double* acc, uint32_t* lfsr, float* out_latch, int32_t* tram_ptrs) {
+    FX_NEED_PROGRAM(h);
+    const int rc = sync_all(h);
+    if (rc) return rc;
+    const size_t N = (size_t)h->N;
+    if (acc) FX_CUDA(h, cudaMemcpy(acc, h->d_acc, sizeof(double) * N, cudaMemcpyDeviceToHost));
+    if (lfsr) FX_CUDA(h, cudaMemcpy(lfsr, h->d_lfsr, sizeof(uint32_t) * 2 * N, cudaMemcpyDeviceToHost));
+    if (out_latch) FX_CUDA(h, cudaMemcpy(out_latch, h->d_latch, sizeof(float) * h->C * N, cudaMemcpyDeviceToHost));
+    if (tram_ptrs) FX_CUDA(h, cudaMemcpy(tram_ptrs, h->d_ptrs, sizeof(int32_t) * 4 * N, cudaMemcpyDeviceToHost));
+    return FX8010_OK;
+}
+
+int fx8010_gpu_set_scalars(fx8010_gpu* h, const double* acc, const uint32_t* lfsr, const float* out_latch, const int32_t* tram_ptrs) {
+    FX_NEED_PROGRAM(h);
+    const int rc = sync_all(h);
+    if (rc) return rc;
+    const size_t N = (size_t)h->N;
+    if (tram_ptrs) {                                  // pointers index the rings: keep them inside
+        const int sizes[4] = {h->itram_size, h->itram_size, h->xtram_size, h->xtram_size};
+        for (int q = 0; q < 4; ++q)
+            for (size_t i = 0; i < N; ++i) {
+                const int32_t v = tram_ptrs[q * N + i];
+                if (v < 0 || (sizes[q] > 0 && v >= sizes[q]) || (sizes[q] == 0 && v != 0))
+                    return fail(h, FX8010_ERR_ARG, "TRAM pointer outside its ring");
+            }
+    }
+    if (acc) FX_CUDA(h, cudaMemcpy(h->d_acc, acc, sizeof(double) * N, cudaMemcpyHostToDevice));
+    if (lfsr) FX_CUDA(h, cudaMemcpy(h->d_lfsr, lfsr, sizeof(uint32_t) * 2 * N, cudaMemcpyHostToDevice));
+    if (out_latch) FX_CUDA(h, cudaMemcpy(h->d_latch, out_latch, sizeof(float) * h->C * N, cudaMemcpyHostToDevice));
+    if (tram_ptrs) FX_CUDA(h, cudaMemcpy(h->d_ptrs, tram_ptrs, sizeof(int32_t) * 4 * N, cudaMemcpyHostToDevice));
+    return FX8010_OK;
+}
+
+int fx8010_gpu_get_tram(fx8010_gpu* h, int which, int instance, float* out) {
+    FX_NEED_PROGRAM(h);
+    const int size = which == 0 ? h->itram_size : h->xtram_size;
+    const float* ring = which == 0 ? h->d_itram : h->d_xtram;
+    if (!out || (which != 0 && which != 1) || instance < 0 || instance >= h->N || !ring) return fail(h, FX8010_ERR_ARG, "bad TRAM selector / instance, or that TRAM is unused");
+    const int rc = sync_all(h);
+    if (rc) return rc;
+    FX_CUDA(h, cudaMemcpy2D(out, sizeof(float), ring + instance, sizeof(float) * h->N, sizeof(float), size, cudaMemcpyDeviceToHost));
+    return FX8010_OK;
+}
+
+int fx8010_gpu_set_tram(fx8010_gpu* h, int which, int instance, const float* in) {
+    FX_NEED_PROGRAM(h);
+    const int size = which == 0 ? h->itram_size : h->xtram_size;
+    float* ring = which == 0 ? h->d_itram : h->d_xtram;
+    if (!in || (which != 0 && which != 1) || instance < 0 || instance >= h->N || !ring) return fail(h, FX8010_ERR_ARG, "bad TRAM selector / instance, or that TRAM is unused");
+    const int rc = sync_all(h);
+    if (rc) return rc;
+    FX_CUDA(h, cudaMemcpy2D(ring + instance, sizeof(float) * h->N, in, sizeof(float), sizeof(float), size, cudaMemcpyHostToDevice));
+    return FX8010_OK;
+}
+
+int fx8010_gpu_get_runtime_flags(fx8010_gpu* h, unsigned int* flags, int clear) {
+    if (!h || !flags) return FX8010_ERR_ARG;
+    FX_CUDA(h, cudaSetDevice(h->device));
+    const int rc = sync_all(h);
+    if (rc) return rc;
+    FX_CUDA(h, cudaMemcpy(flags, h->d_flags, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    if (clear) FX_CUDA(h, cudaMemset(h->d_flags, 0, sizeof(unsigned int)));
+    return FX8010_OK;
+}
+
+const char* fx8010_gpu_last_error(fx8010_gpu* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int fx8010_gpu_get_launch_info(fx8010_gpu* h, fx8010_launch_info* out) {
+    if (!h || !out) return FX8010_ERR_ARG;
+    *out = h->info;
+    return FX8010_OK;
+}
+
+}  // extern "C"

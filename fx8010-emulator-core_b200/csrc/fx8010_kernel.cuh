@@ -1,0 +1,495 @@
+// fx8010_kernel.cuh — the batched FX8010 interpreter kernel (sm_100a).
+//
+// One thread runs K emulated DSP instances ("contexts", K = 1, 2 or 4 ADJACENT instances) over one
+// time segment.  The decoded program sits in __constant__ memory; the program counter is
+// warp-uniform, so fetch, decode and the opcode switch run once per thread for K contexts and
+// every lane executes the same DSP instruction on its own instances.  Data-dependent SKIP never
+// diverges: a per-context skip counter turns into a write predicate.  The GPR file is a
+// structure-of-arrays tile in shared memory (gpr[reg][thread][K], one 4/8/16-byte access per
+// operand, bank-conflict free); accumulator, LFSR, TRAM pointers and counters live in hardware
+// registers.  Sample blocks stream HBM -> shared through double-buffered cp.async stages (one
+// 16-byte LDGSTS per thread and sample at K = 4) and go back with coalesced 16-byte stores.
+//
+// Semantics follow the reference's FX8010::process (reference source/FX8010.cpp:1023-1249) op by
+// op; every float/double operation uses an explicitly rounded intrinsic so nothing can be
+// contracted into an FMA.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fx8010_gpu.h"
+
+namespace fxk {
+
+// ---- micro-ops: the reference opcodes with IDELAY/XDELAY resolved by the type of R -----------
+enum Uop : uint32_t {
+    U_MACS = 0, U_MACSN, U_MACW, U_MACWN, U_MACINTW, U_ACC3, U_MACMV, U_ANDXOR, U_TSTNEG, U_LIMIT,
+    U_LIMITN, U_LOG, U_EXP, U_INTERP, U_SKIP, U_IREAD, U_IWRITE, U_XREAD, U_XWRITE, U_NOP, U_END
+};
+
+// flag bits (word0 bits 8..15)
+constexpr uint32_t F_PRE_A = 1u << 8;    // A <- in[in_ch]   (source/FX8010.cpp:1055)
+constexpr uint32_t F_PRE_X = 1u << 9;    // X <- in[in_ch]   (:1057, uses A's IOIndex)
+constexpr uint32_t F_PRE_Y = 1u << 10;   // Y <- in[in_ch]   (:1059)
+constexpr uint32_t F_NOISE = 1u << 11;   // reg[aux] <- whitenoise()  (:1063-1071)
+constexpr uint32_t F_OUT = 1u << 12;     // latch[out_ch] <- R after the instruction (:1229-1233)
+constexpr uint32_t F_CCR = 1u << 13;     // CCR value is observable: materialise it (:211-232)
+constexpr uint32_t F_TAB_SMEM = 1u << 14; // LOG/EXP: literal selector, table staged in shared memory (aux = slot)
+constexpr uint32_t F_TAB_IMM = 1u << 15;  // LOG/EXP: literal selector, table in global memory (aux = op*32+sel)
+constexpr uint32_t F_PRE_ANY = F_PRE_A | F_PRE_X | F_PRE_Y;
+
+// 16-byte decoded instruction:
+//   w0: uop[0:8) flags[8:16) in_ch[16:24) out_ch[24:32)
+//   w1: r | a << 16        w2: x | y << 16        w3: aux (noise target register / table slot)
+constexpr int MAX_INSTR = FX8010_MAX_INSTRUCTIONS;
+constexpr int PROG_SLOTS = 3;            // live programs per device (one slot per handle)
+__constant__ uint4 c_prog[PROG_SLOTS][MAX_INSTR + 1];
+
+constexpr int CHUNK = 8;                 // samples per cp.async stage
+constexpr int MAX_SMEM_TABLES = 2;       // LOG/EXP tables replicated into shared memory
+constexpr int TAB_REPL = 8;              // replicas: one per lane of a 128-bit access phase
+constexpr int TAB_SMEM_BYTES = FX8010_TABLE_ENTRIES * TAB_REPL * 16;   // 8 KiB per table
+
+struct __align__(16) TableEntry { double y1, slope; }; // T[i], (T[i+1]-T[i])/(x2-x1) — host-computed in IEEE double
+
+struct Params {
+    // per-instance state, all [..][N]
+    float* gpr;                 // [n_regs][N]
+    double* acc;                // [N]
+    uint32_t* lfsr;             // [2][N]
+    float* latch;               // [C][N]
+    int32_t* ptrs;              // [4][N]  iw, ir, xw, xr
+    float* itram;               // [itram_size][N]
+    float* xtram;               // [xtram_size][N]
+    unsigned long long* counts; // [N]
+    unsigned int* rt_flags;     // 1 word
+    const uint32_t* wb_regs;    // registers the program may write (write-back list)
+    const TableEntry* tabs;     // [2][32][64]  LOG then EXP
+    // I/O
+    const float* in;            // element (c, s, i) at in[c * in_cstride + s * N + i]
+    float* out;                 // element (c, s, i) at out[c * out_cstride + s * N + i]
+    size_t in_cstride, out_cstride;
+    int n_samples;              // S of this call
+    int seg_len;                // samples per time segment (== S when serial)
+    int n_seg;
+    // geometry
+    int N, C, n_regs, n_instrs, n_wb, slot;
+    int itram_size, xtram_size;
+    int n_smem_tabs;            // tables staged in shared memory
+    int smem_tab_id[MAX_SMEM_TABLES];   // op*32 + selector
+};
+
+// ---- K-wide context vectors -------------------------------------------------------------------
+template <int K> struct VT;
+template <> struct VT<1> { using T = float; };
+template <> struct VT<2> { using T = float2; };
+template <> struct VT<4> { using T = float4; };
+
+template <int K> struct Vec {
+    float v[K];
+    __device__ __forceinline__ float& operator[](int i) { return v[i]; }
+    __device__ __forceinline__ const float& operator[](int i) const { return v[i]; }
+};
+template <int K> __device__ __forceinline__ Vec<K> vload(const float* p) {
+    Vec<K> r;
+    const typename VT<K>::T t = *reinterpret_cast<const typename VT<K>::T*>(p);
+    __builtin_memcpy(&r, &t, sizeof(t));
+    return r;
+}
+template <int K> __device__ __forceinline__ void vstore(float* p, const Vec<K>& r) {
+    typename VT<K>::T t;
+    __builtin_memcpy(&t, &r, sizeof(t));
+    *reinterpret_cast<typename VT<K>::T*>(p) = t;
+}
+
+// ---- exact scalar semantics ----------------------------------------------------------------
+
+// static_cast<int32_t>(float) on x86-64 (cvttss2si): NaN / out of range -> 0x80000000
+__device__ __forceinline__ int32_t cvt_x86(float f) {
+    const int32_t i = __float2int_rz(f);        // saturating, NaN -> 0
+    return (f < 2147483648.0f) ? i : INT32_MIN; // fixes +overflow and NaN; -overflow saturates to INT_MIN already
+}
+// saturate(): source/FX8010.cpp:275-279 (NaN passes through)
+__device__ __forceinline__ float sat1(float v) { return (v >= 1.0f) ? 1.0f : ((v <= -1.0f) ? -1.0f : v); }
+// setCCR(): source/FX8010.cpp:211-232
+__device__ __forceinline__ float ccr_of(float r) {
+    const float ar = fabsf(r);
+    const float c = (ar < 1.0f) ? ((r < 0.0f) ? 6.0f : 2.0f) : ((ar == 1.0f) ? ((r < 0.0f) ? 20.0f : 16.0f) : 0.0f);
+    return (r == 0.0f) ? 8.0f : c;
+}
+// wrapAround() value path: source/FX8010.cpp:299-328
+__device__ __forceinline__ float wrap1(float v) {
+    return (v >= 1.0f) ? __fadd_rn(v, -2.0f) : ((v < -1.0f) ? __fadd_rn(v, 2.0f) : v);
+}
+// logicOps(): source/FX8010.cpp:330-360 (first matching rule wins; written last-to-first)
+__device__ __forceinline__ int32_t logic_ops(float fa, float fx, float fy) {
+    const int32_t A = cvt_x86(fa), X = cvt_x86(fx), Y = cvt_x86(fy);
+    int32_t r = (A & X) ^ Y;
+    if (Y == 0xFFFFFF) r = ~A & X;
+    if (Y == ~X) r = A | Y;
+    if (X == 0xFFFFFFF && Y == 0xFFFFFF) r = ~A;
+    if (X == 0xFFFFFF) r = A ^ Y;
+    if (Y == 0) r = A & X;
+    return r;
+}
+
+// linearInterpolate() index: static_cast<int>((x - x_min) / step), source/FX8010.cpp:285-286.
+// (x + 1.0) * 31.5 in double gives the same integer as (x + 1.0) / (2.0/63) for every binary32 x in
+// [-1, 1] (exhaustively checked, tests/test_oracle.py::test_table_index_formula and the GPU sweep);
+// outside it only the clamp matters.  cvttsd2si overflow / NaN -> INT_MIN -> clamped to 0 (rule U6).
+__device__ __forceinline__ int table_index(double xd) {
+    const double q = __dmul_rn(__dadd_rn(xd, 1.0), 31.5);
+    int i = __double2int_rz(q);
+    i = min(max(i, 0), FX8010_TABLE_ENTRIES - 1);
+    return (q < 2147483648.0) ? i : 0;
+}
+// y = (y2 - y1) / (x2 - x1) * (x - x1) + y1 with the quotient precomputed on the host (:287-293)
+__device__ __forceinline__ float table_finish(double xd, int i, double y1, double slope) {
+    const double step = 2.0 / 63.0;
+    const double x1 = __dadd_rn(-1.0, __dmul_rn((double)i, step));
+    return __double2float_rn(__dadd_rn(__dmul_rn(slope, __dsub_rn(xd, x1)), y1));
+}
+
+__device__ __forceinline__ void cp_async_bytes(void* smem, const void* gmem, int bytes_tag) {}
+template <int BYTES> __device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Shared-memory bytes one block needs (host and device agree through this one formula).
+__host__ __device__ inline size_t smem_bytes(int n_regs, int C, int B, int K, int n_smem_tabs) {
+    return (size_t)n_smem_tabs * TAB_SMEM_BYTES +
+           (size_t)B * K * sizeof(float) * ((size_t)n_regs + C + 2 * (size_t)C * CHUNK);
+}
+
+// ---- the kernel ------------------------------------------------------------------------------
+//
+// grid = (ceil(N / (K * B)), n_seg), block = B threads.
+//   SKIP: the program contains SKIP (per-context predicate, extra passes when END is skipped)
+//   EXT : the program uses TRAM, the noise LFSR or MACMV (their state stays out of the registers
+//         of simpler programs)
+template <int K, bool SKIP, bool EXT>
+__global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int B = blockDim.x;
+    const int tid = threadIdx.x;
+    const int N = p.N, C = p.C;
+    const int tslot_raw = blockIdx.x * B + tid;
+    const bool valid = tslot_raw * K < N;
+    const int inst0 = valid ? tslot_raw * K : N - K;       // N % K == 0 (host guarantees it)
+    const int seg = blockIdx.y;
+    const bool last_seg = (seg == p.n_seg - 1);
+    const int s_begin = seg * p.seg_len;
+    const int s_end = min(p.n_samples, s_begin + p.seg_len);
+    const uint4* const prog = c_prog[p.slot];
+
+    // shared-memory carve-up
+    TableEntry* const s_tab = reinterpret_cast<TableEntry*>(smem_raw);                 // [n_smem_tabs][64][TAB_REPL]
+    float* const gpr = reinterpret_cast<float*>(smem_raw + (size_t)p.n_smem_tabs * TAB_SMEM_BYTES); // [n_regs][B][K]
+    float* const latch = gpr + (size_t)p.n_regs * B * K;                               // [C][B][K]
+    float* const in_stage = latch + (size_t)C * B * K;                                 // [2][C][CHUNK][B][K]
+    const int RS = B * K;                                                              // register stride (floats)
+
+    // prefetch the first input chunk while the state loads
+    const bool has_in = (p.in != nullptr);
+    auto stage_inputs = [&](int buf, int s0) {
+        if (has_in) {
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int k = 0; k < CHUNK; ++k) {
+                    const int s = min(s0 + k, p.n_samples - 1);
+                    cp_async<4 * K>(&in_stage[(((size_t)(buf * C + c) * CHUNK + k) * B + tid) * K],
+                                    &p.in[(size_t)c * p.in_cstride + (size_t)s * N + inst0]);
+                }
+        }
+        cp_async_commit();
+    };
+    stage_inputs(0, s_begin);
+
+    // literal-selector LOG/EXP tables -> shared, replicated so that lane (l & 7) of a 128-bit access
+    // phase always reads bank group (l & 7): entry e of replica q lives at slot e * TAB_REPL + q.
+    for (int t = 0; t < p.n_smem_tabs; ++t) {
+        const TableEntry* src = p.tabs + (size_t)p.smem_tab_id[t] * FX8010_TABLE_ENTRIES;
+        for (int i = tid; i < FX8010_TABLE_ENTRIES * TAB_REPL; i += B)
+            s_tab[t * FX8010_TABLE_ENTRIES * TAB_REPL + i] = src[i / TAB_REPL];
+    }
+
+    float* const g = gpr + tid * K;                      // this thread's column: register r at g[r * RS]
+    for (int r = 0; r < p.n_regs; ++r) vstore<K>(g + r * RS, vload<K>(p.gpr + (size_t)r * N + inst0));
+    float* const lt = latch + tid * K;
+    for (int c = 0; c < C; ++c) vstore<K>(lt + c * RS, vload<K>(p.latch + (size_t)c * N + inst0));
+
+    float acc_f[K];
+    double acc_d[K];
+    bool acc_is_f[K];                 // the accumulator currently holds the float acc_f (else acc_d)
+    int skip[K];
+    unsigned int count[K];
+    uint32_t g1[K], g2[K];
+    int32_t iw[K], ir[K], xw[K], xr[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        acc_d[k] = p.acc[inst0 + k]; acc_f[k] = 0.0f; acc_is_f[k] = false;
+        skip[k] = 0; count[k] = 0;
+        if (EXT) {
+            g1[k] = p.lfsr[inst0 + k]; g2[k] = p.lfsr[N + inst0 + k];
+            iw[k] = p.ptrs[inst0 + k]; ir[k] = p.ptrs[N + inst0 + k];
+            xw[k] = p.ptrs[2 * N + inst0 + k]; xr[k] = p.ptrs[3 * N + inst0 + k];
+        }
+    }
+    unsigned int flags = 0;
+    __syncthreads();                  // s_tab visible (the only block-wide dependency)
+
+    const int lane_rep = tid & (TAB_REPL - 1);
+    int buf = 0;
+    for (int s0 = s_begin; s0 < s_end; s0 += CHUNK) {
+        if (s0 + CHUNK < s_end) { stage_inputs(buf ^ 1, s0 + CHUNK); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        const float* const stage = in_stage + (size_t)buf * C * CHUNK * RS + tid * K;
+        const int kn = min(CHUNK, s_end - s0);
+        for (int ks = 0; ks < kn; ++ks) {
+            // ---- one sample period: FX8010::process, source/FX8010.cpp:1023-1249 ----
+            // The final CCR must be in the register file when the batch ends (getRegisterValue("ccr")).
+            const bool force_ccr = (s0 + ks == p.n_samples - 1);
+            bool saw_end[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) { skip[k] = 0; saw_end[k] = false; }
+            int pass = 0;
+            do {
+                uint4 wn = prog[0];
+                for (int pc = 0; pc < p.n_instrs; ++pc) {
+                    const uint4 w = wn;
+                    wn = prog[pc + 1];                                // slot is padded with one extra word
+                    const uint32_t uop = w.x & 0xffu;
+                    bool act[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        if (SKIP) {                                   // :1037 / :1235-1241
+                            act[k] = (skip[k] == 0);
+                            skip[k] = (skip[k] > 0) ? skip[k] - 1 : 0; // a negative count skips exactly one
+                        } else act[k] = true;
+                    }
+                    float* const pr = g + (w.y & 0xffffu) * RS;
+                    float* const pa = g + (w.y >> 16) * RS;
+                    float* const px = g + (w.z & 0xffffu) * RS;
+                    float* const py = g + (w.z >> 16) * RS;
+                    if (w.x & F_PRE_ANY) {                            // :1053-1061
+                        Vec<K> v;
+                        if (has_in) v = vload<K>(stage + (size_t)(((w.x >> 16) & 0xffu) * CHUNK + ks) * RS);
+                        else {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) v[k] = 0.0f;
+                        }
+                        if (!SKIP) {
+                            if (w.x & F_PRE_A) vstore<K>(pa, v);
+                            if (w.x & F_PRE_X) vstore<K>(px, v);
+                            if (w.x & F_PRE_Y) vstore<K>(py, v);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; ++k)
+                                if (act[k]) {
+                                    if (w.x & F_PRE_A) pa[k] = v[k];
+                                    if (w.x & F_PRE_X) px[k] = v[k];
+                                    if (w.x & F_PRE_Y) py[k] = v[k];
+                                }
+                        }
+                    }
+                    if (EXT && (w.x & F_NOISE)) {                     // :1063-1071, whitenoise :993-1000
+                        float* const pn = g + (w.w & 0xffffu) * RS;
+#pragma unroll
+                        for (int k = 0; k < K; ++k)
+                            if (act[k]) {
+                                g1[k] ^= g2[k];
+                                pn[k] = __fmul_rn(__int2float_rn((int32_t)g2[k]), 4.656612873077392578125e-10f);
+                                g2[k] += g1[k];
+                            }
+                    }
+                    Vec<K> r;
+                    bool writes_r = true;
+#define FX_LOAD_A const Vec<K> a = vload<K>(pa)
+#define FX_LOAD_X const Vec<K> x = vload<K>(px)
+#define FX_LOAD_Y const Vec<K> y = vload<K>(py)
+#define FX_EACH _Pragma("unroll") for (int k = 0; k < K; ++k)
+#define FX_ACC(val) { if (act[k]) { acc_f[k] = (val); acc_is_f[k] = true; } }
+                    switch (uop) {
+                    case U_MACS: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;   // :1077-1085 (MACINTS :1095-1103 is identical)
+                        FX_EACH { const float t = __fadd_rn(a[k], __fmul_rn(x[k], y[k])); FX_ACC(t); r[k] = sat1(t); } break; }
+                    case U_MACSN: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;  // :1086-1094
+                        FX_EACH { const float t = __fsub_rn(a[k], __fmul_rn(x[k], y[k])); FX_ACC(t); r[k] = sat1(t); } break; }
+                    case U_ACC3: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;   // :1104-1112
+                        FX_EACH { const float t = __fadd_rn(__fadd_rn(a[k], x[k]), y[k]); FX_ACC(t); r[k] = sat1(t); } break; }
+                    case U_MACW: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;   // :1126-1131
+                        FX_EACH { r[k] = __fadd_rn(a[k], wrap1(__fmul_rn(x[k], y[k]))); FX_ACC(r[k]); } break; }
+                    case U_MACWN: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;  // :1132-1137
+                        FX_EACH { r[k] = __fsub_rn(a[k], wrap1(__fmul_rn(x[k], y[k]))); FX_ACC(r[k]); } break; }
+                    case U_MACINTW: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y; // :1138-1143
+                        FX_EACH { r[k] = wrap1(__fadd_rn(a[k], __fmul_rn(x[k], y[k]))); FX_ACC(r[k]); } break; }
+                    case U_MACMV: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;  // :1144-1149
+                        FX_EACH {
+                            if (EXT && act[k]) {
+                                const double base = acc_is_f[k] ? (double)acc_f[k] : acc_d[k];
+                                acc_d[k] = __dadd_rn(base, (double)__fmul_rn(x[k], y[k]));
+                                acc_is_f[k] = false;
+                            }
+                            r[k] = a[k];
+                        } break; }
+                    case U_ANDXOR: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y; // :1150-1154 (accumulator untouched)
+                        FX_EACH { r[k] = __int2float_rn(logic_ops(a[k], x[k], y[k])); } break; }
+                    case U_TSTNEG: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y; // :1155-1162
+                        FX_EACH {
+                            const int32_t q = cvt_x86(__fmul_rn(x[k], 2147483648.0f));
+                            r[k] = (a[k] >= y[k]) ? x[k] : __fmul_rn(__int2float_rn(~q), 4.656612873077392578125e-10f);
+                            FX_ACC(r[k]);
+                        } break; }
+                    case U_LIMIT: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;  // :1163-1168
+                        FX_EACH { r[k] = (a[k] >= y[k]) ? x[k] : y[k]; FX_ACC(r[k]); } break; }
+                    case U_LIMITN: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y; // :1169-1174
+                        FX_EACH { r[k] = (a[k] < y[k]) ? x[k] : y[k]; FX_ACC(r[k]); } break; }
+                    case U_LOG:                                       // :1113-1119
+                    case U_EXP: { FX_LOAD_A;                          // :1120-1125, linearInterpolate :283-296
+                        if (w.x & F_TAB_SMEM) {
+                            const TableEntry* const tb = s_tab + (size_t)(w.w & 0xffu) * (FX8010_TABLE_ENTRIES * TAB_REPL) + lane_rep;
+                            FX_EACH {
+                                if (!(a[k] >= -1.0f && a[k] <= 1.0f) && act[k]) flags |= FX8010_RT_TABLE_RANGE;
+                                const double xd = (double)a[k];
+                                const int i = table_index(xd);
+                                const TableEntry e = tb[i * TAB_REPL];
+                                r[k] = table_finish(xd, i, e.y1, e.slope); FX_ACC(r[k]);
+                            }
+                        } else {
+                            Vec<K> x;
+                            if (!(w.x & F_TAB_IMM)) x = vload<K>(px);
+                            FX_EACH {
+                                int tsel;
+                                if (w.x & F_TAB_IMM) tsel = (int)(w.w & 0xffu);
+                                else {
+                                    int32_t sel = cvt_x86(x[k]);
+                                    if (sel < 0 || sel > FX8010_TABLE_COUNT - 1) {
+                                        if (act[k]) flags |= FX8010_RT_TABLE_RANGE;
+                                        sel = sel < 0 ? 0 : FX8010_TABLE_COUNT - 1;
+                                    }
+                                    tsel = (uop == U_EXP ? FX8010_TABLE_COUNT : 0) + sel;
+                                }
+                                if (!(a[k] >= -1.0f && a[k] <= 1.0f) && act[k]) flags |= FX8010_RT_TABLE_RANGE;
+                                const double xd = (double)a[k];
+                                const int i = table_index(xd);
+                                const double2 e = __ldg(reinterpret_cast<const double2*>(p.tabs + tsel * FX8010_TABLE_ENTRIES + i));
+                                r[k] = table_finish(xd, i, e.x, e.y); FX_ACC(r[k]);
+                            }
+                        }
+                        break; }
+                    case U_INTERP: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y; // :1180-1187
+                        FX_EACH {
+                            const double d = __dadd_rn(__dmul_rn(__dsub_rn(1.0, (double)x[k]), (double)a[k]), (double)__fmul_rn(x[k], y[k]));
+                            const float t = __double2float_rn(d); FX_ACC(t); r[k] = sat1(t);
+                        } break; }
+                    case U_SKIP:                                      // :1175-1179
+                        if (SKIP) { FX_LOAD_X; FX_LOAD_Y; const Vec<K> c = vload<K>(g);
+                            FX_EACH { if (act[k] && __int2float_rn(cvt_x86(x[k])) == c[k]) skip[k] = cvt_x86(y[k]); } }
+                        writes_r = false; break;
+                    case U_IREAD: case U_XREAD:                       // :1190-1193 / :1202-1205, readSmallDelay :934-956
+                        if (EXT) { FX_LOAD_Y;
+                            const bool isx = (uop == U_XREAD);
+                            const float* const ring = isx ? p.xtram : p.itram;
+                            const int size = isx ? p.xtram_size : p.itram_size;
+                            FX_EACH {
+                                int32_t& rp = isx ? xr[k] : ir[k];
+                                if (act[k]) {
+                                    const int pos = min(max(cvt_x86(y[k]), 0), size - 1);
+                                    int idx = rp - pos;
+                                    idx += (idx < 0) ? size : 0;      // rule U1: mathematical modulo
+                                    rp = (rp + 1 == size) ? 0 : rp + 1;
+                                    pa[k] = ring[(size_t)idx * N + inst0 + k];
+                                }
+                            } }
+                        writes_r = false; break;
+                    case U_IWRITE: case U_XWRITE:                     // :1195-1198 / :1207-1210, writeSmallDelay :909-917
+                        if (EXT) { FX_LOAD_A; FX_LOAD_Y;
+                            const bool isx = (uop == U_XWRITE);
+                            float* const ring = isx ? p.xtram : p.itram;
+                            const int size = isx ? p.xtram_size : p.itram_size;
+                            FX_EACH {
+                                int32_t& wp = isx ? xw[k] : iw[k];
+                                if (act[k]) {
+                                    const int pos = min(max(cvt_x86(y[k]), 0), size - 1);
+                                    const int idx = wp + pos;         // the reference does not wrap wp + pos: slots at or
+                                    if (idx < size && valid) ring[(size_t)idx * N + inst0 + k] = a[k]; // beyond the ring are never read back
+                                    wp = (wp + 1 == size) ? 0 : wp + 1;
+                                }
+                            } }
+                        writes_r = false; break;
+                    case U_END:                                       // :1212-1215
+                        FX_EACH { if (act[k]) saw_end[k] = true; }
+                        writes_r = false; break;
+                    default: writes_r = false; break;                 // U_NOP: IDELAY/XDELAY whose R is neither read nor write
+                    }
+#undef FX_LOAD_A
+#undef FX_LOAD_X
+#undef FX_LOAD_Y
+#undef FX_ACC
+                    if (writes_r) {
+                        if (!SKIP) vstore<K>(pr, r);
+                        else { FX_EACH { if (act[k]) pr[k] = r[k]; } }
+                        if ((w.x & F_CCR) || force_ccr) {             // setCCR :211-232 (after the R store: R may be ccr)
+                            if (!SKIP) { Vec<K> c; FX_EACH { c[k] = ccr_of(r[k]); } vstore<K>(g, c); }
+                            else { FX_EACH { if (act[k]) g[k] = ccr_of(r[k]); } }
+                        }
+                    }
+                    if (SKIP) { FX_EACH { count[k] += act[k] ? 1u : 0u; } }   // :1222
+                    if (w.x & F_OUT) {                                // :1229-1233 (after EVERY executed instruction)
+                        float* const pl = lt + (w.x >> 24) * RS;
+                        if (!SKIP) vstore<K>(pl, vload<K>(pr));
+                        else { FX_EACH { if (act[k]) pl[k] = pr[k]; } }
+                    }
+                }
+                ++pass;
+                if (!SKIP) break;
+                // END skipped by some context: run the program again (source/FX8010.cpp:1243); contexts
+                // that saw END idle through the extra pass via an "infinite" skip count.
+                bool again = false;
+                FX_EACH {
+                    const bool more = !saw_end[k] && pass < FX8010_MAX_PASSES;
+                    if (!saw_end[k] && pass >= FX8010_MAX_PASSES) flags |= FX8010_RT_END_SKIPPED_CAP;   // rule U9
+                    again |= more;
+                    if (!more) skip[k] = 0x7fffffff;
+                }
+                if (!__any_sync(0xffffffffu, again)) break;
+            } while (true);
+            if (valid)                                                // :1248 — coalesced, lane = K adjacent instances
+                for (int c = 0; c < C; ++c)
+                    vstore<K>(p.out + (size_t)c * p.out_cstride + (size_t)(s0 + ks) * N + inst0, vload<K>(lt + c * RS));
+        }
+        buf ^= 1;
+    }
+#undef FX_EACH
+
+    // ---- write the state back (the last time segment carries the final state) ----
+    if (flags) atomicOr(p.rt_flags, flags);
+    if (!valid || !last_seg) return;
+    for (int i = 0; i < p.n_wb; ++i) { const uint32_t r = p.wb_regs[i]; vstore<K>(p.gpr + (size_t)r * N + inst0, vload<K>(g + r * RS)); }
+    for (int c = 0; c < C; ++c) vstore<K>(p.latch + (size_t)c * N + inst0, vload<K>(lt + c * RS));
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        p.acc[inst0 + k] = acc_is_f[k] ? (double)acc_f[k] : acc_d[k];
+        if (EXT) {
+            p.lfsr[inst0 + k] = g1[k]; p.lfsr[N + inst0 + k] = g2[k];
+            p.ptrs[inst0 + k] = iw[k]; p.ptrs[N + inst0 + k] = ir[k];
+            p.ptrs[2 * N + inst0 + k] = xw[k]; p.ptrs[3 * N + inst0 + k] = xr[k];
+        }
+        const unsigned long long c = SKIP ? (unsigned long long)count[k]
+                                          : (unsigned long long)p.n_samples * (unsigned long long)p.n_instrs;
+        p.counts[inst0 + k] += c;
+    }
+}
+
+// Fills register `reg` of every instance with one value (broadcast setRegisterValue).
+__global__ void fx_fill_kernel(float* dst, float v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
+}
+
+}  // namespace fxk

@@ -1,0 +1,138 @@
+// FX8010.cpp — the Klangraum::FX8010 facade (see FX8010.h).  Parsing is host C++ (fx8010_frontend);
+// every sample is computed by the CUDA interpreter behind the C ABI.
+#include "FX8010.h"
+
+#include <stdexcept>
+
+namespace Klangraum {
+
+FX8010::FX8010(int numChannels) : front_(numChannels) {}
+FX8010::FX8010(int numChannels, int numInstances, int device)
+    : front_(numChannels), instances_(numInstances), device_(device) {}
+
+FX8010::~FX8010() {
+    if (gpu_) fx8010_gpu_destroy(gpu_);
+}
+
+void FX8010::initialize() { front_.initialize(); }
+
+void FX8010::check(int rc, const char* what) {
+    if (rc == FX8010_OK) return;
+    std::string msg = std::string("FX8010 (B200): ") + what + " failed: " + fx8010_gpu_last_error(gpu_);
+    throw std::runtime_error(msg);
+}
+
+bool FX8010::loadFile(const std::string& path) { return front_.loadFile(path); }
+bool FX8010::loadText(const std::string& source) { return front_.loadText(source); }
+
+void FX8010::ensureUploaded() {
+    if (!front_.ready()) throw std::runtime_error("FX8010 (B200): process() before a successful loadFile()");
+    if (!gpu_) {
+        const int rc = fx8010_gpu_create(device_, instances_, front_.channels(), &gpu_);
+        if (rc != FX8010_OK) {
+            std::string msg = std::string("FX8010 (B200): no GPU executor: ") + fx8010_gpu_last_error(nullptr);
+            gpu_ = nullptr;
+            throw std::runtime_error(msg);
+        }
+    }
+    if (uploaded_instrs_ != front_.instructions().size() || uploaded_regs_ != front_.registers().size()) {
+        check(fx8010_gpu_load_program(gpu_, front_.image()), "load_program");
+        uploaded_instrs_ = front_.instructions().size();
+        uploaded_regs_ = front_.registers().size();
+    }
+}
+
+fx8010_gpu* FX8010::gpuHandle() {
+    ensureUploaded();
+    return gpu_;
+}
+
+std::vector<float> FX8010::process(const std::vector<float>& inputSamples) {
+    ensureUploaded();
+    const size_t C = (size_t)front_.channels(), N = (size_t)instances_;
+    in_block_.assign(C * N, 0.0f);
+    out_block_.assign(C * N, 0.0f);
+    for (size_t c = 0; c < C && c < inputSamples.size(); ++c)
+        for (size_t i = 0; i < N; ++i) in_block_[c * N + i] = inputSamples[c];
+    check(fx8010_gpu_process_batch_host(gpu_, in_block_.data(), out_block_.data(), 1), "process_batch_host");
+    std::vector<float> out(C);
+    for (size_t c = 0; c < C; ++c) out[c] = out_block_[c * N];
+    return out;
+}
+
+void FX8010::processBlock(const float* in, float* out, int n_samples) {
+    ensureUploaded();
+    check(fx8010_gpu_process_batch_host(gpu_, in, out, n_samples), "process_batch_host");
+}
+
+void FX8010::processBlockDevice(const float* d_in, float* d_out, int n_samples, void* stream) {
+    ensureUploaded();
+    check(fx8010_gpu_process_batch(gpu_, d_in, d_out, n_samples, stream), "process_batch");
+}
+
+int FX8010::getInstructionCounter() {
+    if (!gpu_ || uploaded_instrs_ == (size_t)-1) return 0;
+    std::vector<unsigned long long> c((size_t)instances_);
+    check(fx8010_gpu_get_instruction_counts(gpu_, c.data()), "get_instruction_counts");
+    return (int)(unsigned int)c[0];                             // the reference counter is a 32-bit int
+}
+
+unsigned long long FX8010::getInstructionCounterTotal() {
+    if (!gpu_ || uploaded_instrs_ == (size_t)-1) return 0;
+    unsigned long long t = 0;
+    check(fx8010_gpu_get_instruction_count(gpu_, &t), "get_instruction_count");
+    return t;
+}
+
+std::vector<FX8010::MyError> FX8010::getErrorList() {
+    std::vector<MyError> out;
+    for (const fx8010::Diagnostic& d : front_.errors()) {
+        MyError e;
+        e.errorDescription = d.description;
+        e.errorRow = d.row;
+        out.push_back(e);
+    }
+    return out;
+}
+
+// Any register can be written by name, first match wins (source/FX8010.cpp:236-253).
+int FX8010::setRegisterValue(const std::string& key, float value) {
+    const int idx = front_.findRegister(key);
+    if (idx < 0) return 1;
+    front_.registers()[idx].value = value;                      // initial value of a later upload
+    if (gpu_ && uploaded_regs_ == front_.registers().size())
+        check(fx8010_gpu_set_controls(gpu_, idx, &value, 1), "set_controls");
+    return 0;
+}
+
+int FX8010::setRegisterValues(const std::string& key, const float* values) {
+    const int idx = front_.findRegister(key);
+    if (idx < 0) return 1;
+    ensureUploaded();
+    check(fx8010_gpu_set_controls(gpu_, idx, values, 0), "set_controls");
+    return 0;
+}
+
+float FX8010::getRegisterValue(const std::string& key) {
+    const int idx = front_.findRegister(key);
+    if (idx < 0) return 1;                                      // the reference's "not found" value (:265)
+    if (gpu_ && uploaded_regs_ == front_.registers().size()) {
+        std::vector<float> v((size_t)instances_);
+        check(fx8010_gpu_get_register(gpu_, idx, v.data()), "get_register");
+        return v[0];
+    }
+    return front_.registers()[idx].value;
+}
+
+int FX8010::getRegisterValues(const std::string& key, float* out) {
+    const int idx = front_.findRegister(key);
+    if (idx < 0) return 1;
+    ensureUploaded();
+    check(fx8010_gpu_get_register(gpu_, idx, out), "get_register");
+    return 0;
+}
+
+std::vector<std::string> FX8010::getControlRegisters() { return front_.controls(); }
+std::unordered_map<std::string, std::string> FX8010::getMetaData() { return front_.metadata(); }
+
+}  // namespace Klangraum

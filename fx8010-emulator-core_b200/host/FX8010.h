@@ -1,0 +1,78 @@
+// FX8010.h — drop-in for the reference's class Klangraum::FX8010 (reference include/FX8010.h:47-302)
+// on top of the B200 executor.  The public members of the reference keep their names, arguments
+// and return conventions; the batched members below them are the reason this library exists: one
+// parsed program executed over N independent DSP instances on one GPU.
+//
+// There is no CPU interpreter behind this class: process*/ need a CUDA device and throw
+// std::runtime_error when the C ABI (include/fx8010_gpu.h) reports an error.
+#ifndef FX8010_B200_FACADE_H
+#define FX8010_B200_FACADE_H
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "fx8010_frontend.h"
+#include "fx8010_gpu.h"
+
+#if defined(__GNUC__)
+#define FX8010_CLASS __attribute__((visibility("default")))
+#else
+#define FX8010_CLASS
+#endif
+
+namespace Klangraum {
+
+class FX8010_CLASS FX8010 {
+public:
+    // ---- the reference's surface (include/FX8010.h:49-75) --------------------------------------
+    FX8010(int numChannels);                                   // one instance on device 0
+    ~FX8010();
+    void initialize();                                         // re-runs the constructor's set-up (appends, like the reference)
+    std::vector<float> process(const std::vector<float>& inputSamples);   // one sample period (:57)
+    int getInstructionCounter();                               // executed instructions of instance 0 (:60)
+    bool loadFile(const std::string& path);                    // (:62)
+    struct MyError {
+        std::string errorDescription = "";
+        int errorRow = 1;
+    };
+    std::vector<FX8010::MyError> getErrorList();               // (:68)
+    int setRegisterValue(const std::string& key, float value); // 0 ok / 1 unknown name; every instance (:69)
+    float getRegisterValue(const std::string& key);            // instance 0; 1 when unknown (:70)
+    std::vector<std::string> getControlRegisters();            // (:71)
+    std::unordered_map<std::string, std::string> getMetaData();// (:72)
+    inline void setChannels(int numChannels_) { front_.setChannels(numChannels_); }
+    inline int getChannels() { return front_.channels(); }
+    bool getReadyStatus() { return front_.ready(); }
+
+    // ---- batched extension ------------------------------------------------------------------------
+    FX8010(int numChannels, int numInstances, int device);
+    bool loadText(const std::string& source);
+    int getInstances() const { return instances_; }
+    // per-instance control values, values[numInstances]; 0 ok / 1 unknown name
+    int setRegisterValues(const std::string& key, const float* values);
+    // reads one register of every instance into out[numInstances]; 0 ok / 1 unknown name
+    int getRegisterValues(const std::string& key, float* out);
+    // n_samples sample periods for all instances; HOST buffers laid out [channel][sample][instance]
+    void processBlock(const float* in, float* out, int n_samples);
+    // same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t)
+    void processBlockDevice(const float* d_in, float* d_out, int n_samples, void* stream);
+    unsigned long long getInstructionCounterTotal();           // summed over instances
+    fx8010_gpu* gpuHandle();                                   // creates the handle / uploads the program if needed
+    fx8010::Frontend& frontend() { return front_; }
+
+private:
+    void ensureUploaded();
+    void check(int rc, const char* what);
+
+    fx8010::Frontend front_;
+    int instances_ = 1;
+    int device_ = 0;
+    fx8010_gpu* gpu_ = nullptr;
+    size_t uploaded_instrs_ = (size_t)-1, uploaded_regs_ = 0;
+    std::vector<float> in_block_, out_block_;
+};
+
+}  // namespace Klangraum
+
+#endif

@@ -68,7 +68,7 @@ enum fx8010_runtime_flag {
 };
 
 #define FX8010_MAX_PASSES        8      /* program re-runs per sample while END stays skipped     */
-#define FX8010_MAX_INSTRUCTIONS  2048   /* decoded program lives in 64 KiB of __constant__ memory */
+#define FX8010_MAX_INSTRUCTIONS  1024   /* decoded programs live in __constant__ memory (3 slots x 16 KiB) */
 #define FX8010_TABLE_COUNT       32     /* reference source/FX8010.cpp:63                          */
 #define FX8010_TABLE_ENTRIES     64     /* 32 mirrored + 32 generated, source/FX8010.cpp:73-105    */
 #define FX8010_LFSR_SEED1        0x70f4f854u /* include/FX8010.h:290 */
@@ -144,6 +144,11 @@ FX8010_API int fx8010_gpu_process_batch(fx8010_gpu* h, const float* d_in, float*
  * `out` is complete. */
 FX8010_API int fx8010_gpu_process_batch_host(fx8010_gpu* h, const float* in, float* out, int n_samples);
 
+/* Page-locked host memory for process_batch_host buffers: with these the host<->device copies run
+ * asynchronously at full PCIe rate (pageable buffers work too, through the driver's staging). */
+FX8010_API void* fx8010_gpu_host_alloc(size_t bytes);
+FX8010_API void fx8010_gpu_host_free(void* p);
+
 /* Blocks until all work queued on the handle's internal streams and `stream` is done. */
 FX8010_API int fx8010_gpu_synchronize(fx8010_gpu* h, void* stream);
 
@@ -189,7 +194,7 @@ typedef struct fx8010_launch_info {
     int32_t last_grid, last_block;        /* geometry of the last interpreter launch       */
     int32_t last_time_split;              /* sample segments per instance (1 = serial)     */
     int32_t last_smem_bytes;
-    int32_t kernel_variant;               /* bit0 has_skip, bit1 has_tram, bit2 stateless  */
+    int32_t kernel_variant;               /* bit0 SKIP, bit1 TRAM/noise/MACMV, bit2 stateless (time split allowed), bits 8.. instances per thread */
 } fx8010_launch_info;
 FX8010_API int fx8010_gpu_get_launch_info(fx8010_gpu* h, fx8010_launch_info* out);
 
