@@ -264,8 +264,8 @@ void encode(fx8010_gpu* h) {
         if (tab_of[i] >= 0) {
             int slot = -1;
             for (int t = 0; t < h->n_smem_tabs; ++t) if (h->smem_tab_id[t] == tab_of[i]) slot = t;
-            if (slot >= 0) { w0 |= F_TAB_SMEM; aux = (uint32_t)slot; }
-            else { w0 |= F_TAB_IMM; aux = (uint32_t)tab_of[i]; }
+            if (slot >= 0) { w0 |= F_TAB_SMEM; aux |= (uint32_t)slot << 16; }
+            else { w0 |= F_TAB_IMM; aux |= (uint32_t)tab_of[i] << 16; }
         }
         h->h_prog[i] = make_uint4(w0, (uint32_t)in.r | ((uint32_t)in.a << 16), (uint32_t)in.x | ((uint32_t)in.y << 16), aux);
     }

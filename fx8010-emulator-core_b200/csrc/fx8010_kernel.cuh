@@ -41,7 +41,7 @@ constexpr uint32_t F_PRE_ANY = F_PRE_A | F_PRE_X | F_PRE_Y;
 
 // 16-byte decoded instruction:
 //   w0: uop[0:8) flags[8:16) in_ch[16:24) out_ch[24:32)
-//   w1: r | a << 16        w2: x | y << 16        w3: aux (noise target register / table slot)
+//   w1: r | a << 16        w2: x | y << 16        w3: noise target register | table slot or id << 16
 constexpr int MAX_INSTR = FX8010_MAX_INSTRUCTIONS;
 constexpr int PROG_SLOTS = 3;            // live programs per device (one slot per handle)
 __constant__ uint4 c_prog[PROG_SLOTS][MAX_INSTR + 1];
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                     case U_LOG:                                       // :1113-1119
                     case U_EXP: { FX_LOAD_A;                          // :1120-1125, linearInterpolate :283-296
                         if (w.x & F_TAB_SMEM) {
-                            const TableEntry* const tb = s_tab + (size_t)(w.w & 0xffu) * (FX8010_TABLE_ENTRIES * TAB_REPL) + lane_rep;
+                            const TableEntry* const tb = s_tab + (size_t)((w.w >> 16) & 0xffu) * (FX8010_TABLE_ENTRIES * TAB_REPL) + lane_rep;
                             FX_EACH {
                                 if (!(a[k] >= -1.0f && a[k] <= 1.0f) && act[k]) flags |= FX8010_RT_TABLE_RANGE;
                                 const double xd = (double)a[k];
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                             if (!(w.x & F_TAB_IMM)) x = vload<K>(px);
                             FX_EACH {
                                 int tsel;
-                                if (w.x & F_TAB_IMM) tsel = (int)(w.w & 0xffu);
+                                if (w.x & F_TAB_IMM) tsel = (int)((w.w >> 16) & 0xffu);
                                 else {
                                     int32_t sel = cvt_x86(x[k]);
                                     if (sel < 0 || sel > FX8010_TABLE_COUNT - 1) {

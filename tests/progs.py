@@ -278,3 +278,81 @@ def opcode_histogram(text: str) -> dict:
                           "tstneg", "limit", "limitn", "log", "exp", "interp", "skip", "idelay", "xdelay", "end"):
             h[w[0]] = h.get(w[0], 0) + 1
     return h
+
+
+# ---- front-end corpus: valid, odd and malformed sources ---------------------------------------------
+
+FRONTEND_CASES = {
+    "decl_forms": "static a\nstatic b = 0.5\nstatic c=0.25\nstatic d, 0.75\nstatic e 1\ntemp t\nconst k = 2\ncontrol v = 0.1\ninput i0 0\noutput o0 0\nmacs o0, a, b, c\nend",
+    "decl_backtrack_name": "static a1.5\nstatic b12\nstatic 7\noutput o 0\nmacs o, a, b12, 7\nend",
+    "decl_negative_value": "static x = -0.5\nend",
+    "decl_two_per_line": "static a,b\nend",
+    "decl_duplicate": "static a\ncontrol a = 1\nstatic ccr\nend",
+    "decl_bad_number": "static a 0.\nstatic b .5\nstatic c 1.2.3\nend",
+    "io_out_of_range": "input in_r 1\noutput out_r 2\nend",
+    "io_fraction_index": "input in_l 0.9\noutput out_l 0\nmacs out_l, 0, in_l, 1\nend",
+    "uppercase": "STATIC A\nINPUT IN_L 0\nOUTPUT OUT_L 0\nMACS OUT_L, 0, IN_L, 0.5\nEND",
+    "comments_and_blanks": "; header\n\nstatic a ; trailing\n   \noutput o 0\nmacs o, 0, a, 1 ; c\n;\nend",
+    "tram_ok": "itramsize 100 \nxtramsize 48000 \nstatic rd\nidelay read, rd, at, 0\nidelay write, rd, at, 0\nend",
+    "tram_no_trailing_blank": "itramsize 100\nend",
+    "tram_two_blanks": "itramsize 100  \nend",
+    "tram_tab": "itramsize 64\t\nend",
+    "tram_oversize_then_second": "itramsize 65536 \nitramsize 10 \nend",
+    "tram_x_oversize": "xtramsize 2000000 \nxtramsize 5 \nend",
+    "instr_undeclared": "output o 0\nmacs o, 0, nope, 1\nend",
+    "instr_partial_literals": "output o 0\nmacs 0.5, 0.25, nope, 1\nmacs o, 0.5, 0.25, 1\nend",
+    "instr_input_as_r": "input i 0\nmacs i, 0, 0, 0\nend",
+    "instr_spacing": "output o 0\nmacs   o ,0,  0.5 ,   -0.5   \nmacs\to,\t1,\t1,\t1\nend",
+    "instr_missing_operand": "output o 0\nmacs o, 0, 1\nmacs o, 0, 1, 1, 1\nmacs o 0 1 1\nend",
+    "instr_unknown_op": "output o 0\nmacx o, 0, 1, 1\nmacs, o, 0, 1, 1\nend",
+    "instr_number_forms": "output o 0\nmacs o, 1e5, 0, 0\nmacs o, 5., 0, 0\nmacs o, --1, 0, 0\nmacs o, -, 0, 0\nmacs o, -3, 0.50, 00.5\nend",
+    "noise_and_flags": "static noise\ninput i 0\noutput o 0\nmacs o, noise, i, noise\nmacs o, i, noise, 0\nend",
+    "metadata": 'name "Test Prog"\ncopyright "2023, x"\ncreated "2023/08/01"\nengine "e"\ncomment "c c"\nguid "0-0"\nname "second"\nend',
+    "metadata_bad": 'name "x" \nname ""\nname x\ncomment "a;b"\nend',
+    "end_trailing_blank": "static a\nend ",
+    "end_leading_blank": "static a\n end",
+    "end_missing": "static a\nmacs a, 0, 0, 0",
+    "end_crlf": "static a\r\nend\r\n",
+    "end_twice": "static a\nend\nmacs a, 0, 0, 0\nend",
+    "end_blank_after": "static a\nend\n\n",
+    "no_final_newline": "static a\nend",
+    "keywords_as_names": "static end\nstatic macs\noutput o 0\nmacs o, end, macs, 0\nend",
+    "special_registers": "output o 0\nmacs o, ccr, read, write\nmacs ccr, at, 0, 0\nend",
+    "literal_spellings": "output o 0\nmacs o, 0, 0.0, 1\nmacs o, 1.0, 1, 0.00\nend",
+    "garbage": "hello world\n= 5\nstatic\ncontrol\nmacs\n,,,\nend",
+}
+
+_FUZZ_ATOMS = ["static", "temp", "control", "input", "output", "const", "itramsize", "xtramsize", "macs", "macsn", "skip",
+               "log", "idelay", "end", "name", "comment", "a", "b", "in_l", "out_l", "ccr", "read", "write", "at", "noise",
+               "0", "1", "0.5", "-0.5", "12", "1.", ".5", "1.2.3", "-", "=", ",", " ", "  ", "\t", "\"", "x y", ".", "_"]
+
+
+def fuzz_source(rng: np.random.Generator) -> str:
+    """A small random source: mostly valid lines with random token-level damage (never the two
+    inputs that abort the reference: an empty number after itramsize/xtramsize, 10+ digit numbers)."""
+    head = ["static a", "static b = 0.5", "input in_l 0", "output out_l 0", "control c = 0.25", "itramsize 64 "]
+    body = ["macs out_l, 0, in_l, c", "macsn a, b, 0.5, -0.5", "log a, in_l, 3, 0", "skip ccr, ccr, 2, 1",
+            "idelay write, a, at, 0", "idelay read, b, at, 0", "name \"n\""]
+    lines = list(head) + [str(rng.choice(body)) for _ in range(int(rng.integers(1, 5)))]
+    for _ in range(int(rng.integers(1, 4))):
+        k = int(rng.integers(0, len(lines)))
+        toks = lines[k].replace(",", " , ").split(" ")
+        op = rng.random()
+        j = int(rng.integers(0, len(toks)))
+        if op < 0.35:
+            toks[j] = str(rng.choice(_FUZZ_ATOMS))
+        elif op < 0.6:
+            toks.insert(j, str(rng.choice(_FUZZ_ATOMS)))
+        elif op < 0.8 and len(toks) > 1:
+            del toks[j]
+        else:
+            toks[j] = toks[j].upper() + str(rng.choice(["", " ", "\t", ";x"]))
+        lines[k] = " ".join(toks).replace(" , ", ", ")
+    tail = str(rng.choice(["end", "end", "end", "end ", "END", "", "end\n"]))
+    text = "\n".join(lines + [tail])
+    import re
+    if re.search(r"(?mi)^\s*[ix]tramsize\s\s+$", text) or re.search(r"\d{10,}", text) or re.search(r"(?mi)^\s*[ix]tramsize\s+;", text):
+        return fuzz_source(rng)
+    if not text.strip("\n"):
+        return fuzz_source(rng)
+    return text

@@ -1,0 +1,304 @@
+"""GPU parity: the CUDA interpreter (through the C ABI) against the oracle, bit for bit.
+
+Every case parses the program with the product's host front-end, hands the same decoded image to
+oracle/liboracle.so and to fx8010_gpu_load_program, feeds both the same seeded inputs and controls
+and compares outputs, the whole register file, accumulator, LFSR, output latch, TRAM pointers,
+TRAM contents, executed-instruction counters and runtime flags as raw bit patterns (tolerance: 0).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import progs
+from conftest import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(fx, po, text, n, channels=1):
+    prog = fx.Program(text, channels=channels)
+    assert prog.loaded, prog.errors()
+    img = po.Image(prog.instructions(), prog.registers(), prog.itram_size, prog.xtram_size, prog.controls(), prog.tables())
+    orc = po.Oracle(img, n, channels)
+    gpu = fx.Gpu(n, channels)
+    gpu.load_program(prog)
+    return prog, img, orc, gpu
+
+
+def compare_state(gpu, orc, img, what, tram_instances=(0,)):
+    assert_bits_equal(gpu.registers(), orc.registers, what + " registers")
+    acc, lfsr, latch, ptrs = gpu.scalars()
+    assert_bits_equal(acc, orc.acc, what + " accumulator")
+    assert_bits_equal(lfsr, orc.lfsr, what + " lfsr")
+    assert_bits_equal(latch, orc.out_latch, what + " out latch")
+    assert_bits_equal(ptrs, orc.tram_ptrs, what + " tram pointers")
+    assert_bits_equal(gpu.counts(), orc.counts, what + " instruction counters")
+    d = gpu.dims()
+    for which, size in ((0, d.itram_size), (1, d.xtram_size)):
+        if size:
+            for i in tram_instances:
+                assert_bits_equal(gpu.tram(which, i), orc.tram(which, i), f"{what} tram{which}[{i}]")
+    assert gpu.flags() == orc.flags, what + " runtime flags"
+
+
+def run_case(fx, po, text, n, blocks, rng, channels=1, controls=None, stimulus=None, what="case"):
+    prog, img, orc, gpu = make_pair(fx, po, text, n, channels)
+    try:
+        for name, vals in (controls or {}).items():
+            idx = prog.reg_index(name)
+            assert idx >= 0
+            gpu.set_controls(idx, vals)
+            orc.set_register(idx, vals)
+        start = 0
+        for s in blocks:
+            if stimulus is not None:
+                x = stimulus(start, s)
+            else:
+                x = (1.8 * rng.random((channels, s, n)) - 0.9).astype(np.float32)
+            yo = orc.process(x)
+            yg = gpu.process_host(x)
+            assert_bits_equal(yg, yo, f"{what} outputs of block at {start}")
+            start += s
+        inst = sorted({0, n - 1, n // 2})
+        compare_state(gpu, orc, img, what, inst)
+        return gpu.launch_info()
+    finally:
+        gpu.close()
+
+
+# ---- BASELINE.json configs at sizes the oracle finishes in seconds --------------------------------
+
+def test_cfg1_testcode_shipped(fx, po):
+    rng = np.random.default_rng(progs.SEED)
+    n = 64
+    vol = rng.random(n).astype(np.float32)
+    x = progs.sine_bank(n, 257, rng)
+    run_case(fx, po, progs.CFG1A_TESTCODE, n, [100, 157], rng, controls={"volume": vol},
+             stimulus=lambda a, s: x[a:a + s].reshape(1, s, n), what="cfg1a")
+
+
+def test_cfg1b_logtube_edges(fx, po):
+    n = 16
+    edge = np.array([1.0, -1.0, 0.0, -0.0, 1 / 63, -1 / 63, 0.99999994, -0.99999994, 0.5, -0.5, 0.0159, 0.9375,
+                     1e-30, -1e-30, 0.031746034, 0.96825397], dtype=np.float32)
+    rng = np.random.default_rng(1)
+    run_case(fx, po, progs.CFG1B_LOGTUBE, n, [8], rng, stimulus=lambda a, s: np.tile(edge, (s, 1)).reshape(1, s, n), what="cfg1b")
+
+
+@pytest.mark.parametrize("n", [4096, 1000, 333])
+def test_cfg2_log_gain(fx, po, n):
+    rng = np.random.default_rng(progs.SEED)
+    vol = rng.random(n).astype(np.float32)
+    x = progs.sine_bank(n, 1024 + 40, rng)
+    info = run_case(fx, po, progs.CFG2_LOG_GAIN, n, [1024, 40], rng, controls={"volume": vol},
+                    stimulus=lambda a, s: x[a:a + s].reshape(1, s, n), what=f"cfg2 n={n}")
+    assert info.kernel_variant & 4, "cfg2 is stateless: the time axis must be splittable"
+
+
+@pytest.mark.parametrize("size", [100, 1000, 8192])
+def test_cfg3_delay(fx, po, size):
+    rng = np.random.default_rng(progs.SEED)
+    n = 256
+    s = min(2 * size + 33, 2500)
+    x = progs.impulse_noise(n, s, rng)
+    run_case(fx, po, progs.cfg3_delay(size), n, [s // 2, s - s // 2], rng,
+             stimulus=lambda a, k: x[a:a + k].reshape(1, k, n), what=f"cfg3 S={size}")
+
+
+def test_cfg3_delay_65536(fx, po):
+    rng = np.random.default_rng(progs.SEED)
+    n = 32
+    x = progs.impulse_noise(n, 1500, rng)
+    run_case(fx, po, progs.cfg3_delay(65536), n, [1500], rng, stimulus=lambda a, k: x[a:a + k].reshape(1, k, n), what="cfg3 S=65536")
+
+
+def test_cfg4_onepole_sweep(fx, po):
+    rng = np.random.default_rng(progs.SEED)
+    n = 2048
+    cutoff = (0.001 + 0.998 * np.arange(n) / (n - 1)).astype(np.float32)
+    x = progs.sine_bank(n, 700, rng)
+    run_case(fx, po, progs.CFG4_ONEPOLE, n, [512, 188], rng, controls={"filter_cutoff": cutoff},
+             stimulus=lambda a, s: x[a:a + s].reshape(1, s, n), what="cfg4")
+
+
+def test_cfg5_allops_512(fx, po):
+    rng = np.random.default_rng(progs.SEED)
+    n = 512
+    text = progs.cfg5_allops()
+    ctl = {f"k{i}": rng.random(n).astype(np.float32) for i in range(4)}
+    x = progs.sine_bank(n, 96, rng, amp_lo=0.9, amp_hi=0.9)
+    info = run_case(fx, po, text, n, [64, 32], rng, controls=ctl, stimulus=lambda a, s: x[a:a + s].reshape(1, s, n), what="cfg5")
+    assert info.kernel_variant & 1
+
+
+# ---- one program per feature snippet of the reference's testcode.da ----------------------------------
+
+@pytest.mark.parametrize("name", sorted(progs.SNIPPETS))
+def test_snippets(fx, po, name):
+    rng = np.random.default_rng(7)
+    run_case(fx, po, progs.SNIPPETS[name], 96, [50, 31], rng, what=name)
+
+
+# ---- random programs over every opcode, with SKIP / TRAM / noise / xTRAM -------------------------------
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_programs(fx, po, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = [128, 100, 37, 64][seed % 4]
+    ch = 1 + seed % 2
+    text = progs.random_program(rng, 60 + 10 * seed, channels=ch, xtram=(seed % 3 == 0), read_offsets=(seed % 4 == 1))
+    run_case(fx, po, text, n, [40, 25], rng, channels=ch, what=f"random {seed}")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_programs_unsafe(fx, po, seed):
+    """Operands may leave [-1,1], ccr appears as an operand, LOG/EXP may see out-of-range input
+    (rule U6: clamped + flagged identically by oracle and kernel)."""
+    rng = np.random.default_rng(2000 + seed)
+    text = progs.random_program(rng, 80, safe=False, skip=(seed % 2 == 0))
+    run_case(fx, po, text, 64, [30, 30], rng, what=f"unsafe {seed}")
+
+
+def test_end_skipped_wraps_and_cap(fx, po):
+    """END skipped: the program runs again carrying the skip count (reference :1243); a program that
+    always skips END is cut off after FX8010_MAX_PASSES and flagged (rule U9)."""
+    rng = np.random.default_rng(3)
+    wrap = "static a\ninput in_l 0\noutput out_l 0\nmacs a, 0, in_l, 1.0\nmacs out_l, a, 0.25, 0.5\nskip ccr, ccr, 2, 1\nend"
+    run_case(fx, po, wrap, 64, [40], rng, what="end skipped sometimes")
+    forever = "static a\noutput out_l 0\nmacs a, 0, 0.5, 0.5\nmacs out_l, a, 0.1, 0.1\nskip ccr, ccr, 2, 1\nend"
+    prog, img, orc, gpu = make_pair(fx, po, forever, 8)
+    try:
+        assert_bits_equal(gpu.process_host(None, 3), orc.process(None, 3), "capped outputs")
+        assert gpu.flags() & fx.RT_END_SKIPPED_CAP
+        compare_state(gpu, orc, img, "capped")
+    finally:
+        gpu.close()
+
+
+def test_two_channels_input_index_quirk(fx, po):
+    """X and Y operands of INPUT type read the channel of A (reference :1057-1060)."""
+    rng = np.random.default_rng(4)
+    text = "static a\ninput in_l 0\ninput in_r 1\noutput out_l 0\noutput out_r 1\nmacs out_r, 0, in_r, 1.0\nmacs out_l, in_r, in_l, 0.5\nmacs a, 0.1, 0.5, in_r\nend"
+    run_case(fx, po, text, 40, [33], rng, channels=2, what="two channels")
+
+
+def test_state_roundtrip_checkpoint(fx, po):
+    """get_state -> new handle -> set_state continues bit-identically (checkpoint / resume)."""
+    rng = np.random.default_rng(5)
+    text = progs.random_program(rng, 50, xtram=True)
+    n = 32
+    prog, img, orc, gpu = make_pair(fx, po, text, n)
+    gpu2 = fx.Gpu(n, 1)
+    try:
+        x1 = (1.8 * rng.random((1, 64, n)) - 0.9).astype(np.float32)
+        x2 = (1.8 * rng.random((1, 64, n)) - 0.9).astype(np.float32)
+        gpu.process_host(x1); orc.process(x1)
+        gpu2.load_program(prog)
+        gpu2.set_registers(gpu.registers())
+        acc, lfsr, latch, ptrs = gpu.scalars()
+        gpu2.set_scalars(acc, lfsr, latch, ptrs)
+        d = gpu.dims()
+        for i in range(n):
+            if d.itram_size: gpu2.set_tram(0, i, gpu.tram(0, i))
+            if d.xtram_size: gpu2.set_tram(1, i, gpu.tram(1, i))
+        yo = orc.process(x2)
+        assert_bits_equal(gpu2.process_host(x2), yo, "resumed outputs")
+        assert_bits_equal(gpu2.registers(), orc.registers, "resumed registers")
+    finally:
+        gpu.close(); gpu2.close()
+
+
+def test_device_pointers_and_streams(fx, po):
+    import torch
+    rng = np.random.default_rng(6)
+    n, s = 4096, 256
+    prog, img, orc, gpu = make_pair(fx, po, progs.CFG4_ONEPOLE, n)
+    try:
+        cut = rng.random(n).astype(np.float32)
+        idx = prog.reg_index("filter_cutoff")
+        st = torch.cuda.Stream()
+        d_cut = torch.from_numpy(cut).cuda()
+        x = progs.sine_bank(n, 2 * s, rng).reshape(1, 2 * s, n)
+        d_x = torch.from_numpy(x).cuda()
+        torch.cuda.synchronize()
+        gpu.set_controls_device(idx, d_cut, st.cuda_stream)
+        a = d_x[0, :s].contiguous(); b = d_x[0, s:].contiguous()
+        ya = torch.empty_like(a); yb = torch.empty_like(b)
+        torch.cuda.synchronize()
+        gpu.process_device(a, ya, s, st.cuda_stream)
+        gpu.process_device(b, yb, s, st.cuda_stream)
+        gpu.synchronize(st.cuda_stream)
+        orc.set_register(idx, cut)
+        yo = orc.process(x)
+        assert_bits_equal(np.concatenate([ya.cpu().numpy(), yb.cpu().numpy()])[None], yo, "device path outputs")
+        compare_state(gpu, orc, img, "device path")
+    finally:
+        gpu.close()
+
+
+def test_table_sweep_all_selectors(fx, po):
+    """LOG and EXP over a dense grid of inputs (incl. every table boundary neighbourhood) for all 32
+    selectors, against the oracle's single-evaluation entry point."""
+    rng = np.random.default_rng(8)
+    n = 4096
+    k = np.arange(64)
+    bounds = (-1.0 + k * (2.0 / 63)).astype(np.float32)
+    near = np.concatenate([np.nextafter(bounds, np.float32(-2)), bounds, np.nextafter(bounds, np.float32(2))]).astype(np.float32)
+    near = near[np.abs(near) <= 1]
+    grid = np.concatenate([near, (2 * rng.random(n - near.size) - 1).astype(np.float32)]).astype(np.float32)
+    for op in ("log", "exp"):
+        for sel in (0, 1, 3, 7, 31):
+            text = f"static a\ninput in_l 0\noutput out_l 0\n{op} a, in_l, {sel}, 0\nmacs out_l, 0, a, 1.0\nend"
+            run_case(fx, po, text, n, [2], rng, stimulus=lambda a, s: np.tile(grid, (s, 1)).reshape(1, s, n), what=f"{op} {sel}")
+    # dynamic selector (a control, per instance) goes through the global-memory table path
+    text = "static a\ninput in_l 0\ncontrol sel = 3\noutput out_l 0\nlog a, in_l, sel, 0\nexp out_l, a, sel, 0\nend"
+    sel = rng.integers(0, 32, n).astype(np.float32)
+    run_case(fx, po, text, n, [3], rng, controls={"sel": sel}, stimulus=lambda a, s: np.tile(grid, (s, 1)).reshape(1, s, n), what="dynamic selector")
+
+
+@pytest.mark.parametrize("k,b", [(1, 32), (2, 64), (4, 128), (4, 32)])
+def test_forced_geometries(fx, po, k, b, monkeypatch):
+    """Every contexts-per-thread / block-size variant of the kernel gives the same bits."""
+    monkeypatch.setenv("FX8010_TUNE_K", str(k))
+    monkeypatch.setenv("FX8010_TUNE_B", str(b))
+    rng = np.random.default_rng(9)
+    text = progs.random_program(rng, 70, xtram=True)
+    run_case(fx, po, text, 200, [37, 20], rng, what=f"K={k} B={b}")
+    run_case(fx, po, progs.CFG2_LOG_GAIN, 256, [100], rng, what=f"cfg2 K={k} B={b}")
+
+
+def test_errors_are_loud(fx):
+    g = fx.Gpu(8, 1)
+    try:
+        with pytest.raises(fx.FxError) as e:
+            g.process_host(np.zeros((1, 4, 8), np.float32))
+        assert e.value.code == 3          # ERR_NO_PROGRAM
+        p = fx.Program("static a\nidelay write, a, at, 0\nend")
+        assert p.loaded
+        with pytest.raises(fx.FxError) as e:
+            g.load_program(p)             # IDELAY without itramsize: rule U4
+        assert e.value.code == 4
+    finally:
+        g.close()
+
+
+def test_facade_per_sample_process_matches_reference_driver(fx, po):
+    """The legacy drop-in call: one process() per sample, volume slider changed every 8 samples,
+    exactly as the reference's main.cpp:103-122 drives it; anchors from SURVEY.md §8c."""
+    p = fx.Program(progs.CFG1A_TESTCODE)
+    ramp = np.array([(i - 16) / 16 for i in range(32)], dtype=np.float32)
+    out = []
+    for i in range(32):
+        if i % 8 == 0:
+            assert p.set_register("volume", [0.1, 0.25, 0.5, 1.0][i // 8]) == 0
+        out.append(p.process(ramp[i:i + 1])[0, 0])
+    out = np.array(out, dtype=np.float32)
+    want = [0xbdcccccd, 0xbdc00000, 0xbdb33333, 0xbda66667, 0xbd99999a, 0xbd8ccccd, 0xbd800000, 0xbd666667,
+            0xbe000000, 0xbde00000, 0xbdc00000, 0xbda00000, 0xbd800000, 0xbd400000, 0xbd000000, 0xbc800000,
+            0x00000000, 0x3d000000, 0x3d800000, 0x3dc00000, 0x3e000000, 0x3e200000, 0x3e400000, 0x3e600000] + \
+           [0x3f000000 + 0x100000 * k for k in range(8)]
+    assert [int(v) for v in out.view(np.uint32)] == want
+    assert p.instruction_counter == 64
+    assert p.get_register("nonexistent") == 1.0 and p.set_register("nonexistent", 0.0) == 1
+    p.close()
