@@ -131,7 +131,7 @@ HOST_SYMBOLS = {
 def _bind(path, table):
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: run __graft_entry__.build() (there is no CPU fallback)")
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path)          # RTLD_LOCAL: the facade and the reference harness both define Klangraum::FX8010
     for name, (res, args) in table.items():
         f = getattr(lib, name)
         f.restype, f.argtypes = res, args

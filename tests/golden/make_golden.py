@@ -44,7 +44,7 @@ def exec_programs():
         cases[f"unsafe_{s}"] = (progs.random_program(np.random.default_rng(600 + s), 60, safe=False), 1)
     cases["two_channel_quirk"] = ("static a\ninput in_l 0\ninput in_r 1\noutput out_l 0\noutput out_r 1\nmacs out_r, 0, in_r, 1.0\n"
                                   "macs out_l, in_r, in_l, 0.5\nmacs a, 0.1, 0.5, in_r\nend", 2)
-    cases["end_skipped_wrap"] = ("static a\ninput in_l 0\noutput out_l 0\nmacs a, 0, in_l, 1.0\nmacs out_l, a, 0.25, 0.5\nskip ccr, ccr, 2, 1\nend", 1)
+    cases["end_skipped_wrap"] = (progs.END_SKIPPED_WRAP, 1)
     return cases, rng
 
 

@@ -71,6 +71,10 @@ output out_l 0
 interp out_l, out_l, filter_cutoff, in_l
 end"""
 
+# END is skipped while `a` is in (0,1); `a` advances by a wrapping 0.3 per pass, so every sample period
+# ends after at most 4 passes (a program that always skips END hangs the reference, SURVEY U9).
+END_SKIPPED_WRAP = "static a\noutput out_l 0\nmacintw a, a, 0.3, 1.0\nmacs out_l, 0, a, 1.0\nskip ccr, ccr, 2, 1\nend"
+
 SNIPPETS = {
     # one per commented feature snippet of reference source/testcode.da:26-57
     "exp": "static a\ninput in_l 0\noutput out_l 0\nexp a, in_l, 7, 0\nmacs out_l, 0, a, 1.0\nend",
@@ -122,12 +126,14 @@ INT_LITERALS = ["0", "1", "2", "3", "5", "-4", "-1", "7", "16777215", "-2"]
 def random_program(rng: np.random.Generator, n_instr: int, *, channels: int = 1, n_static: int = 8,
                    n_controls: int = 2, skip: bool = True, tram: bool = True, noise: bool = True,
                    xtram: bool = False, itram_size: int = 64, xtram_size: int = 128, safe: bool = True,
-                   ops: list | None = None, read_offsets: bool = False) -> str:
+                   ops: list | None = None, read_offsets: bool = False, wild_tables: bool = False) -> str:
     """Emit a random `.da` program with `n_instr` instructions + END.
 
     safe=True keeps the program inside the reference's DEFINED behaviour (SURVEY.md §8a UB ledger):
     LOG/EXP see |A|<=1 and a literal selector 0..31, wrap-family operands are bounded, TRAM reads
     use offset 0 (unless read_offsets), SKIP can never reach END, values cannot blow up to inf/NaN.
+    safe=False adds `ccr` operands and unbounded operands for the wrap family (still defined in the
+    reference); wild_tables=True also lets LOG/EXP see out-of-range input (defined only by rule U6).
     """
     lines = []
     narrow = []                     # registers guaranteed in [-1, 1]
@@ -199,7 +205,7 @@ def random_program(rng: np.random.Generator, n_instr: int, *, channels: int = 1,
             s = src_narrow if safe else src_any
             body.append(f"{op} {rng.choice(wide)}, {s()}, {s()}, {s()}")
         elif op in TABLE_OPS:
-            a = src_narrow() if safe else src_any()
+            a = src_any() if wild_tables else src_narrow()     # |A| > 1 is undefined in the reference (U6)
             sel = int(rng.integers(0, 32))
             body.append(f"{op} {dst_narrow()}, {a}, {sel}, {rng.choice(['0', '1'])}")
         elif op == "andxor":

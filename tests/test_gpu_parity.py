@@ -156,7 +156,7 @@ def test_random_programs_unsafe(fx, po, seed):
     """Operands may leave [-1,1], ccr appears as an operand, LOG/EXP may see out-of-range input
     (rule U6: clamped + flagged identically by oracle and kernel)."""
     rng = np.random.default_rng(2000 + seed)
-    text = progs.random_program(rng, 80, safe=False, skip=(seed % 2 == 0))
+    text = progs.random_program(rng, 80, safe=False, skip=(seed % 2 == 0), wild_tables=True)
     run_case(fx, po, text, 64, [30, 30], rng, what=f"unsafe {seed}")
 
 
@@ -164,7 +164,7 @@ def test_end_skipped_wraps_and_cap(fx, po):
     """END skipped: the program runs again carrying the skip count (reference :1243); a program that
     always skips END is cut off after FX8010_MAX_PASSES and flagged (rule U9)."""
     rng = np.random.default_rng(3)
-    wrap = "static a\ninput in_l 0\noutput out_l 0\nmacs a, 0, in_l, 1.0\nmacs out_l, a, 0.25, 0.5\nskip ccr, ccr, 2, 1\nend"
+    wrap = progs.END_SKIPPED_WRAP
     run_case(fx, po, wrap, 64, [40], rng, what="end skipped sometimes")
     forever = "static a\noutput out_l 0\nmacs a, 0, 0.5, 0.5\nmacs out_l, a, 0.1, 0.1\nskip ccr, ccr, 2, 1\nend"
     prog, img, orc, gpu = make_pair(fx, po, forever, 8)
