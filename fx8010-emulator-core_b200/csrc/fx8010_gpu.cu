@@ -28,6 +28,7 @@ bool g_slot_used[MAX_DEVICES][PROG_SLOTS];
 thread_local std::string g_create_error;
 
 struct Launch { int K, B, n_seg, seg_len, grid_x; size_t smem; };
+struct PlanKey { int ns = -1; unsigned align = 0; };
 
 }  // namespace
 
@@ -46,16 +47,24 @@ struct fx8010_gpu {
     std::vector<uint8_t> written;                // program may write the register
     std::vector<uint8_t> reg_uniform;            // every instance holds reg_value (host knowledge)
     std::vector<float> reg_value;
-    std::vector<uint32_t> wb;
+    std::vector<uint32_t> wb;                    // shared-memory rows to write back
+    std::vector<uint32_t> reg_map;               // row -> register index
+    std::vector<int> row_of;                     // register index -> row (-1: the program never refers to it)
     bool has_skip = false, has_ext = false, stateless = false;
     bool encode_dirty = true;
     int n_smem_tabs = 0;
     int smem_tab_id[MAX_SMEM_TABLES] = {0, 0};
-    uint4* h_prog = nullptr;                     // pinned, MAX_INSTR + 1 words
+    std::vector<int> tab_of;                     // per instruction: literal table id or -1
+    uint4* h_prog = nullptr;                     // pinned, SLOT_WORDS words
+    int enc_K = 0, enc_B = 0;                    // geometry the uploaded encoding was made for
+    PlanKey plan_key; Launch plan = {};          // last launch plan (reused while nothing relevant changes)
+    bool attr_set[3][2][2] = {};                 // MaxDynamicSharedMemorySize set for kernel <K, SKIP, EXT>
+    int n_exec = 0;                              // encoded instructions
+    std::vector<uint32_t> latch_ch;              // channels served from the latch every sample period
     // device state
     float* d_gpr = nullptr; double* d_acc = nullptr; uint32_t* d_lfsr = nullptr; float* d_latch = nullptr;
     int32_t* d_ptrs = nullptr; float* d_itram = nullptr; float* d_xtram = nullptr;
-    unsigned long long* d_counts = nullptr; unsigned int* d_flags = nullptr; uint32_t* d_wb = nullptr;
+    unsigned long long* d_counts = nullptr; unsigned int* d_flags = nullptr; uint32_t* d_wb = nullptr; uint32_t* d_latch_ch = nullptr; uint32_t* d_reg_map = nullptr;
     TableEntry* d_tabs = nullptr;
     // streams
     cudaStream_t last_stream = nullptr;
@@ -158,8 +167,24 @@ void analyse(fx8010_gpu* h) {
         if (u == U_SKIP) h->has_skip = true;
     }
     if (any_ccr_writer) h->written[0] = 1;
-    h->wb.clear();
-    for (int r = 0; r < nr; ++r) if (h->written[r]) h->wb.push_back((uint32_t)r);
+    // Only registers some instruction refers to (plus ccr) get a shared-memory row; the others
+    // (unused declarations, the read/write/at pseudo registers) stay in the state arrays untouched.
+    std::vector<uint8_t> used(nr, 0);
+    used[0] = 1;
+    for (int i = 0; i < n; ++i) {
+        const fx8010_instr& in = h->instrs[i];
+        const Uop u = uop_of(h, in);
+        if (u == U_END || u == U_NOP) continue;
+        if (writes_r(u) || h->regs[in.r].type == FX_REG_OUTPUT) used[in.r] = 1;   // OUTPUT R feeds the latch after any op
+        used[in.a] = used[in.x] = used[in.y] = 1;
+    }
+    h->reg_map.clear(); h->row_of.assign(nr, -1); h->wb.clear();
+    for (int r = 0; r < nr; ++r)
+        if (used[r]) {
+            h->row_of[r] = (int)h->reg_map.size();
+            if (h->written[r]) h->wb.push_back((uint32_t)h->reg_map.size());
+            h->reg_map.push_back((uint32_t)r);
+        }
 
     // Stateless = no sample period reads anything an earlier period wrote: then the time axis can
     // be cut into independent segments.  Conservative: SKIP / TRAM / noise / MACMV rule it out.
@@ -183,9 +208,40 @@ void analyse(fx8010_gpu* h) {
     }
 }
 
-// Encodes the program for the kernel: micro-ops, flags, CCR liveness, table placement.
-void encode(fx8010_gpu* h) {
+// LOG/EXP with a literal selector (a register the program never writes and that holds one value in
+// every instance): the table is known at encode time; the most frequent ones go to shared memory.
+// Runs before launch planning because it decides the shared-memory footprint.
+void select_tables(fx8010_gpu* h) {
     const int n = (int)h->instrs.size();
+    auto is_const = [&](int r) { return !h->written[r] && h->reg_uniform[r]; };
+    int freq[2 * FX8010_TABLE_COUNT] = {0};
+    h->tab_of.assign(n, -1);
+    for (int i = 0; i < n; ++i) {
+        const Uop u = uop_of(h, h->instrs[i]);
+        if (u != U_LOG && u != U_EXP) continue;
+        const int xr = h->instrs[i].x;
+        if (!is_const(xr)) continue;
+        const int32_t sel = cvt_x86_host(h->reg_value[xr]);
+        if (sel < 0 || sel >= FX8010_TABLE_COUNT) continue;      // out of range: dynamic path raises the flag
+        h->tab_of[i] = (u == U_EXP ? FX8010_TABLE_COUNT : 0) + sel;
+        freq[h->tab_of[i]]++;
+    }
+    h->n_smem_tabs = 0;
+    for (int t = 0; t < MAX_SMEM_TABLES; ++t) {
+        int best = -1;
+        for (int id = 0; id < 2 * FX8010_TABLE_COUNT; ++id)
+            if (freq[id] > 0 && (best < 0 || freq[id] > freq[best])) best = id;
+        if (best < 0) break;
+        h->smem_tab_id[h->n_smem_tabs++] = best;
+        freq[best] = -1;
+    }
+}
+
+// Encodes the program for the kernel: micro-ops, flags, CCR liveness, table placement.
+void encode(fx8010_gpu* h, int K, int B) {
+    const int n = (int)h->instrs.size();
+    const int RS = K * B, nr = (int)h->reg_map.size(), C = h->C;
+    auto row = [&](int r) { return h->row_of[r] < 0 ? 0 : h->row_of[r]; };   // unused operands (R of SKIP/TRAM ops) are never touched
     std::vector<Uop> uops(n);
     for (int i = 0; i < n; ++i) uops[i] = uop_of(h, h->instrs[i]);
     auto is_const = [&](int r) { return !h->written[r] && h->reg_uniform[r]; };
@@ -224,59 +280,59 @@ void encode(fx8010_gpu* h) {
         ccr_live[i] = live;
     }
 
-    // LOG/EXP with a literal selector: most frequent tables go to shared memory
-    int freq[2 * FX8010_TABLE_COUNT] = {0};
-    std::vector<int> tab_of(n, -1);
-    for (int i = 0; i < n; ++i) {
-        if (uops[i] != U_LOG && uops[i] != U_EXP) continue;
-        const int xr = h->instrs[i].x;
-        if (!is_const(xr)) continue;
-        const int32_t sel = cvt_x86_host(h->reg_value[xr]);
-        if (sel < 0 || sel >= FX8010_TABLE_COUNT) continue;      // out of range: dynamic path raises the flag
-        tab_of[i] = (uops[i] == U_EXP ? FX8010_TABLE_COUNT : 0) + sel;
-        freq[tab_of[i]]++;
-    }
-    h->n_smem_tabs = 0;
-    for (int t = 0; t < MAX_SMEM_TABLES; ++t) {
-        int best = -1;
-        for (int id = 0; id < 2 * FX8010_TABLE_COUNT; ++id)
-            if (freq[id] > 0 && (best < 0 || freq[id] > freq[best])) best = id;
-        if (best < 0) break;
-        h->smem_tab_id[h->n_smem_tabs++] = best;
-        freq[best] = -1;
-    }
+    // SKIP-free programs: the value a channel puts out is what its LAST writer in program order leaves
+    // (earlier latch updates are dead), so that writer stores straight to the output block; channels
+    // nobody writes — and every channel of a program with SKIP — are served from the latch.
+    std::vector<int> last_writer(C, -1);
+    if (!h->has_skip)
+        for (int i = 0; i < n; ++i)
+            if (h->regs[h->instrs[i].r].type == FX_REG_OUTPUT && uops[i] != U_END && uops[i] != U_NOP)
+                last_writer[h->regs[h->instrs[i].r].io_index] = i;
+    h->latch_ch.clear();
+    for (int c = 0; c < C; ++c) if (last_writer[c] < 0) h->latch_ch.push_back((uint32_t)c);
 
+    int e = 0;
     for (int i = 0; i < n; ++i) {
         const fx8010_instr& in = h->instrs[i];
+        if (!h->has_skip && (uops[i] == U_END || uops[i] == U_NOP)) continue;    // no-ops unless a SKIP counts them
         bool pa, px, py; int nz;
         pre_targets(h, in, pa, px, py, nz);
         uint32_t w0 = (uint32_t)uops[i];
         if (pa) w0 |= F_PRE_A;
         if (px) w0 |= F_PRE_X;
         if (py) w0 |= F_PRE_Y;
-        if (pa || px || py) w0 |= (uint32_t)(h->regs[in.a].io_index & 0xff) << 16;   // X and Y use A's IOIndex (:1057-1060)
-        uint32_t aux = 0;
-        if (nz >= 0) { w0 |= F_NOISE; aux = (uint32_t)nz; }
-        if (h->regs[in.r].type == FX_REG_OUTPUT && uops[i] != U_END) {           // :1229-1233
-            w0 |= F_OUT | ((uint32_t)(h->regs[in.r].io_index & 0xff) << 24);
+        uint32_t pre_off = 0, out_off = 0, aux = 0;
+        if (pa || px || py) pre_off = stage_offset(nr, C, h->regs[in.a].io_index, RS);      // X and Y use A's IOIndex (:1057-1060)
+        if (nz >= 0) { w0 |= F_NOISE; aux = reg_offset(row(nz), RS); }
+        if (h->regs[in.r].type == FX_REG_OUTPUT && uops[i] != U_END && uops[i] != U_NOP) { // :1229-1233
+            const int c = h->regs[in.r].io_index;
+            if (h->has_skip) w0 |= F_OUT;
+            else if (last_writer[c] == i) w0 |= F_OUT | F_OUT_DIRECT;
+            w0 |= (uint32_t)c << 24;
+            out_off = latch_offset(nr, c, RS);
         }
         if (ccr_live[i]) w0 |= F_CCR;
-        if (tab_of[i] >= 0) {
+        if (h->tab_of[i] >= 0) {
             int slot = -1;
-            for (int t = 0; t < h->n_smem_tabs; ++t) if (h->smem_tab_id[t] == tab_of[i]) slot = t;
-            if (slot >= 0) { w0 |= F_TAB_SMEM; aux |= (uint32_t)slot << 16; }
-            else { w0 |= F_TAB_IMM; aux |= (uint32_t)tab_of[i] << 16; }
+            for (int t = 0; t < h->n_smem_tabs; ++t) if (h->smem_tab_id[t] == h->tab_of[i]) slot = t;
+            if (slot >= 0) { w0 |= F_TAB_SMEM; aux |= (uint32_t)slot << 24; }
+            else { w0 |= F_TAB_IMM; aux |= (uint32_t)h->tab_of[i] << 24; }
         }
-        h->h_prog[i] = make_uint4(w0, (uint32_t)in.r | ((uint32_t)in.a << 16), (uint32_t)in.x | ((uint32_t)in.y << 16), aux);
+        h->h_prog[2 * e] = make_uint4(w0, reg_offset(row(in.r), RS), reg_offset(row(in.a), RS), reg_offset(row(in.x), RS));
+        h->h_prog[2 * e + 1] = make_uint4(reg_offset(row(in.y), RS), aux, pre_off, out_off);
+        ++e;
     }
-    h->h_prog[n] = make_uint4((uint32_t)U_END, 0, 0, 0);          // pad: the kernel prefetches pc + 1
+    h->n_exec = e;
+    h->h_prog[2 * e] = make_uint4((uint32_t)U_NOP, 0, 0, 0);      // pad: the kernel prefetches pc + 1
+    h->h_prog[2 * e + 1] = make_uint4(0, 0, 0, 0);
+    h->enc_K = K; h->enc_B = B;
 }
 
 void free_state(fx8010_gpu* h) {
     cudaFree(h->d_gpr); cudaFree(h->d_acc); cudaFree(h->d_lfsr); cudaFree(h->d_latch); cudaFree(h->d_ptrs);
-    cudaFree(h->d_itram); cudaFree(h->d_xtram); cudaFree(h->d_counts); cudaFree(h->d_wb);
+    cudaFree(h->d_itram); cudaFree(h->d_xtram); cudaFree(h->d_counts); cudaFree(h->d_wb); cudaFree(h->d_latch_ch); cudaFree(h->d_reg_map);
     h->d_gpr = nullptr; h->d_acc = nullptr; h->d_lfsr = nullptr; h->d_latch = nullptr; h->d_ptrs = nullptr;
-    h->d_itram = nullptr; h->d_xtram = nullptr; h->d_counts = nullptr; h->d_wb = nullptr;
+    h->d_itram = nullptr; h->d_xtram = nullptr; h->d_counts = nullptr; h->d_wb = nullptr; h->d_latch_ch = nullptr; h->d_reg_map = nullptr;
 }
 
 typedef void (*KernelFn)(const Params);
@@ -290,7 +346,7 @@ KernelFn pick_kernel(int K, bool skip, bool ext) {
 
 // Geometry of one launch: contexts per thread, block size, time split.
 int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_cs, size_t out_cs, int n_samples, Launch& L) {
-    const int N = h->N, C = h->C, nr = (int)h->regs.size();
+    const int N = h->N, C = h->C, nr = (int)h->reg_map.size();
     auto aligned = [&](int K) {
         const size_t a = (size_t)K * 4;
         return N % K == 0 && ((uintptr_t)d_in % a) == 0 && ((uintptr_t)d_out % a) == 0 &&
@@ -333,37 +389,49 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
 
 int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, size_t out_cs, int n_samples, cudaStream_t st) {
     if (n_samples == 0) return FX8010_OK;
-    if (h->encode_dirty) {
-        encode(h);
-        FX_CUDA(h, cudaMemcpyToSymbolAsync(c_prog, h->h_prog, sizeof(uint4) * (h->instrs.size() + 1),
-                                           sizeof(uint4) * (size_t)(MAX_INSTR + 1) * h->slot, cudaMemcpyHostToDevice, st));
-        // h_prog is reused by the next encode: make sure the copy has left the pinned buffer
-        FX_CUDA(h, cudaStreamSynchronize(st));
-        h->encode_dirty = false;
-    }
     // per-launch executed-instruction counters are 32-bit: split very long batches
     const long long per_sample = (long long)h->instrs.size() * FX8010_MAX_PASSES;
     const int max_samples = (int)std::max<long long>(1, std::min<long long>(0x7fffffffLL, 0xffffffffLL / per_sample));
     for (int s0 = 0; s0 < n_samples; s0 += max_samples) {
         const int ns = std::min(max_samples, n_samples - s0);
+        if (h->encode_dirty) { select_tables(h); h->plan_key.ns = -1; }
         Launch L;
         const float* in = d_in ? d_in + (size_t)s0 * h->N : nullptr;
         float* out = d_out + (size_t)s0 * h->N;
-        const int rc = plan_launch(h, in, out, in_cs, out_cs, ns, L);
-        if (rc) return rc;
+        // the plan depends on the batch length and on how far the buffers are aligned
+        const unsigned align = (unsigned)(((uintptr_t)in | (uintptr_t)out | (uintptr_t)(in_cs * 4) | (uintptr_t)(out_cs * 4)) & 15u) | (in ? 16u : 0u);
+        if (h->plan_key.ns == ns && h->plan_key.align == align) L = h->plan;
+        else {
+            const int rc = plan_launch(h, in, out, in_cs, out_cs, ns, L);
+            if (rc) return rc;
+            h->plan = L; h->plan_key.ns = ns; h->plan_key.align = align;
+        }
+        if (h->encode_dirty || h->enc_K != L.K || h->enc_B != L.B) {
+            // the previous upload must have left the pinned buffer before it is rewritten
+            FX_CUDA(h, cudaStreamSynchronize(st));
+            if (h->last_stream && h->last_stream != st) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));
+            encode(h, L.K, L.B);
+            FX_CUDA(h, cudaMemcpyToSymbolAsync(c_prog, h->h_prog, sizeof(uint4) * 2 * (h->n_exec + 1),
+                                               sizeof(uint4) * (size_t)SLOT_WORDS * h->slot, cudaMemcpyHostToDevice, st));
+            FX_CUDA(h, cudaMemcpyAsync(h->d_latch_ch, h->latch_ch.data(), sizeof(uint32_t) * h->latch_ch.size(), cudaMemcpyHostToDevice, st));
+            FX_CUDA(h, cudaStreamSynchronize(st));
+            h->encode_dirty = false;
+        }
         Params p = {};
         p.gpr = h->d_gpr; p.acc = h->d_acc; p.lfsr = h->d_lfsr; p.latch = h->d_latch; p.ptrs = h->d_ptrs;
         p.itram = h->d_itram; p.xtram = h->d_xtram; p.counts = h->d_counts; p.rt_flags = h->d_flags;
-        p.wb_regs = h->d_wb; p.tabs = h->d_tabs;
+        p.reg_map = h->d_reg_map; p.wb_regs = h->d_wb; p.latch_ch = h->d_latch_ch; p.tabs = h->d_tabs;
         p.in = in; p.out = out; p.in_cstride = in_cs; p.out_cstride = out_cs;
         p.n_samples = ns; p.seg_len = L.seg_len; p.n_seg = L.n_seg;
-        p.N = h->N; p.C = h->C; p.n_regs = (int)h->regs.size(); p.n_instrs = (int)h->instrs.size();
+        p.N = h->N; p.C = h->C; p.n_regs = (int)h->reg_map.size(); p.n_instrs = (int)h->instrs.size();
         p.n_wb = (int)h->wb.size(); p.slot = h->slot;
+        p.n_exec = h->n_exec; p.n_latch_ch = (int)h->latch_ch.size();
         p.itram_size = h->itram_size; p.xtram_size = h->xtram_size;
         p.n_smem_tabs = h->n_smem_tabs;
         for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
         KernelFn fn = pick_kernel(L.K, h->has_skip, h->has_ext);
-        FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        bool& attr = h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][h->has_skip ? 1 : 0][h->has_ext ? 1 : 0];
+        if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
         fn<<<dim3(L.grid_x, L.n_seg), L.B, L.smem, st>>>(p);
         FX_CUDA(h, cudaGetLastError());
         h->info.kernel_launches++;
@@ -414,7 +482,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
         ok = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaMallocHost(&h->h_prog, sizeof(uint4) * (MAX_INSTR + 1)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&h->h_prog, sizeof(uint4) * SLOT_WORDS) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_flags, sizeof(unsigned int)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_tabs, sizeof(TableEntry) * 2 * FX8010_TABLE_COUNT * FX8010_TABLE_ENTRIES) == cudaSuccess;
     if (!ok) {
@@ -550,6 +618,9 @@ int fx8010_gpu_load_program(fx8010_gpu* h, const fx8010_program_image* im) {
     for (size_t r = 0; r < nr; ++r) h->reg_value[r] = im->regs[r].init_value;
     analyse(h);
     FX_CUDA(h, cudaMalloc(&h->d_wb, sizeof(uint32_t) * std::max<size_t>(1, h->wb.size())));
+    FX_CUDA(h, cudaMalloc(&h->d_latch_ch, sizeof(uint32_t) * 256));
+    FX_CUDA(h, cudaMalloc(&h->d_reg_map, sizeof(uint32_t) * h->reg_map.size()));
+    FX_CUDA(h, cudaMemcpy(h->d_reg_map, h->reg_map.data(), sizeof(uint32_t) * h->reg_map.size(), cudaMemcpyHostToDevice));
     if (!h->wb.empty()) FX_CUDA(h, cudaMemcpy(h->d_wb, h->wb.data(), sizeof(uint32_t) * h->wb.size(), cudaMemcpyHostToDevice));
     FX_CUDA(h, cudaDeviceSynchronize());
     h->encode_dirty = true;

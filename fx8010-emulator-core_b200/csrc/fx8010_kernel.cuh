@@ -28,25 +28,33 @@ enum Uop : uint32_t {
     U_LIMITN, U_LOG, U_EXP, U_INTERP, U_SKIP, U_IREAD, U_IWRITE, U_XREAD, U_XWRITE, U_NOP, U_END
 };
 
-// flag bits (word0 bits 8..15)
+// flag bits (word0 bits 8..23)
 constexpr uint32_t F_PRE_A = 1u << 8;    // A <- in[in_ch]   (source/FX8010.cpp:1055)
 constexpr uint32_t F_PRE_X = 1u << 9;    // X <- in[in_ch]   (:1057, uses A's IOIndex)
 constexpr uint32_t F_PRE_Y = 1u << 10;   // Y <- in[in_ch]   (:1059)
-constexpr uint32_t F_NOISE = 1u << 11;   // reg[aux] <- whitenoise()  (:1063-1071)
+constexpr uint32_t F_NOISE = 1u << 11;   // noise register <- whitenoise()  (:1063-1071)
 constexpr uint32_t F_OUT = 1u << 12;     // latch[out_ch] <- R after the instruction (:1229-1233)
 constexpr uint32_t F_CCR = 1u << 13;     // CCR value is observable: materialise it (:211-232)
-constexpr uint32_t F_TAB_SMEM = 1u << 14; // LOG/EXP: literal selector, table staged in shared memory (aux = slot)
-constexpr uint32_t F_TAB_IMM = 1u << 15;  // LOG/EXP: literal selector, table in global memory (aux = op*32+sel)
+constexpr uint32_t F_TAB_SMEM = 1u << 14; // LOG/EXP: literal selector, table staged in shared memory
+constexpr uint32_t F_TAB_IMM = 1u << 15;  // LOG/EXP: literal selector, table in global memory
+constexpr uint32_t F_OUT_DIRECT = 1u << 16; // SKIP-free programs: the last writer of its channel in program order
+                                            // stores R straight to the output block (no latch round trip)
 constexpr uint32_t F_PRE_ANY = F_PRE_A | F_PRE_X | F_PRE_Y;
 
-// 16-byte decoded instruction:
-//   w0: uop[0:8) flags[8:16) in_ch[16:24) out_ch[24:32)
-//   w1: r | a << 16        w2: x | y << 16        w3: noise target register | table slot or id << 16
+// 32-byte decoded instruction (two uint4 words).  All operand locations are ready-made BYTE offsets
+// into the thread's shared-memory column (register r of thread t lives at column(t) + r * RS * 4 with
+// RS = blockDim.x * K; the output latches and the input stages follow the registers in the same
+// column), so an operand fetch is one add and one LDS:
+//   A: { uop[0:8) | flags[8:24) | output channel[24:32),  R offset,  A offset,  X offset }
+//   B: { Y offset,  noise-register offset[0:24) | table slot or id[24:32),
+//        input-stage offset of the preload channel,  latch offset of the output channel }
+// The encoding depends on the launch geometry (RS) and is redone by the host when that changes.
 constexpr int MAX_INSTR = FX8010_MAX_INSTRUCTIONS;
-constexpr int PROG_SLOTS = 3;            // live programs per device (one slot per handle)
-__constant__ uint4 c_prog[PROG_SLOTS][MAX_INSTR + 1];
+constexpr int PROG_SLOTS = 2;            // live programs per device (one slot per handle)
+constexpr int SLOT_WORDS = 2 * (MAX_INSTR + 1);
+__constant__ uint4 c_prog[PROG_SLOTS][SLOT_WORDS];
 
-constexpr int CHUNK = 8;                 // samples per cp.async stage
+constexpr int CHUNK = 4;                 // samples per cp.async stage
 constexpr int MAX_SMEM_TABLES = 2;       // LOG/EXP tables replicated into shared memory
 constexpr int TAB_REPL = 8;              // replicas: one per lane of a 128-bit access phase
 constexpr int TAB_SMEM_BYTES = FX8010_TABLE_ENTRIES * TAB_REPL * 16;   // 8 KiB per table
@@ -64,7 +72,10 @@ struct Params {
     float* xtram;               // [xtram_size][N]
     unsigned long long* counts; // [N]
     unsigned int* rt_flags;     // 1 word
-    const uint32_t* wb_regs;    // registers the program may write (write-back list)
+    const uint32_t* reg_map;    // [n_regs] shared-memory row -> register index in the state arrays (only the
+                                // registers the program refers to get a row)
+    const uint32_t* wb_regs;    // rows the program may write (write-back list)
+    const uint32_t* latch_ch;   // output channels still served from the latch at the end of a sample period
     const TableEntry* tabs;     // [2][32][64]  LOG then EXP
     // I/O
     const float* in;            // element (c, s, i) at in[c * in_cstride + s * N + i]
@@ -74,7 +85,9 @@ struct Params {
     int seg_len;                // samples per time segment (== S when serial)
     int n_seg;
     // geometry
-    int N, C, n_regs, n_instrs, n_wb, slot;
+    int N, C, n_regs, n_instrs, n_wb, slot;   // n_regs = shared-memory rows
+    int n_exec;                 // encoded instructions (END/NOP are dropped for SKIP-free programs)
+    int n_latch_ch;             // entries of latch_ch
     int itram_size, xtram_size;
     int n_smem_tabs;            // tables staged in shared memory
     int smem_tab_id[MAX_SMEM_TABLES];   // op*32 + selector
@@ -136,10 +149,14 @@ __device__ __forceinline__ int32_t logic_ops(float fa, float fx, float fy) {
 
 // linearInterpolate() index: static_cast<int>((x - x_min) / step), source/FX8010.cpp:285-286.
 // (x + 1.0) * 31.5 in double gives the same integer as (x + 1.0) / (2.0/63) for every binary32 x in
-// [-1, 1] (exhaustively checked, tests/test_oracle.py::test_table_index_formula and the GPU sweep);
-// outside it only the clamp matters.  cvttsd2si overflow / NaN -> INT_MIN -> clamped to 0 (rule U6).
-__device__ __forceinline__ int table_index(double xd) {
-    const double q = __dmul_rn(__dadd_rn(xd, 1.0), 31.5);
+// [-1, 1] (exhaustively checked in C, sampled in tests/test_oracle.py::test_table_index_formula, swept
+// on the GPU by test_table_sweep_all_selectors); there the result is already inside 0..63.
+__device__ __forceinline__ int table_index_inrange(double xd) {
+    return __double2int_rz(__dmul_rn(__dadd_rn(xd, 1.0), 31.5));
+}
+// Outside [-1, 1] (rule U6) the reference's index is clamped; cvttsd2si overflow / NaN -> INT_MIN -> 0.
+__device__ __noinline__ int table_index_wild(float a) {
+    const double q = __dmul_rn(__dadd_rn((double)a, 1.0), 31.5);
     int i = __double2int_rz(q);
     i = min(max(i, 0), FX8010_TABLE_ENTRIES - 1);
     return (q < 2147483648.0) ? i : 0;
@@ -151,7 +168,6 @@ __device__ __forceinline__ float table_finish(double xd, int i, double y1, doubl
     return __double2float_rn(__dadd_rn(__dmul_rn(slope, __dsub_rn(xd, x1)), y1));
 }
 
-__device__ __forceinline__ void cp_async_bytes(void* smem, const void* gmem, int bytes_tag) {}
 template <int BYTES> __device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
     if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -161,11 +177,15 @@ template <int BYTES> __device__ __forceinline__ void cp_async(void* smem, const 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Shared-memory bytes one block needs (host and device agree through this one formula).
+// Shared-memory layout of one block (host and device agree through these formulas):
+//   [ tables ][ registers n_regs ][ latches C ][ input stages 2 x C x CHUNK ]   (the last three per column)
 __host__ __device__ inline size_t smem_bytes(int n_regs, int C, int B, int K, int n_smem_tabs) {
     return (size_t)n_smem_tabs * TAB_SMEM_BYTES +
            (size_t)B * K * sizeof(float) * ((size_t)n_regs + C + 2 * (size_t)C * CHUNK);
 }
+__host__ __device__ inline uint32_t reg_offset(int r, int RS) { return (uint32_t)r * RS * 4u; }
+__host__ __device__ inline uint32_t latch_offset(int n_regs, int c, int RS) { return (uint32_t)(n_regs + c) * RS * 4u; }
+__host__ __device__ inline uint32_t stage_offset(int n_regs, int C, int c, int RS) { return (uint32_t)(n_regs + C + c * CHUNK) * RS * 4u; }
 
 // ---- the kernel ------------------------------------------------------------------------------
 //
@@ -187,13 +207,15 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
     const int s_begin = seg * p.seg_len;
     const int s_end = min(p.n_samples, s_begin + p.seg_len);
     const uint4* const prog = c_prog[p.slot];
+    const int RS = B * K;                                  // register stride (floats)
 
     // shared-memory carve-up
     TableEntry* const s_tab = reinterpret_cast<TableEntry*>(smem_raw);                 // [n_smem_tabs][64][TAB_REPL]
-    float* const gpr = reinterpret_cast<float*>(smem_raw + (size_t)p.n_smem_tabs * TAB_SMEM_BYTES); // [n_regs][B][K]
-    float* const latch = gpr + (size_t)p.n_regs * B * K;                               // [C][B][K]
-    float* const in_stage = latch + (size_t)C * B * K;                                 // [2][C][CHUNK][B][K]
-    const int RS = B * K;                                                              // register stride (floats)
+    unsigned char* const col = smem_raw + (size_t)p.n_smem_tabs * TAB_SMEM_BYTES + (size_t)tid * K * 4;   // this thread's column
+    auto at = [&](uint32_t byte_off) { return reinterpret_cast<float*>(col + byte_off); };
+    const uint32_t latch0 = latch_offset(p.n_regs, 0, RS);
+    const uint32_t stage0 = stage_offset(p.n_regs, C, 0, RS);
+    const uint32_t stage_buf_bytes = (uint32_t)C * CHUNK * RS * 4u;
 
     // prefetch the first input chunk while the state loads
     const bool has_in = (p.in != nullptr);
@@ -203,7 +225,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
 #pragma unroll
                 for (int k = 0; k < CHUNK; ++k) {
                     const int s = min(s0 + k, p.n_samples - 1);
-                    cp_async<4 * K>(&in_stage[(((size_t)(buf * C + c) * CHUNK + k) * B + tid) * K],
+                    cp_async<4 * K>(at(stage0 + buf * stage_buf_bytes + (uint32_t)(c * CHUNK + k) * RS * 4u),
                                     &p.in[(size_t)c * p.in_cstride + (size_t)s * N + inst0]);
                 }
         }
@@ -215,14 +237,23 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
     // phase always reads bank group (l & 7): entry e of replica q lives at slot e * TAB_REPL + q.
     for (int t = 0; t < p.n_smem_tabs; ++t) {
         const TableEntry* src = p.tabs + (size_t)p.smem_tab_id[t] * FX8010_TABLE_ENTRIES;
+#pragma unroll 4
         for (int i = tid; i < FX8010_TABLE_ENTRIES * TAB_REPL; i += B)
             s_tab[t * FX8010_TABLE_ENTRIES * TAB_REPL + i] = src[i / TAB_REPL];
     }
 
-    float* const g = gpr + tid * K;                      // this thread's column: register r at g[r * RS]
-    for (int r = 0; r < p.n_regs; ++r) vstore<K>(g + r * RS, vload<K>(p.gpr + (size_t)r * N + inst0));
-    float* const lt = latch + tid * K;
-    for (int c = 0; c < C; ++c) vstore<K>(lt + c * RS, vload<K>(p.latch + (size_t)c * N + inst0));
+    {   // register rows: batches of four independent loads keep the startup off the L2 latency chain
+        int r = 0;
+        for (; r + 4 <= p.n_regs; r += 4) {
+            Vec<K> t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[j] = vload<K>(p.gpr + (size_t)p.reg_map[r + j] * N + inst0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vstore<K>(at(reg_offset(r + j, RS)), t[j]);
+        }
+        for (; r < p.n_regs; ++r) vstore<K>(at(reg_offset(r, RS)), vload<K>(p.gpr + (size_t)p.reg_map[r] * N + inst0));
+    }
+    for (int c = 0; c < C; ++c) vstore<K>(at(latch0 + (uint32_t)c * RS * 4u), vload<K>(p.latch + (size_t)c * N + inst0));
 
     float acc_f[K];
     double acc_d[K];
@@ -245,26 +276,28 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
     __syncthreads();                  // s_tab visible (the only block-wide dependency)
 
     const int lane_rep = tid & (TAB_REPL - 1);
+    float* out_s = p.out + (size_t)s_begin * N + inst0;   // this thread's slot in the current output row
     int buf = 0;
     for (int s0 = s_begin; s0 < s_end; s0 += CHUNK) {
         if (s0 + CHUNK < s_end) { stage_inputs(buf ^ 1, s0 + CHUNK); cp_async_wait<1>(); }
         else cp_async_wait<0>();
-        const float* const stage = in_stage + (size_t)buf * C * CHUNK * RS + tid * K;
         const int kn = min(CHUNK, s_end - s0);
-        for (int ks = 0; ks < kn; ++ks) {
+        for (int ks = 0; ks < kn; ++ks, out_s += N) {
             // ---- one sample period: FX8010::process, source/FX8010.cpp:1023-1249 ----
-            // The final CCR must be in the register file when the batch ends (getRegisterValue("ccr")).
-            const bool force_ccr = (s0 + ks == p.n_samples - 1);
+            // The final CCR / latch must be in shared memory when the batch ends (state write-back).
+            const bool last_sample = (s0 + ks == p.n_samples - 1);
+            const uint32_t stage_s = buf * stage_buf_bytes + (uint32_t)ks * RS * 4u;
             bool saw_end[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) { skip[k] = 0; saw_end[k] = false; }
             int pass = 0;
             do {
-                uint4 wn = prog[0];
-                for (int pc = 0; pc < p.n_instrs; ++pc) {
-                    const uint4 w = wn;
-                    wn = prog[pc + 1];                                // slot is padded with one extra word
-                    const uint32_t uop = w.x & 0xffu;
+                uint4 nA = prog[0], nB = prog[1];
+                for (int pc = 0; pc < p.n_exec; ++pc) {
+                    const uint4 wA = nA, wB = nB;
+                    nA = prog[2 * pc + 2]; nB = prog[2 * pc + 3];     // the slot is padded with one extra instruction
+                    const uint32_t w0 = wA.x;
+                    const uint32_t uop = w0 & 0xffu;
                     bool act[K];
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
@@ -273,33 +306,33 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                             skip[k] = (skip[k] > 0) ? skip[k] - 1 : 0; // a negative count skips exactly one
                         } else act[k] = true;
                     }
-                    float* const pr = g + (w.y & 0xffffu) * RS;
-                    float* const pa = g + (w.y >> 16) * RS;
-                    float* const px = g + (w.z & 0xffffu) * RS;
-                    float* const py = g + (w.z >> 16) * RS;
-                    if (w.x & F_PRE_ANY) {                            // :1053-1061
+                    float* const pr = at(wA.y);
+                    float* const pa = at(wA.z);
+                    float* const px = at(wA.w);
+                    float* const py = at(wB.x);
+                    if (w0 & F_PRE_ANY) {                             // :1053-1061
                         Vec<K> v;
-                        if (has_in) v = vload<K>(stage + (size_t)(((w.x >> 16) & 0xffu) * CHUNK + ks) * RS);
+                        if (has_in) v = vload<K>(at(wB.z + stage_s));
                         else {
 #pragma unroll
                             for (int k = 0; k < K; ++k) v[k] = 0.0f;
                         }
                         if (!SKIP) {
-                            if (w.x & F_PRE_A) vstore<K>(pa, v);
-                            if (w.x & F_PRE_X) vstore<K>(px, v);
-                            if (w.x & F_PRE_Y) vstore<K>(py, v);
+                            if (w0 & F_PRE_A) vstore<K>(pa, v);
+                            if (w0 & F_PRE_X) vstore<K>(px, v);
+                            if (w0 & F_PRE_Y) vstore<K>(py, v);
                         } else {
 #pragma unroll
                             for (int k = 0; k < K; ++k)
                                 if (act[k]) {
-                                    if (w.x & F_PRE_A) pa[k] = v[k];
-                                    if (w.x & F_PRE_X) px[k] = v[k];
-                                    if (w.x & F_PRE_Y) py[k] = v[k];
+                                    if (w0 & F_PRE_A) pa[k] = v[k];
+                                    if (w0 & F_PRE_X) px[k] = v[k];
+                                    if (w0 & F_PRE_Y) py[k] = v[k];
                                 }
                         }
                     }
-                    if (EXT && (w.x & F_NOISE)) {                     // :1063-1071, whitenoise :993-1000
-                        float* const pn = g + (w.w & 0xffffu) * RS;
+                    if (EXT && (w0 & F_NOISE)) {                      // :1063-1071, whitenoise :993-1000
+                        float* const pn = at(wB.y & 0xffffffu);
 #pragma unroll
                         for (int k = 0; k < K; ++k)
                             if (act[k]) {
@@ -351,21 +384,28 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                         FX_EACH { r[k] = (a[k] < y[k]) ? x[k] : y[k]; FX_ACC(r[k]); } break; }
                     case U_LOG:                                       // :1113-1119
                     case U_EXP: { FX_LOAD_A;                          // :1120-1125, linearInterpolate :283-296
-                        if (w.x & F_TAB_SMEM) {
-                            const TableEntry* const tb = s_tab + (size_t)((w.w >> 16) & 0xffu) * (FX8010_TABLE_ENTRIES * TAB_REPL) + lane_rep;
+                        int idx[K];
+                        bool wild = false;
+                        FX_EACH { wild |= !(fabsf(a[k]) <= 1.0f); }
+                        if (!wild) { FX_EACH { idx[k] = table_index_inrange((double)a[k]); } }
+                        else {                                        // rule U6: clamp and flag (rare, may diverge)
                             FX_EACH {
-                                if (!(a[k] >= -1.0f && a[k] <= 1.0f) && act[k]) flags |= FX8010_RT_TABLE_RANGE;
-                                const double xd = (double)a[k];
-                                const int i = table_index(xd);
-                                const TableEntry e = tb[i * TAB_REPL];
-                                r[k] = table_finish(xd, i, e.y1, e.slope); FX_ACC(r[k]);
+                                idx[k] = table_index_wild(a[k]);
+                                if (!(fabsf(a[k]) <= 1.0f) && act[k]) flags |= FX8010_RT_TABLE_RANGE;
+                            }
+                        }
+                        if (w0 & F_TAB_SMEM) {
+                            const TableEntry* const tb = s_tab + (size_t)(wB.y >> 24) * (FX8010_TABLE_ENTRIES * TAB_REPL) + lane_rep;
+                            FX_EACH {
+                                const TableEntry e = tb[idx[k] * TAB_REPL];
+                                r[k] = table_finish((double)a[k], idx[k], e.y1, e.slope); FX_ACC(r[k]);
                             }
                         } else {
                             Vec<K> x;
-                            if (!(w.x & F_TAB_IMM)) x = vload<K>(px);
+                            if (!(w0 & F_TAB_IMM)) x = vload<K>(px);
                             FX_EACH {
                                 int tsel;
-                                if (w.x & F_TAB_IMM) tsel = (int)((w.w >> 16) & 0xffu);
+                                if (w0 & F_TAB_IMM) tsel = (int)(wB.y >> 24);
                                 else {
                                     int32_t sel = cvt_x86(x[k]);
                                     if (sel < 0 || sel > FX8010_TABLE_COUNT - 1) {
@@ -374,11 +414,8 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                                     }
                                     tsel = (uop == U_EXP ? FX8010_TABLE_COUNT : 0) + sel;
                                 }
-                                if (!(a[k] >= -1.0f && a[k] <= 1.0f) && act[k]) flags |= FX8010_RT_TABLE_RANGE;
-                                const double xd = (double)a[k];
-                                const int i = table_index(xd);
-                                const double2 e = __ldg(reinterpret_cast<const double2*>(p.tabs + tsel * FX8010_TABLE_ENTRIES + i));
-                                r[k] = table_finish(xd, i, e.x, e.y); FX_ACC(r[k]);
+                                const double2 e = __ldg(reinterpret_cast<const double2*>(p.tabs + tsel * FX8010_TABLE_ENTRIES + idx[k]));
+                                r[k] = table_finish((double)a[k], idx[k], e.x, e.y); FX_ACC(r[k]);
                             }
                         }
                         break; }
@@ -388,7 +425,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                             const float t = __double2float_rn(d); FX_ACC(t); r[k] = sat1(t);
                         } break; }
                     case U_SKIP:                                      // :1175-1179
-                        if (SKIP) { FX_LOAD_X; FX_LOAD_Y; const Vec<K> c = vload<K>(g);
+                        if (SKIP) { FX_LOAD_X; FX_LOAD_Y; const Vec<K> c = vload<K>(at(0));
                             FX_EACH { if (act[k] && __int2float_rn(cvt_x86(x[k])) == c[k]) skip[k] = cvt_x86(y[k]); } }
                         writes_r = false; break;
                     case U_IREAD: case U_XREAD:                       // :1190-1193 / :1202-1205, readSmallDelay :934-956
@@ -434,16 +471,21 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                     if (writes_r) {
                         if (!SKIP) vstore<K>(pr, r);
                         else { FX_EACH { if (act[k]) pr[k] = r[k]; } }
-                        if ((w.x & F_CCR) || force_ccr) {             // setCCR :211-232 (after the R store: R may be ccr)
-                            if (!SKIP) { Vec<K> c; FX_EACH { c[k] = ccr_of(r[k]); } vstore<K>(g, c); }
-                            else { FX_EACH { if (act[k]) g[k] = ccr_of(r[k]); } }
+                        if ((w0 & F_CCR) || last_sample) {            // setCCR :211-232 (after the R store: R may be ccr)
+                            if (!SKIP) { Vec<K> c; FX_EACH { c[k] = ccr_of(r[k]); } vstore<K>(at(0), c); }
+                            else { FX_EACH { if (act[k]) at(0)[k] = ccr_of(r[k]); } }
                         }
                     }
                     if (SKIP) { FX_EACH { count[k] += act[k] ? 1u : 0u; } }   // :1222
-                    if (w.x & F_OUT) {                                // :1229-1233 (after EVERY executed instruction)
-                        float* const pl = lt + (w.x >> 24) * RS;
-                        if (!SKIP) vstore<K>(pl, vload<K>(pr));
-                        else { FX_EACH { if (act[k]) pl[k] = pr[k]; } }
+                    if (w0 & F_OUT) {                                 // :1229-1233 (after EVERY executed instruction)
+                        if (!SKIP && (w0 & F_OUT_DIRECT)) {
+                            // R was just written by this instruction and nothing later in the sample period
+                            // touches the channel: the value is the period's output (:1248)
+                            const Vec<K> v = vload<K>(pr);
+                            if (valid) vstore<K>(out_s + (size_t)(w0 >> 24) * p.out_cstride, v);
+                            if (last_sample) vstore<K>(at(wB.w), v);
+                        } else if (!SKIP) vstore<K>(at(wB.w), vload<K>(pr));
+                        else { float* const pl = at(wB.w); FX_EACH { if (act[k]) pl[k] = pr[k]; } }
                     }
                 }
                 ++pass;
@@ -460,8 +502,10 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                 if (!__any_sync(0xffffffffu, again)) break;
             } while (true);
             if (valid)                                                // :1248 — coalesced, lane = K adjacent instances
-                for (int c = 0; c < C; ++c)
-                    vstore<K>(p.out + (size_t)c * p.out_cstride + (size_t)(s0 + ks) * N + inst0, vload<K>(lt + c * RS));
+                for (int j = 0; j < p.n_latch_ch; ++j) {
+                    const uint32_t c = p.latch_ch[j];
+                    vstore<K>(out_s + (size_t)c * p.out_cstride, vload<K>(at(latch0 + c * RS * 4u)));
+                }
         }
         buf ^= 1;
     }
@@ -470,8 +514,8 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
     // ---- write the state back (the last time segment carries the final state) ----
     if (flags) atomicOr(p.rt_flags, flags);
     if (!valid || !last_seg) return;
-    for (int i = 0; i < p.n_wb; ++i) { const uint32_t r = p.wb_regs[i]; vstore<K>(p.gpr + (size_t)r * N + inst0, vload<K>(g + r * RS)); }
-    for (int c = 0; c < C; ++c) vstore<K>(p.latch + (size_t)c * N + inst0, vload<K>(lt + c * RS));
+    for (int i = 0; i < p.n_wb; ++i) { const uint32_t r = p.wb_regs[i]; vstore<K>(p.gpr + (size_t)p.reg_map[r] * N + inst0, vload<K>(at(reg_offset(r, RS)))); }
+    for (int c = 0; c < C; ++c) vstore<K>(p.latch + (size_t)c * N + inst0, vload<K>(at(latch0 + (uint32_t)c * RS * 4u)));
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         p.acc[inst0 + k] = acc_is_f[k] ? (double)acc_f[k] : acc_d[k];

@@ -68,7 +68,7 @@ enum fx8010_runtime_flag {
 };
 
 #define FX8010_MAX_PASSES        8      /* program re-runs per sample while END stays skipped     */
-#define FX8010_MAX_INSTRUCTIONS  1024   /* decoded programs live in __constant__ memory (3 slots x 16 KiB) */
+#define FX8010_MAX_INSTRUCTIONS  1000   /* decoded programs live in __constant__ memory (2 slots x 32 KiB) */
 #define FX8010_TABLE_COUNT       32     /* reference source/FX8010.cpp:63                          */
 #define FX8010_TABLE_ENTRIES     64     /* 32 mirrored + 32 generated, source/FX8010.cpp:73-105    */
 #define FX8010_LFSR_SEED1        0x70f4f854u /* include/FX8010.h:290 */
