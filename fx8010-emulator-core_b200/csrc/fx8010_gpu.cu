@@ -49,6 +49,8 @@ struct fx8010_gpu {
     std::vector<float> reg_value;
     std::vector<uint32_t> wb;                    // shared-memory rows to write back
     std::vector<uint32_t> reg_map;               // row -> register index
+    std::vector<uint32_t> load_rows;             // rows loaded from the state arrays at kernel start
+    bool load_latch = true, load_acc = true;
     std::vector<int> row_of;                     // register index -> row (-1: the program never refers to it)
     bool has_skip = false, has_ext = false, stateless = false;
     bool encode_dirty = true;
@@ -58,13 +60,17 @@ struct fx8010_gpu {
     uint4* h_prog = nullptr;                     // pinned, SLOT_WORDS words
     int enc_K = 0, enc_B = 0;                    // geometry the uploaded encoding was made for
     PlanKey plan_key; Launch plan = {};          // last launch plan (reused while nothing relevant changes)
-    bool attr_set[3][2][2] = {};                 // MaxDynamicSharedMemorySize set for kernel <K, SKIP, EXT>
+    bool attr_set[3][2][2] = {};
+    // previous launch on last_stream: the buffers it writes / reads (for the PDL overlap decision)
+    struct Span { const char* out_lo = nullptr; const char* out_hi = nullptr; const char* in_lo = nullptr; const char* in_hi = nullptr;
+                  cudaStream_t stream = nullptr; bool valid = false; } prev[2];   // [0] = latest
+    int use_pdl = 1;                 // MaxDynamicSharedMemorySize set for kernel <K, SKIP, EXT>
     int n_exec = 0;                              // encoded instructions
     std::vector<uint32_t> latch_ch;              // channels served from the latch every sample period
     // device state
     float* d_gpr = nullptr; double* d_acc = nullptr; uint32_t* d_lfsr = nullptr; float* d_latch = nullptr;
     int32_t* d_ptrs = nullptr; float* d_itram = nullptr; float* d_xtram = nullptr;
-    unsigned long long* d_counts = nullptr; unsigned int* d_flags = nullptr; uint32_t* d_wb = nullptr; uint32_t* d_latch_ch = nullptr; uint32_t* d_reg_map = nullptr;
+    unsigned long long* d_counts = nullptr; unsigned int* d_flags = nullptr; uint32_t* d_wb = nullptr; uint32_t* d_latch_ch = nullptr; uint32_t* d_reg_map = nullptr; uint32_t* d_load_rows = nullptr;
     TableEntry* d_tabs = nullptr;
     // streams
     cudaStream_t last_stream = nullptr;
@@ -176,7 +182,8 @@ void analyse(fx8010_gpu* h) {
         const Uop u = uop_of(h, in);
         if (u == U_END || u == U_NOP) continue;
         if (writes_r(u) || h->regs[in.r].type == FX_REG_OUTPUT) used[in.r] = 1;   // OUTPUT R feeds the latch after any op
-        used[in.a] = used[in.x] = used[in.y] = 1;
+        used[in.a] = used[in.x] = 1;
+        if (u != U_LOG && u != U_EXP) used[in.y] = 1;            // LOG/EXP never read Y (the sign operand, :1114 TODO)
     }
     h->reg_map.clear(); h->row_of.assign(nr, -1); h->wb.clear();
     for (int r = 0; r < nr; ++r)
@@ -206,6 +213,23 @@ void analyse(fx8010_gpu* h) {
             if (writes_r(u)) { defined[in.r] = 1; defined[0] = 1; }
         }
     }
+    // What the kernel has to fetch at start.  A stateless program overwrites every register it
+    // writes before reading it, so only the rows it never writes carry information in; likewise the
+    // latches when every channel has a writer, and the accumulator when some instruction sets it.
+    h->load_rows.clear();
+    bool acc_writer = false;
+    std::vector<uint8_t> ch_written(h->C, 0);
+    for (int i = 0; i < n; ++i) {
+        const Uop u = uop_of(h, h->instrs[i]);
+        if (writes_r(u) && u != U_MACMV && u != U_ANDXOR) acc_writer = true;
+        if (writes_r(u) && h->regs[h->instrs[i].r].type == FX_REG_OUTPUT) ch_written[h->regs[h->instrs[i].r].io_index] = 1;
+    }
+    bool all_ch = true;
+    for (int c = 0; c < h->C; ++c) all_ch = all_ch && ch_written[c];
+    for (size_t row = 0; row < h->reg_map.size(); ++row)
+        if (!h->stateless || !h->written[h->reg_map[row]]) h->load_rows.push_back((uint32_t)row);
+    h->load_latch = !(h->stateless && all_ch);
+    h->load_acc = !(h->stateless && acc_writer);
 }
 
 // LOG/EXP with a literal selector (a register the program never writes and that holds one value in
@@ -286,7 +310,7 @@ void encode(fx8010_gpu* h, int K, int B) {
     std::vector<int> last_writer(C, -1);
     if (!h->has_skip)
         for (int i = 0; i < n; ++i)
-            if (h->regs[h->instrs[i].r].type == FX_REG_OUTPUT && uops[i] != U_END && uops[i] != U_NOP)
+            if (h->regs[h->instrs[i].r].type == FX_REG_OUTPUT && writes_r(uops[i]))
                 last_writer[h->regs[h->instrs[i].r].io_index] = i;
     h->latch_ch.clear();
     for (int c = 0; c < C; ++c) if (last_writer[c] < 0) h->latch_ch.push_back((uint32_t)c);
@@ -330,9 +354,9 @@ void encode(fx8010_gpu* h, int K, int B) {
 
 void free_state(fx8010_gpu* h) {
     cudaFree(h->d_gpr); cudaFree(h->d_acc); cudaFree(h->d_lfsr); cudaFree(h->d_latch); cudaFree(h->d_ptrs);
-    cudaFree(h->d_itram); cudaFree(h->d_xtram); cudaFree(h->d_counts); cudaFree(h->d_wb); cudaFree(h->d_latch_ch); cudaFree(h->d_reg_map);
+    cudaFree(h->d_itram); cudaFree(h->d_xtram); cudaFree(h->d_counts); cudaFree(h->d_wb); cudaFree(h->d_latch_ch); cudaFree(h->d_reg_map); cudaFree(h->d_load_rows);
     h->d_gpr = nullptr; h->d_acc = nullptr; h->d_lfsr = nullptr; h->d_latch = nullptr; h->d_ptrs = nullptr;
-    h->d_itram = nullptr; h->d_xtram = nullptr; h->d_counts = nullptr; h->d_wb = nullptr; h->d_latch_ch = nullptr; h->d_reg_map = nullptr;
+    h->d_itram = nullptr; h->d_xtram = nullptr; h->d_counts = nullptr; h->d_wb = nullptr; h->d_latch_ch = nullptr; h->d_reg_map = nullptr; h->d_load_rows = nullptr;
 }
 
 typedef void (*KernelFn)(const Params);
@@ -352,7 +376,7 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
         return N % K == 0 && ((uintptr_t)d_in % a) == 0 && ((uintptr_t)d_out % a) == 0 &&
                (in_cs * 4) % a == 0 && (out_cs * 4) % a == 0;
     };
-    const int min_seg = CHUNK;
+    const int min_seg = 4;
     const long max_seg = h->stateless ? std::max(1, n_samples / min_seg) : 1;
     const long want_threads = (long)h->num_sms * 512;
     int K = 4;
@@ -380,7 +404,6 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
         if (h->tune_seg) n_seg = h->tune_seg;
         n_seg = std::min(n_seg, max_seg);
         int seg_len = (int)((n_samples + n_seg - 1) / n_seg);
-        seg_len = (seg_len + CHUNK - 1) / CHUNK * CHUNK;
         L.seg_len = seg_len;
         L.n_seg = (n_samples + seg_len - 1) / seg_len;
     }
@@ -420,20 +443,43 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
         Params p = {};
         p.gpr = h->d_gpr; p.acc = h->d_acc; p.lfsr = h->d_lfsr; p.latch = h->d_latch; p.ptrs = h->d_ptrs;
         p.itram = h->d_itram; p.xtram = h->d_xtram; p.counts = h->d_counts; p.rt_flags = h->d_flags;
-        p.reg_map = h->d_reg_map; p.wb_regs = h->d_wb; p.latch_ch = h->d_latch_ch; p.tabs = h->d_tabs;
+        p.reg_map = h->d_reg_map; p.load_rows = h->d_load_rows; p.wb_regs = h->d_wb; p.latch_ch = h->d_latch_ch; p.tabs = h->d_tabs;
         p.in = in; p.out = out; p.in_cstride = in_cs; p.out_cstride = out_cs;
         p.n_samples = ns; p.seg_len = L.seg_len; p.n_seg = L.n_seg;
         p.N = h->N; p.C = h->C; p.n_regs = (int)h->reg_map.size(); p.n_instrs = (int)h->instrs.size();
         p.n_wb = (int)h->wb.size(); p.slot = h->slot;
         p.n_exec = h->n_exec; p.n_latch_ch = (int)h->latch_ch.size();
+        p.n_load = (int)h->load_rows.size(); p.load_latch = h->load_latch; p.load_acc = h->load_acc;
         p.itram_size = h->itram_size; p.xtram_size = h->xtram_size;
         p.n_smem_tabs = h->n_smem_tabs;
         for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
         KernelFn fn = pick_kernel(L.K, h->has_skip, h->has_ext);
         bool& attr = h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][h->has_skip ? 1 : 0][h->has_ext ? 1 : 0];
         if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
-        fn<<<dim3(L.grid_x, L.n_seg), L.B, L.smem, st>>>(p);
-        FX_CUDA(h, cudaGetLastError());
+        // Programmatic dependent launch: the kernel may start while the previous launch on this stream
+        // drains.  It can postpone its wait to the final state write-back when it reads nothing that
+        // launch writes: stateless program (start-up reads only rows nobody writes) and I/O buffers
+        // disjoint from the previous launch's.
+        const char* out_lo = (const char*)out; const char* out_hi = out_lo + sizeof(float) * ((size_t)(h->C - 1) * out_cs + (size_t)ns * h->N);
+        const char* in_lo = (const char*)in; const char* in_hi = in ? in_lo + sizeof(float) * ((size_t)(h->C - 1) * in_cs + (size_t)ns * h->N) : in_lo;
+        auto overlap = [](const char* a0, const char* a1, const char* b0, const char* b1) { return a0 < b1 && b0 < a1; };
+        // A late-waiting launch can still be running its sample loop while the launch TWO before it
+        // drains (it starts once every block of its predecessor has started), so both must be clear.
+        bool disjoint = true;
+        for (const fx8010_gpu::Span& q : h->prev)
+            disjoint = disjoint && q.valid && q.stream == st && !overlap(out_lo, out_hi, q.out_lo, q.out_hi) &&
+                       !overlap(in_lo, in_hi, q.out_lo, q.out_hi) && !overlap(out_lo, out_hi, q.in_lo, q.in_hi);
+        p.pdl_late_wait = (h->use_pdl && h->stateless && disjoint) ? 1 : 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(L.grid_x, L.n_seg); cfg.blockDim = dim3(L.B); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+        cudaLaunchAttribute attrs[1];
+        attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attrs; cfg.numAttrs = h->use_pdl ? 1 : 0;
+        FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
+        h->prev[1] = h->prev[0];
+        h->prev[0].out_lo = out_lo; h->prev[0].out_hi = out_hi; h->prev[0].in_lo = in_lo; h->prev[0].in_hi = in_hi;
+        h->prev[0].stream = st; h->prev[0].valid = true;
         h->info.kernel_launches++;
         h->info.last_grid = L.grid_x * L.n_seg; h->info.last_block = L.B; h->info.last_time_split = L.n_seg;
         h->info.last_smem_bytes = (int)L.smem;
@@ -492,6 +538,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     }
     h->tune_K = env_int("FX8010_TUNE_K"); h->tune_B = env_int("FX8010_TUNE_B");
     h->tune_seg = env_int("FX8010_TUNE_SEG"); h->tune_sub = env_int("FX8010_TUNE_SUB");
+    if (getenv("FX8010_NO_PDL")) h->use_pdl = 0;
     if (h->tune_K != 1 && h->tune_K != 2 && h->tune_K != 4) h->tune_K = 0;
     if (h->tune_B != 32 && h->tune_B != 64 && h->tune_B != 128) h->tune_B = 0;
     *out = h;
@@ -620,6 +667,8 @@ int fx8010_gpu_load_program(fx8010_gpu* h, const fx8010_program_image* im) {
     FX_CUDA(h, cudaMalloc(&h->d_wb, sizeof(uint32_t) * std::max<size_t>(1, h->wb.size())));
     FX_CUDA(h, cudaMalloc(&h->d_latch_ch, sizeof(uint32_t) * 256));
     FX_CUDA(h, cudaMalloc(&h->d_reg_map, sizeof(uint32_t) * h->reg_map.size()));
+    FX_CUDA(h, cudaMalloc(&h->d_load_rows, sizeof(uint32_t) * std::max<size_t>(1, h->load_rows.size())));
+    if (!h->load_rows.empty()) FX_CUDA(h, cudaMemcpy(h->d_load_rows, h->load_rows.data(), sizeof(uint32_t) * h->load_rows.size(), cudaMemcpyHostToDevice));
     FX_CUDA(h, cudaMemcpy(h->d_reg_map, h->reg_map.data(), sizeof(uint32_t) * h->reg_map.size(), cudaMemcpyHostToDevice));
     if (!h->wb.empty()) FX_CUDA(h, cudaMemcpy(h->d_wb, h->wb.data(), sizeof(uint32_t) * h->wb.size(), cudaMemcpyHostToDevice));
     FX_CUDA(h, cudaDeviceSynchronize());
@@ -685,9 +734,9 @@ int fx8010_gpu_process_batch_host(fx8010_gpu* h, const float* in, float* out, in
     if (!out || n_samples < 0) return fail(h, FX8010_ERR_ARG, "out is NULL or n_samples negative");
     if (n_samples == 0) return FX8010_OK;
     const size_t N = (size_t)h->N, C = (size_t)h->C;
-    // sub-block: ~8 MiB of samples per channel set, a multiple of the cp.async chunk
+    // sub-block: ~8 MiB of samples per channel set
     long sub = h->tune_sub ? h->tune_sub : (long)((8u << 20) / (4 * N * C));
-    sub = std::max<long>(CHUNK, sub / CHUNK * CHUNK);
+    sub = std::max<long>(8, sub / 8 * 8);
     sub = std::min<long>(sub, n_samples);
     const size_t need = C * (size_t)sub * N;
     if (need > h->stage_floats) {

@@ -7,8 +7,9 @@
 // diverges: a per-context skip counter turns into a write predicate.  The GPR file is a
 // structure-of-arrays tile in shared memory (gpr[reg][thread][K], one 4/8/16-byte access per
 // operand, bank-conflict free); accumulator, LFSR, TRAM pointers and counters live in hardware
-// registers.  Sample blocks stream HBM -> shared through double-buffered cp.async stages (one
-// 16-byte LDGSTS per thread and sample at K = 4) and go back with coalesced 16-byte stores.
+// registers.  Input samples stream HBM -> shared through a ring of cp.async stages that runs three
+// sample periods ahead (one 16-byte LDGSTS per thread and sample at K = 4); outputs go back with
+// coalesced 16-byte stores straight from registers.
 //
 // Semantics follow the reference's FX8010::process (reference source/FX8010.cpp:1023-1249) op by
 // op; every float/double operation uses an explicitly rounded intrinsic so nothing can be
@@ -54,7 +55,7 @@ constexpr int PROG_SLOTS = 2;            // live programs per device (one slot p
 constexpr int SLOT_WORDS = 2 * (MAX_INSTR + 1);
 __constant__ uint4 c_prog[PROG_SLOTS][SLOT_WORDS];
 
-constexpr int CHUNK = 4;                 // samples per cp.async stage
+constexpr int STAGE_DEPTH = 4;           // input ring: cp.async runs STAGE_DEPTH - 1 sample periods ahead
 constexpr int MAX_SMEM_TABLES = 2;       // LOG/EXP tables replicated into shared memory
 constexpr int TAB_REPL = 8;              // replicas: one per lane of a 128-bit access phase
 constexpr int TAB_SMEM_BYTES = FX8010_TABLE_ENTRIES * TAB_REPL * 16;   // 8 KiB per table
@@ -74,6 +75,7 @@ struct Params {
     unsigned int* rt_flags;     // 1 word
     const uint32_t* reg_map;    // [n_regs] shared-memory row -> register index in the state arrays (only the
                                 // registers the program refers to get a row)
+    const uint32_t* load_rows;  // rows whose initial value the program can see (a stateless program never reads the others)
     const uint32_t* wb_regs;    // rows the program may write (write-back list)
     const uint32_t* latch_ch;   // output channels still served from the latch at the end of a sample period
     const TableEntry* tabs;     // [2][32][64]  LOG then EXP
@@ -88,6 +90,11 @@ struct Params {
     int N, C, n_regs, n_instrs, n_wb, slot;   // n_regs = shared-memory rows
     int n_exec;                 // encoded instructions (END/NOP are dropped for SKIP-free programs)
     int n_latch_ch;             // entries of latch_ch
+    int n_load;                 // entries of load_rows
+    int load_latch, load_acc;   // the latches / the accumulator can be observed before the program rewrites them
+    int pdl_late_wait;          // programmatic dependent launch: 1 = this launch reads nothing the previous launch on
+                                // the stream writes until its own state write-back (stateless program, disjoint
+                                // buffers), so it only waits for that launch right before writing state
     int itram_size, xtram_size;
     int n_smem_tabs;            // tables staged in shared memory
     int smem_tab_id[MAX_SMEM_TABLES];   // op*32 + selector
@@ -124,7 +131,10 @@ __device__ __forceinline__ int32_t cvt_x86(float f) {
     return (f < 2147483648.0f) ? i : INT32_MIN; // fixes +overflow and NaN; -overflow saturates to INT_MIN already
 }
 // saturate(): source/FX8010.cpp:275-279 (NaN passes through)
-__device__ __forceinline__ float sat1(float v) { return (v >= 1.0f) ? 1.0f : ((v <= -1.0f) ? -1.0f : v); }
+__device__ __forceinline__ float sat1(float v) {
+    const float t = (v <= -1.0f) ? -1.0f : v;      // same result as the reference's nested ternary for every input
+    return (t >= 1.0f) ? 1.0f : t;                 // (v >= 1 -> t == v -> 1; NaN -> NaN), two FMNMX.NAN instead of three ops
+}
 // setCCR(): source/FX8010.cpp:211-232
 __device__ __forceinline__ float ccr_of(float r) {
     const float ar = fabsf(r);
@@ -178,14 +188,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // Shared-memory layout of one block (host and device agree through these formulas):
-//   [ tables ][ registers n_regs ][ latches C ][ input stages 2 x C x CHUNK ]   (the last three per column)
+//   [ tables ][ registers n_regs ][ latches C ][ input ring C x STAGE_DEPTH ]   (the last three per column)
 __host__ __device__ inline size_t smem_bytes(int n_regs, int C, int B, int K, int n_smem_tabs) {
     return (size_t)n_smem_tabs * TAB_SMEM_BYTES +
-           (size_t)B * K * sizeof(float) * ((size_t)n_regs + C + 2 * (size_t)C * CHUNK);
+           (size_t)B * K * sizeof(float) * ((size_t)n_regs + C + (size_t)C * STAGE_DEPTH);
 }
 __host__ __device__ inline uint32_t reg_offset(int r, int RS) { return (uint32_t)r * RS * 4u; }
 __host__ __device__ inline uint32_t latch_offset(int n_regs, int c, int RS) { return (uint32_t)(n_regs + c) * RS * 4u; }
-__host__ __device__ inline uint32_t stage_offset(int n_regs, int C, int c, int RS) { return (uint32_t)(n_regs + C + c * CHUNK) * RS * 4u; }
+__host__ __device__ inline uint32_t stage_offset(int n_regs, int C, int c, int RS) { return (uint32_t)(n_regs + C + c * STAGE_DEPTH) * RS * 4u; }
 
 // ---- the kernel ------------------------------------------------------------------------------
 //
@@ -209,51 +219,63 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
     const uint4* const prog = c_prog[p.slot];
     const int RS = B * K;                                  // register stride (floats)
 
+    // Programmatic dependent launch: let the next launch on the stream start filling SMs as this one
+    // drains; unless told otherwise, wait here for the previous launch (it may still be writing the
+    // state arrays or the buffers this one reads).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!p.pdl_late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+
     // shared-memory carve-up
     TableEntry* const s_tab = reinterpret_cast<TableEntry*>(smem_raw);                 // [n_smem_tabs][64][TAB_REPL]
     unsigned char* const col = smem_raw + (size_t)p.n_smem_tabs * TAB_SMEM_BYTES + (size_t)tid * K * 4;   // this thread's column
     auto at = [&](uint32_t byte_off) { return reinterpret_cast<float*>(col + byte_off); };
     const uint32_t latch0 = latch_offset(p.n_regs, 0, RS);
     const uint32_t stage0 = stage_offset(p.n_regs, C, 0, RS);
-    const uint32_t stage_buf_bytes = (uint32_t)C * CHUNK * RS * 4u;
+    const uint32_t row_bytes = (uint32_t)RS * 4u;
 
-    // prefetch the first input chunk while the state loads
+    // input ring: slot (s - s_begin) % STAGE_DEPTH of channel c holds sample s; one cp.async group per sample
     const bool has_in = (p.in != nullptr);
-    auto stage_inputs = [&](int buf, int s0) {
-        if (has_in) {
-            for (int c = 0; c < C; ++c)
-#pragma unroll
-                for (int k = 0; k < CHUNK; ++k) {
-                    const int s = min(s0 + k, p.n_samples - 1);
-                    cp_async<4 * K>(at(stage0 + buf * stage_buf_bytes + (uint32_t)(c * CHUNK + k) * RS * 4u),
-                                    &p.in[(size_t)c * p.in_cstride + (size_t)s * N + inst0]);
-                }
+    const float* in_s = has_in ? p.in + (size_t)s_begin * N + inst0 : nullptr;     // sample to fetch next
+    int fetch_s = s_begin;
+    auto fetch_next = [&]() {
+        if (has_in && fetch_s < s_end) {
+            const uint32_t slot = (uint32_t)(fetch_s - s_begin) & (STAGE_DEPTH - 1);
+            cp_async<4 * K>(at(stage0 + slot * row_bytes), in_s);
+            if (C > 1) {
+                const float* g = in_s;
+                for (int c = 1; c < C; ++c) { g += p.in_cstride; cp_async<4 * K>(at(stage0 + (uint32_t)(c * STAGE_DEPTH + slot) * row_bytes), g); }
+            }
+            in_s += N;
         }
+        ++fetch_s;
         cp_async_commit();
     };
-    stage_inputs(0, s_begin);
+#pragma unroll
+    for (int d = 0; d < STAGE_DEPTH - 1; ++d) fetch_next();
 
     // literal-selector LOG/EXP tables -> shared, replicated so that lane (l & 7) of a 128-bit access
     // phase always reads bank group (l & 7): entry e of replica q lives at slot e * TAB_REPL + q.
     for (int t = 0; t < p.n_smem_tabs; ++t) {
         const TableEntry* src = p.tabs + (size_t)p.smem_tab_id[t] * FX8010_TABLE_ENTRIES;
 #pragma unroll 4
-        for (int i = tid; i < FX8010_TABLE_ENTRIES * TAB_REPL; i += B)
+        for (int i = tid; i < FX8010_TABLE_ENTRIES * TAB_REPL; i += B)      // consecutive lanes -> consecutive slots (conflict free)
             s_tab[t * FX8010_TABLE_ENTRIES * TAB_REPL + i] = src[i / TAB_REPL];
     }
 
     {   // register rows: batches of four independent loads keep the startup off the L2 latency chain
-        int r = 0;
-        for (; r + 4 <= p.n_regs; r += 4) {
+        int j = 0;
+        for (; j + 4 <= p.n_load; j += 4) {
             Vec<K> t[4];
+            uint32_t row[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) t[j] = vload<K>(p.gpr + (size_t)p.reg_map[r + j] * N + inst0);
+            for (int q = 0; q < 4; ++q) { row[q] = p.load_rows[j + q]; t[q] = vload<K>(p.gpr + (size_t)p.reg_map[row[q]] * N + inst0); }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) vstore<K>(at(reg_offset(r + j, RS)), t[j]);
+            for (int q = 0; q < 4; ++q) vstore<K>(at(reg_offset(row[q], RS)), t[q]);
         }
-        for (; r < p.n_regs; ++r) vstore<K>(at(reg_offset(r, RS)), vload<K>(p.gpr + (size_t)p.reg_map[r] * N + inst0));
+        for (; j < p.n_load; ++j) { const uint32_t row = p.load_rows[j]; vstore<K>(at(reg_offset(row, RS)), vload<K>(p.gpr + (size_t)p.reg_map[row] * N + inst0)); }
     }
-    for (int c = 0; c < C; ++c) vstore<K>(at(latch0 + (uint32_t)c * RS * 4u), vload<K>(p.latch + (size_t)c * N + inst0));
+    if (p.load_latch)
+        for (int c = 0; c < C; ++c) vstore<K>(at(latch0 + (uint32_t)c * RS * 4u), vload<K>(p.latch + (size_t)c * N + inst0));
 
     float acc_f[K];
     double acc_d[K];
@@ -264,7 +286,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
     int32_t iw[K], ir[K], xw[K], xr[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        acc_d[k] = p.acc[inst0 + k]; acc_f[k] = 0.0f; acc_is_f[k] = false;
+        acc_d[k] = p.load_acc ? p.acc[inst0 + k] : 0.0; acc_f[k] = 0.0f; acc_is_f[k] = false;
         skip[k] = 0; count[k] = 0;
         if (EXT) {
             g1[k] = p.lfsr[inst0 + k]; g2[k] = p.lfsr[N + inst0 + k];
@@ -277,16 +299,14 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
 
     const int lane_rep = tid & (TAB_REPL - 1);
     float* out_s = p.out + (size_t)s_begin * N + inst0;   // this thread's slot in the current output row
-    int buf = 0;
-    for (int s0 = s_begin; s0 < s_end; s0 += CHUNK) {
-        if (s0 + CHUNK < s_end) { stage_inputs(buf ^ 1, s0 + CHUNK); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        const int kn = min(CHUNK, s_end - s0);
-        for (int ks = 0; ks < kn; ++ks, out_s += N) {
+    uint32_t stage_s = 0;                                  // byte offset of the current sample's ring slot
+    for (int sidx = s_begin; sidx < s_end; ++sidx, out_s += N) {
+        {
+            fetch_next();
+            cp_async_wait<STAGE_DEPTH - 1>();                      // the group of sample sidx has landed
             // ---- one sample period: FX8010::process, source/FX8010.cpp:1023-1249 ----
             // The final CCR / latch must be in shared memory when the batch ends (state write-back).
-            const bool last_sample = (s0 + ks == p.n_samples - 1);
-            const uint32_t stage_s = buf * stage_buf_bytes + (uint32_t)ks * RS * 4u;
+            const bool last_sample = (sidx == p.n_samples - 1);
             bool saw_end[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) { skip[k] = 0; saw_end[k] = false; }
@@ -481,9 +501,8 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                         if (!SKIP && (w0 & F_OUT_DIRECT)) {
                             // R was just written by this instruction and nothing later in the sample period
                             // touches the channel: the value is the period's output (:1248)
-                            const Vec<K> v = vload<K>(pr);
-                            if (valid) vstore<K>(out_s + (size_t)(w0 >> 24) * p.out_cstride, v);
-                            if (last_sample) vstore<K>(at(wB.w), v);
+                            if (valid) vstore<K>(out_s + (size_t)(w0 >> 24) * p.out_cstride, r);
+                            if (last_sample) vstore<K>(at(wB.w), r);
                         } else if (!SKIP) vstore<K>(at(wB.w), vload<K>(pr));
                         else { float* const pl = at(wB.w); FX_EACH { if (act[k]) pl[k] = pr[k]; } }
                     }
@@ -506,12 +525,13 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                     const uint32_t c = p.latch_ch[j];
                     vstore<K>(out_s + (size_t)c * p.out_cstride, vload<K>(at(latch0 + c * RS * 4u)));
                 }
+            stage_s = (stage_s + row_bytes) & (STAGE_DEPTH * row_bytes - 1);
         }
-        buf ^= 1;
     }
 #undef FX_EACH
 
     // ---- write the state back (the last time segment carries the final state) ----
+    if (p.pdl_late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (flags) atomicOr(p.rt_flags, flags);
     if (!valid || !last_seg) return;
     for (int i = 0; i < p.n_wb; ++i) { const uint32_t r = p.wb_regs[i]; vstore<K>(p.gpr + (size_t)p.reg_map[r] * N + inst0, vload<K>(at(reg_offset(r, RS)))); }
