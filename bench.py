@@ -39,6 +39,8 @@ def workload(name: str):
     """(program text, instances per GPU, algorithmic bytes per instance-sample, label)."""
     if name == "cfg2":
         return progs.CFG2_LOG_GAIN, 4096, 8, "configs[1]: MACS gain + LOG waveshaper, 4096 instances x 1024-sample blocks per GPU"
+    if name == "cfg1":
+        return progs.CFG1A_TESTCODE, 4096, 8, "configs[0] batched: shipped testcode.da (MACS gain), 4096 instances x 1024-sample blocks per GPU"
     if name == "cfg3":
         return progs.cfg3_delay(1000), 16384, 16, "configs[2]: idelay feedback delay line (itramsize 1000), 16384 instances x 1024-sample blocks per GPU"
     if name == "cfg4":
@@ -49,7 +51,7 @@ def workload(name: str):
 
 
 def controls_for(name: str, prog, n: int, rng):
-    if name == "cfg2":
+    if name in ("cfg1", "cfg2"):
         return {"volume": rng.random(n).astype(np.float32)}
     if name == "cfg4":
         return {"filter_cutoff": (0.001 + 0.998 * np.arange(n) / max(1, n - 1)).astype(np.float32)}
@@ -335,7 +337,7 @@ def main():
                            "program_instructions_per_sample": instr_per_sample,
                            "l2": f"rotating {n_bufs} input/output buffer pairs ({2 * n_bufs * block_bytes >> 20} MiB > 126 MiB L2)",
                            "kernel": {"grid": info.last_grid, "block": info.last_block, "time_split": info.last_time_split,
-                                      "smem_bytes": info.last_smem_bytes, "instances_per_thread": info.kernel_variant >> 8}},
+                                      "smem_bytes": info.last_smem_bytes, "instances_per_thread": (info.kernel_variant >> 8) & 0xff, "samples_per_batch": info.kernel_variant >> 16}},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": ncu_traffic(args.config), "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": 1e3 * launch_ms},

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "fx8010_kernel.cuh"
+#include "fx8010_stateless.cuh"
 
 using namespace fxk;
 
@@ -27,8 +28,9 @@ std::mutex g_mutex;
 bool g_slot_used[MAX_DEVICES][PROG_SLOTS];
 thread_local std::string g_create_error;
 
-struct Launch { int K, B, n_seg, seg_len, grid_x; size_t smem; };
+struct Launch { int K, B, n_seg, seg_len, grid_x; size_t smem; int M; };   // M > 0: stateless kernel, samples per batch
 struct PlanKey { int ns = -1; unsigned align = 0; };
+enum RowClass { ROW_NONE = 0, ROW_RO, ROW_WO, ROW_RW, ROW_IN };
 
 }  // namespace
 
@@ -64,7 +66,16 @@ struct fx8010_gpu {
     // previous launch on last_stream: the buffers it writes / reads (for the PDL overlap decision)
     struct Span { const char* out_lo = nullptr; const char* out_hi = nullptr; const char* in_lo = nullptr; const char* in_hi = nullptr;
                   cudaStream_t stream = nullptr; bool valid = false; } prev[2];   // [0] = latest
-    int use_pdl = 1;                 // MaxDynamicSharedMemorySize set for kernel <K, SKIP, EXT>
+    int use_pdl = 1;
+    // stateless fast path (fx8010_stateless.cuh)
+    bool sl_ok = false;                          // program qualifies
+    int use_sl = 1, tune_M = 0;
+    std::vector<int> sl_class, sl_index;         // per register: RowClass and index inside its class
+    int sl_n_ro = 0, sl_n_wo = 0, sl_n_rw = 0;
+    int sl_M = 0;                                // batch length of the uploaded encoding (0 = generic encoding uploaded)
+    std::vector<uint2> sl_load, sl_wb;
+    uint2* d_sl_load = nullptr; uint2* d_sl_wb = nullptr;
+    bool sl_attr_set[3] = {};                 // MaxDynamicSharedMemorySize set for kernel <K, SKIP, EXT>
     int n_exec = 0;                              // encoded instructions
     std::vector<uint32_t> latch_ch;              // channels served from the latch every sample period
     // device state
@@ -230,6 +241,99 @@ void analyse(fx8010_gpu* h) {
         if (!h->stateless || !h->written[h->reg_map[row]]) h->load_rows.push_back((uint32_t)row);
     h->load_latch = !(h->stateless && all_ch);
     h->load_acc = !(h->stateless && acc_writer);
+
+    // Stateless fast path: additionally every channel needs a writer (its latch is never read then) and
+    // every preload of an INPUT register must deliver that register's own channel, so that the input
+    // stage rows can stand in for the INPUT registers (the reference loads X and Y from A's channel,
+    // source/FX8010.cpp:1057-1060 — a program relying on that quirk takes the generic kernel).
+    h->sl_ok = h->stateless && all_ch;
+    std::vector<uint8_t> is_read(nr, 0);
+    for (int i = 0; i < n && h->sl_ok; ++i) {
+        const fx8010_instr& in = h->instrs[i];
+        const Uop u = uop_of(h, in);
+        if (u == U_END || u == U_NOP) continue;
+        bool pa, px, py; int nz;
+        pre_targets(h, in, pa, px, py, nz);
+        const int ch = h->regs[in.a].io_index;
+        if ((pa && h->regs[in.a].io_index != ch) || (px && h->regs[in.x].io_index != ch) || (py && h->regs[in.y].io_index != ch)) h->sl_ok = false;
+        // an INPUT-typed operand that is NOT preloaded here (has_input clear in a hand-made image) would read a stale row
+        const int ops[3] = {in.a, in.x, in.y};
+        const bool pre[3] = {pa, px, py};
+        for (int o = 0; o < 3; ++o) if (h->regs[ops[o]].type == FX_REG_INPUT && !pre[o]) h->sl_ok = false;
+        is_read[in.a] = is_read[in.x] = 1;
+        if (u != U_LOG && u != U_EXP) is_read[in.y] = 1;
+    }
+    h->sl_class.assign(nr, ROW_NONE); h->sl_index.assign(nr, 0);
+    h->sl_n_ro = h->sl_n_wo = h->sl_n_rw = 0;
+    if (h->sl_ok)
+        for (int r = 0; r < nr; ++r) {
+            if (h->row_of[r] < 0) continue;
+            if (h->regs[r].type == FX_REG_INPUT) { h->sl_class[r] = ROW_IN; continue; }
+            if (!h->written[r]) { h->sl_class[r] = ROW_RO; h->sl_index[r] = h->sl_n_ro++; }
+            else if (!is_read[r]) { h->sl_class[r] = ROW_WO; h->sl_index[r] = h->sl_n_wo++; }
+            else { h->sl_class[r] = ROW_RW; h->sl_index[r] = h->sl_n_rw++; }
+        }
+}
+
+size_t sl_smem_bytes(const fx8010_gpu* h, int B, int K, int M) {
+    return (size_t)h->n_smem_tabs * TAB_SMEM_BYTES +
+           (size_t)B * K * 4 * ((size_t)h->sl_n_ro + h->sl_n_wo + (size_t)h->sl_n_rw * M + 2 * (size_t)h->C * M);
+}
+
+// Operand word of register r for the stateless kernel (see fx8010_stateless.cuh).
+uint32_t sl_word(const fx8010_gpu* h, int r, int B, int K, int M) {
+    const uint32_t row_bytes = (uint32_t)B * K * 4u, stride16 = row_bytes >> 4;
+    const uint32_t wo0 = (uint32_t)h->sl_n_ro * row_bytes, rw0 = wo0 + (uint32_t)h->sl_n_wo * row_bytes;
+    const uint32_t st0 = rw0 + (uint32_t)h->sl_n_rw * M * row_bytes;
+    switch (h->sl_class[r]) {
+    case ROW_RO: return (uint32_t)h->sl_index[r] * row_bytes;
+    case ROW_WO: return wo0 + (uint32_t)h->sl_index[r] * row_bytes;
+    case ROW_RW: return (rw0 + (uint32_t)h->sl_index[r] * M * row_bytes) | (stride16 << SL_STRIDE_SHIFT);
+    case ROW_IN: return (st0 + (uint32_t)h->regs[r].io_index * 2u * M * row_bytes) | (stride16 << SL_STRIDE_SHIFT) | SL_BUF;
+    default: return 0;   // never referenced
+    }
+}
+
+void encode_stateless(fx8010_gpu* h, int K, int B, int M) {
+    const int n = (int)h->instrs.size(), nr = (int)h->regs.size(), C = h->C;
+    std::vector<int> last_writer(C, -1);
+    bool ccr_read = h->sl_class[0] == ROW_RW;
+    for (int i = 0; i < n; ++i) {
+        const Uop u = uop_of(h, h->instrs[i]);
+        if (writes_r(u) && h->regs[h->instrs[i].r].type == FX_REG_OUTPUT) last_writer[h->regs[h->instrs[i].r].io_index] = i;
+    }
+    int e = 0;
+    for (int i = 0; i < n; ++i) {
+        const fx8010_instr& in = h->instrs[i];
+        const Uop u = uop_of(h, in);
+        if (u == U_END || u == U_NOP) continue;
+        uint32_t w0 = (uint32_t)u, aux = 0;
+        if (h->sl_class[in.r] == ROW_WO) w0 |= F_ST_LAST;
+        if (ccr_read || in.r == 0) w0 |= F_CCR;                 // a `ccr` operand somewhere: every setCCR is kept per sample
+        if (h->regs[in.r].type == FX_REG_OUTPUT) {
+            const int c = h->regs[in.r].io_index;
+            if (last_writer[c] == i) w0 |= F_OUT | F_OUT_DIRECT;
+            w0 |= (uint32_t)c << 24;
+        }
+        if (h->tab_of[i] >= 0) {
+            int slot = -1;
+            for (int t = 0; t < h->n_smem_tabs; ++t) if (h->smem_tab_id[t] == h->tab_of[i]) slot = t;
+            if (slot >= 0) { w0 |= F_TAB_SMEM; aux = (uint32_t)slot << 24; }
+            else { w0 |= F_TAB_IMM; aux = (uint32_t)h->tab_of[i] << 24; }
+        }
+        h->h_prog[2 * e] = make_uint4(w0, sl_word(h, in.r, B, K, M), sl_word(h, in.a, B, K, M), sl_word(h, in.x, B, K, M));
+        h->h_prog[2 * e + 1] = make_uint4(sl_word(h, in.y, B, K, M), aux, sl_word(h, 0, B, K, M), 0);
+        ++e;
+    }
+    h->n_exec = e;
+    h->h_prog[2 * e] = make_uint4((uint32_t)U_NOP, 0, 0, 0);
+    h->h_prog[2 * e + 1] = make_uint4(0, 0, 0, 0);
+    h->sl_load.clear(); h->sl_wb.clear();
+    for (int r = 0; r < nr; ++r) {
+        if (h->sl_class[r] == ROW_RO) h->sl_load.push_back(make_uint2(sl_word(h, r, B, K, M), (uint32_t)r));
+        else if (h->sl_class[r] != ROW_NONE && h->written[r]) h->sl_wb.push_back(make_uint2(sl_word(h, r, B, K, M), (uint32_t)r));
+    }
+    h->enc_K = K; h->enc_B = B; h->sl_M = M;
 }
 
 // LOG/EXP with a literal selector (a register the program never writes and that holds one value in
@@ -349,14 +453,14 @@ void encode(fx8010_gpu* h, int K, int B) {
     h->n_exec = e;
     h->h_prog[2 * e] = make_uint4((uint32_t)U_NOP, 0, 0, 0);      // pad: the kernel prefetches pc + 1
     h->h_prog[2 * e + 1] = make_uint4(0, 0, 0, 0);
-    h->enc_K = K; h->enc_B = B;
+    h->enc_K = K; h->enc_B = B; h->sl_M = 0;
 }
 
 void free_state(fx8010_gpu* h) {
     cudaFree(h->d_gpr); cudaFree(h->d_acc); cudaFree(h->d_lfsr); cudaFree(h->d_latch); cudaFree(h->d_ptrs);
-    cudaFree(h->d_itram); cudaFree(h->d_xtram); cudaFree(h->d_counts); cudaFree(h->d_wb); cudaFree(h->d_latch_ch); cudaFree(h->d_reg_map); cudaFree(h->d_load_rows);
+    cudaFree(h->d_itram); cudaFree(h->d_xtram); cudaFree(h->d_counts); cudaFree(h->d_wb); cudaFree(h->d_latch_ch); cudaFree(h->d_reg_map); cudaFree(h->d_load_rows); cudaFree(h->d_sl_load); cudaFree(h->d_sl_wb);
     h->d_gpr = nullptr; h->d_acc = nullptr; h->d_lfsr = nullptr; h->d_latch = nullptr; h->d_ptrs = nullptr;
-    h->d_itram = nullptr; h->d_xtram = nullptr; h->d_counts = nullptr; h->d_wb = nullptr; h->d_latch_ch = nullptr; h->d_reg_map = nullptr; h->d_load_rows = nullptr;
+    h->d_itram = nullptr; h->d_xtram = nullptr; h->d_counts = nullptr; h->d_wb = nullptr; h->d_latch_ch = nullptr; h->d_reg_map = nullptr; h->d_load_rows = nullptr; h->d_sl_load = nullptr; h->d_sl_wb = nullptr;
 }
 
 typedef void (*KernelFn)(const Params);
@@ -410,6 +514,44 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     return FX8010_OK;
 }
 
+typedef void (*SLKernelFn)(const SLParams);
+SLKernelFn pick_sl_kernel(int K) {
+    return K == 4 ? fx_stateless_kernel<4> : (K == 2 ? fx_stateless_kernel<2> : fx_stateless_kernel<1>);
+}
+
+// Geometry for the stateless kernel: all the parallelism a launch needs comes from cutting the time
+// axis, so K is as wide as alignment allows and the segment count fills exactly one wave.
+int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_cs, size_t out_cs, int n_samples, Launch& L) {
+    const int N = h->N;
+    auto aligned = [&](int K) {
+        const size_t a = (size_t)K * 4;
+        return N % K == 0 && ((uintptr_t)d_in % a) == 0 && ((uintptr_t)d_out % a) == 0 && (in_cs * 4) % a == 0 && (out_cs * 4) % a == 0;
+    };
+    int K = 4;
+    while (K > 1 && !aligned(K)) K >>= 1;
+    if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
+    int B = h->tune_B ? h->tune_B : 128;
+    while (B > 32 && (N / K + B - 1) / B * B >= 2 * (N / K) && N / K <= B / 2) B >>= 1;      // tiny N: do not launch mostly-idle blocks
+    int M = h->tune_M ? h->tune_M : 4;
+    while (M > 1 && sl_smem_bytes(h, B, K, M) > 48 * 1024) M >>= 1;
+    while (sl_smem_bytes(h, B, K, M) > h->smem_optin && B > 32) B >>= 1;
+    if (sl_smem_bytes(h, B, K, M) > h->smem_optin) return fail(h, FX8010_ERR_CAPACITY, "register file does not fit in shared memory");
+    L.K = K; L.B = B; L.M = M;
+    L.smem = sl_smem_bytes(h, B, K, M);
+    L.grid_x = (N / K + B - 1) / B;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_sl_kernel(K), B, L.smem);
+    occ = std::max(occ, 1);
+    long n_seg = std::max(1L, (long)h->num_sms * occ / L.grid_x);
+    if (h->tune_seg) n_seg = h->tune_seg;
+    n_seg = std::min<long>(n_seg, std::max(1, n_samples / M));
+    int seg_len = (int)((n_samples + n_seg - 1) / n_seg);
+    seg_len = (seg_len + M - 1) / M * M;
+    L.seg_len = seg_len;
+    L.n_seg = (n_samples + seg_len - 1) / seg_len;
+    return FX8010_OK;
+}
+
 int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, size_t out_cs, int n_samples, cudaStream_t st) {
     if (n_samples == 0) return FX8010_OK;
     // per-launch executed-instruction counters are 32-bit: split very long batches
@@ -425,41 +567,30 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
         const unsigned align = (unsigned)(((uintptr_t)in | (uintptr_t)out | (uintptr_t)(in_cs * 4) | (uintptr_t)(out_cs * 4)) & 15u) | (in ? 16u : 0u);
         if (h->plan_key.ns == ns && h->plan_key.align == align) L = h->plan;
         else {
-            const int rc = plan_launch(h, in, out, in_cs, out_cs, ns, L);
+            L.M = 0;
+            const int rc = (h->sl_ok && h->use_sl) ? plan_stateless(h, in, out, in_cs, out_cs, ns, L) : plan_launch(h, in, out, in_cs, out_cs, ns, L);
             if (rc) return rc;
             h->plan = L; h->plan_key.ns = ns; h->plan_key.align = align;
         }
-        if (h->encode_dirty || h->enc_K != L.K || h->enc_B != L.B) {
+        if (h->encode_dirty || h->enc_K != L.K || h->enc_B != L.B || h->sl_M != L.M) {
             // the previous upload must have left the pinned buffer before it is rewritten
             FX_CUDA(h, cudaStreamSynchronize(st));
             if (h->last_stream && h->last_stream != st) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));
-            encode(h, L.K, L.B);
+            if (L.M > 0) encode_stateless(h, L.K, L.B, L.M); else encode(h, L.K, L.B);
             FX_CUDA(h, cudaMemcpyToSymbolAsync(c_prog, h->h_prog, sizeof(uint4) * 2 * (h->n_exec + 1),
                                                sizeof(uint4) * (size_t)SLOT_WORDS * h->slot, cudaMemcpyHostToDevice, st));
-            FX_CUDA(h, cudaMemcpyAsync(h->d_latch_ch, h->latch_ch.data(), sizeof(uint32_t) * h->latch_ch.size(), cudaMemcpyHostToDevice, st));
+            if (L.M > 0) {
+                FX_CUDA(h, cudaMemcpyAsync(h->d_sl_load, h->sl_load.data(), sizeof(uint2) * h->sl_load.size(), cudaMemcpyHostToDevice, st));
+                FX_CUDA(h, cudaMemcpyAsync(h->d_sl_wb, h->sl_wb.data(), sizeof(uint2) * h->sl_wb.size(), cudaMemcpyHostToDevice, st));
+            } else
+                FX_CUDA(h, cudaMemcpyAsync(h->d_latch_ch, h->latch_ch.data(), sizeof(uint32_t) * h->latch_ch.size(), cudaMemcpyHostToDevice, st));
             FX_CUDA(h, cudaStreamSynchronize(st));
             h->encode_dirty = false;
         }
-        Params p = {};
-        p.gpr = h->d_gpr; p.acc = h->d_acc; p.lfsr = h->d_lfsr; p.latch = h->d_latch; p.ptrs = h->d_ptrs;
-        p.itram = h->d_itram; p.xtram = h->d_xtram; p.counts = h->d_counts; p.rt_flags = h->d_flags;
-        p.reg_map = h->d_reg_map; p.load_rows = h->d_load_rows; p.wb_regs = h->d_wb; p.latch_ch = h->d_latch_ch; p.tabs = h->d_tabs;
-        p.in = in; p.out = out; p.in_cstride = in_cs; p.out_cstride = out_cs;
-        p.n_samples = ns; p.seg_len = L.seg_len; p.n_seg = L.n_seg;
-        p.N = h->N; p.C = h->C; p.n_regs = (int)h->reg_map.size(); p.n_instrs = (int)h->instrs.size();
-        p.n_wb = (int)h->wb.size(); p.slot = h->slot;
-        p.n_exec = h->n_exec; p.n_latch_ch = (int)h->latch_ch.size();
-        p.n_load = (int)h->load_rows.size(); p.load_latch = h->load_latch; p.load_acc = h->load_acc;
-        p.itram_size = h->itram_size; p.xtram_size = h->xtram_size;
-        p.n_smem_tabs = h->n_smem_tabs;
-        for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
-        KernelFn fn = pick_kernel(L.K, h->has_skip, h->has_ext);
-        bool& attr = h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][h->has_skip ? 1 : 0][h->has_ext ? 1 : 0];
-        if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
         // Programmatic dependent launch: the kernel may start while the previous launch on this stream
         // drains.  It can postpone its wait to the final state write-back when it reads nothing that
         // launch writes: stateless program (start-up reads only rows nobody writes) and I/O buffers
-        // disjoint from the previous launch's.
+        // disjoint from the previous launches'.
         const char* out_lo = (const char*)out; const char* out_hi = out_lo + sizeof(float) * ((size_t)(h->C - 1) * out_cs + (size_t)ns * h->N);
         const char* in_lo = (const char*)in; const char* in_hi = in ? in_lo + sizeof(float) * ((size_t)(h->C - 1) * in_cs + (size_t)ns * h->N) : in_lo;
         auto overlap = [](const char* a0, const char* a1, const char* b0, const char* b1) { return a0 < b1 && b0 < a1; };
@@ -469,21 +600,58 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
         for (const fx8010_gpu::Span& q : h->prev)
             disjoint = disjoint && q.valid && q.stream == st && !overlap(out_lo, out_hi, q.out_lo, q.out_hi) &&
                        !overlap(in_lo, in_hi, q.out_lo, q.out_hi) && !overlap(out_lo, out_hi, q.in_lo, q.in_hi);
-        p.pdl_late_wait = (h->use_pdl && h->stateless && disjoint) ? 1 : 0;
+        const int late_wait = (h->use_pdl && h->stateless && disjoint) ? 1 : 0;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(L.grid_x, L.n_seg); cfg.blockDim = dim3(L.B); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
         cudaLaunchAttribute attrs[1];
         attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attrs[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attrs; cfg.numAttrs = h->use_pdl ? 1 : 0;
-        FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
+        if (L.M > 0) {
+            SLParams p = {};
+            p.gpr = h->d_gpr; p.acc = h->d_acc; p.latch = h->d_latch; p.counts = h->d_counts; p.rt_flags = h->d_flags;
+            p.tabs = h->d_tabs; p.load_list = h->d_sl_load; p.wb_list = h->d_sl_wb;
+            p.in = in; p.out = out; p.in_cstride = in_cs; p.out_cstride = out_cs;
+            p.n_samples = ns; p.seg_len = L.seg_len; p.n_seg = L.n_seg;
+            p.N = h->N; p.C = h->C; p.n_instrs = (int)h->instrs.size(); p.n_exec = h->n_exec; p.slot = h->slot;
+            p.n_load = (int)h->sl_load.size(); p.n_wb = (int)h->sl_wb.size();
+            p.M = L.M;
+            p.stage0 = (uint32_t)L.B * L.K * 4u * (uint32_t)(h->sl_n_ro + h->sl_n_wo + h->sl_n_rw * L.M);
+            p.n_smem_tabs = h->n_smem_tabs;
+            for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
+            p.acc_writer = h->load_acc ? 0 : 1;
+            p.pdl_late_wait = late_wait;
+            SLKernelFn fn = pick_sl_kernel(L.K);
+            bool& attr = h->sl_attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)];
+            if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
+            FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
+        } else {
+            Params p = {};
+            p.gpr = h->d_gpr; p.acc = h->d_acc; p.lfsr = h->d_lfsr; p.latch = h->d_latch; p.ptrs = h->d_ptrs;
+            p.itram = h->d_itram; p.xtram = h->d_xtram; p.counts = h->d_counts; p.rt_flags = h->d_flags;
+            p.reg_map = h->d_reg_map; p.load_rows = h->d_load_rows; p.wb_regs = h->d_wb; p.latch_ch = h->d_latch_ch; p.tabs = h->d_tabs;
+            p.in = in; p.out = out; p.in_cstride = in_cs; p.out_cstride = out_cs;
+            p.n_samples = ns; p.seg_len = L.seg_len; p.n_seg = L.n_seg;
+            p.N = h->N; p.C = h->C; p.n_regs = (int)h->reg_map.size(); p.n_instrs = (int)h->instrs.size();
+            p.n_wb = (int)h->wb.size(); p.slot = h->slot;
+            p.n_exec = h->n_exec; p.n_latch_ch = (int)h->latch_ch.size();
+            p.n_load = (int)h->load_rows.size(); p.load_latch = h->load_latch; p.load_acc = h->load_acc;
+            p.itram_size = h->itram_size; p.xtram_size = h->xtram_size;
+            p.n_smem_tabs = h->n_smem_tabs;
+            for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
+            p.pdl_late_wait = late_wait;
+            KernelFn fn = pick_kernel(L.K, h->has_skip, h->has_ext);
+            bool& attr = h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][h->has_skip ? 1 : 0][h->has_ext ? 1 : 0];
+            if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
+            FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
+        }
         h->prev[1] = h->prev[0];
         h->prev[0].out_lo = out_lo; h->prev[0].out_hi = out_hi; h->prev[0].in_lo = in_lo; h->prev[0].in_hi = in_hi;
         h->prev[0].stream = st; h->prev[0].valid = true;
         h->info.kernel_launches++;
         h->info.last_grid = L.grid_x * L.n_seg; h->info.last_block = L.B; h->info.last_time_split = L.n_seg;
         h->info.last_smem_bytes = (int)L.smem;
-        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.K << 8);
+        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | (L.K << 8) | (L.M << 16);
     }
     h->last_stream = st;
     return FX8010_OK;
@@ -539,6 +707,9 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     h->tune_K = env_int("FX8010_TUNE_K"); h->tune_B = env_int("FX8010_TUNE_B");
     h->tune_seg = env_int("FX8010_TUNE_SEG"); h->tune_sub = env_int("FX8010_TUNE_SUB");
     if (getenv("FX8010_NO_PDL")) h->use_pdl = 0;
+    if (getenv("FX8010_NO_STATELESS")) h->use_sl = 0;
+    h->tune_M = env_int("FX8010_TUNE_M");
+    if (h->tune_M != 1 && h->tune_M != 2 && h->tune_M != 4 && h->tune_M != 8) h->tune_M = 0;
     if (h->tune_K != 1 && h->tune_K != 2 && h->tune_K != 4) h->tune_K = 0;
     if (h->tune_B != 32 && h->tune_B != 64 && h->tune_B != 128) h->tune_B = 0;
     *out = h;
@@ -666,6 +837,8 @@ int fx8010_gpu_load_program(fx8010_gpu* h, const fx8010_program_image* im) {
     analyse(h);
     FX_CUDA(h, cudaMalloc(&h->d_wb, sizeof(uint32_t) * std::max<size_t>(1, h->wb.size())));
     FX_CUDA(h, cudaMalloc(&h->d_latch_ch, sizeof(uint32_t) * 256));
+    FX_CUDA(h, cudaMalloc(&h->d_sl_load, sizeof(uint2) * std::max<size_t>(1, nr)));
+    FX_CUDA(h, cudaMalloc(&h->d_sl_wb, sizeof(uint2) * std::max<size_t>(1, nr)));
     FX_CUDA(h, cudaMalloc(&h->d_reg_map, sizeof(uint32_t) * h->reg_map.size()));
     FX_CUDA(h, cudaMalloc(&h->d_load_rows, sizeof(uint32_t) * std::max<size_t>(1, h->load_rows.size())));
     if (!h->load_rows.empty()) FX_CUDA(h, cudaMemcpy(h->d_load_rows, h->load_rows.data(), sizeof(uint32_t) * h->load_rows.size(), cudaMemcpyHostToDevice));

@@ -268,6 +268,46 @@ def test_forced_geometries(fx, po, k, b, monkeypatch):
     run_case(fx, po, progs.CFG2_LOG_GAIN, 256, [100], rng, what=f"cfg2 K={k} B={b}")
 
 
+STATELESS_PROGS = {
+    "cfg2": progs.CFG2_LOG_GAIN,
+    "testcode": progs.CFG1A_TESTCODE,
+    "exp": progs.SNIPPETS["exp"],
+    "interp_const": progs.SNIPPETS["interp_const"],
+    "andxor": progs.SNIPPETS["andxor"],
+    # ccr read as an operand (kept per sample), a temp written twice, two outputs, dynamic table selector
+    "ccr_operand": "static a\nstatic b\ninput in_l 0\ncontrol sel = 5\noutput out_l 0\nmacs a, 0, in_l, 0.5\nmacs b, ccr, a, 0.25\n"
+                   "log a, b, sel, 0\nmacsn a, a, in_l, 0.125\nmacs out_l, a, b, ccr\nend",
+    "two_outputs": "static a\ninput in_l 0\ninput in_r 1\noutput out_l 0\noutput out_r 1\nmacw a, in_l, 0.75, 0.5\nlimit out_r, in_r, a, 0.25\n"
+                   "tstneg out_l, in_l, a, 0\nmacintw out_l, out_l, a, 0.75\nend",
+}
+
+
+@pytest.mark.parametrize("name", sorted(STATELESS_PROGS))
+@pytest.mark.parametrize("mode", ["M1", "M2", "M4", "M8", "generic"])
+def test_stateless_kernel_modes(fx, po, name, mode, monkeypatch):
+    """Stateless programs through the sample-batched kernel at every batch length and through the
+    generic kernel: identical bits, identical final state (several calls, ragged lengths)."""
+    if mode == "generic":
+        monkeypatch.setenv("FX8010_NO_STATELESS", "1")
+    else:
+        monkeypatch.setenv("FX8010_TUNE_M", mode[1:])
+    rng = np.random.default_rng(11)
+    ch = 2 if name == "two_outputs" else 1
+    n = 260
+    ctl = {"sel": rng.integers(0, 32, n).astype(np.float32)} if name == "ccr_operand" else None
+    info = run_case(fx, po, STATELESS_PROGS[name], n, [1, 37, 8, 3, 100], rng, channels=ch, controls=ctl, what=f"{name} {mode}")
+    assert bool(info.kernel_variant & 8) == (mode != "generic"), "wrong kernel took the program"
+
+
+def test_input_channel_quirk_takes_generic_kernel(fx, po):
+    """X/Y INPUT operands read A's channel (reference :1057-1060): such a program is stateless but must not
+    use the stage-aliasing kernel."""
+    rng = np.random.default_rng(12)
+    text = "input in_l 0\ninput in_r 1\noutput out_l 0\noutput out_r 1\nmacs out_l, in_l, in_r, 0.5\nmacs out_r, 0.25, in_r, in_l\nend"
+    info = run_case(fx, po, text, 64, [20, 5], rng, channels=2, what="quirk")
+    assert not (info.kernel_variant & 8)
+
+
 def test_errors_are_loud(fx):
     g = fx.Gpu(8, 1)
     try:
