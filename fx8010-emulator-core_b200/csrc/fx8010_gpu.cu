@@ -28,7 +28,7 @@ std::mutex g_mutex;
 bool g_slot_used[MAX_DEVICES][PROG_SLOTS];
 thread_local std::string g_create_error;
 
-struct Launch { int K, B, n_seg, seg_len, grid_x; size_t smem; int M; };   // M > 0: stateless kernel, samples per batch
+struct Launch { int K, B, n_seg, seg_len, grid_x; size_t smem; int M; int chunk; };   // M > 0: stateless kernel, samples per batch
 struct PlanKey { int ns = -1; unsigned align = 0; };
 enum RowClass { ROW_NONE = 0, ROW_RO, ROW_WO, ROW_RW, ROW_IN };
 
@@ -60,16 +60,16 @@ struct fx8010_gpu {
     int smem_tab_id[MAX_SMEM_TABLES] = {0, 0};
     std::vector<int> tab_of;                     // per instruction: literal table id or -1
     uint4* h_prog = nullptr;                     // pinned, SLOT_WORDS words
-    int enc_K = 0, enc_B = 0;                    // geometry the uploaded encoding was made for
+    int enc_K = 0, enc_B = 0, enc_chunk = 0;     // geometry the uploaded encoding was made for
     PlanKey plan_key; Launch plan = {};          // last launch plan (reused while nothing relevant changes)
-    bool attr_set[3][2][2] = {};
+    bool attr_set[3][2][2][2] = {};
     // previous launch on last_stream: the buffers it writes / reads (for the PDL overlap decision)
     struct Span { const char* out_lo = nullptr; const char* out_hi = nullptr; const char* in_lo = nullptr; const char* in_hi = nullptr;
                   cudaStream_t stream = nullptr; bool valid = false; } prev[2];   // [0] = latest
     int use_pdl = 1;
     // stateless fast path (fx8010_stateless.cuh)
     bool sl_ok = false;                          // program qualifies
-    int use_sl = 1, tune_M = 0;
+    int use_sl = 1, tune_M = 0, use_short = 1, tune_chunk = 0;
     std::vector<int> sl_class, sl_index;         // per register: RowClass and index inside its class
     int sl_n_ro = 0, sl_n_wo = 0, sl_n_rw = 0;
     int sl_M = 0;                                // batch length of the uploaded encoding (0 = generic encoding uploaded)
@@ -366,7 +366,7 @@ void select_tables(fx8010_gpu* h) {
 }
 
 // Encodes the program for the kernel: micro-ops, flags, CCR liveness, table placement.
-void encode(fx8010_gpu* h, int K, int B) {
+void encode(fx8010_gpu* h, int K, int B, int chunk) {
     const int n = (int)h->instrs.size();
     const int RS = K * B, nr = (int)h->reg_map.size(), C = h->C;
     auto row = [&](int r) { return h->row_of[r] < 0 ? 0 : h->row_of[r]; };   // unused operands (R of SKIP/TRAM ops) are never touched
@@ -430,7 +430,7 @@ void encode(fx8010_gpu* h, int K, int B) {
         if (px) w0 |= F_PRE_X;
         if (py) w0 |= F_PRE_Y;
         uint32_t pre_off = 0, out_off = 0, aux = 0;
-        if (pa || px || py) pre_off = stage_offset(nr, C, h->regs[in.a].io_index, RS);      // X and Y use A's IOIndex (:1057-1060)
+        if (pa || px || py) pre_off = stage_offset(nr, C, h->regs[in.a].io_index, RS, chunk);      // X and Y use A's IOIndex (:1057-1060)
         if (nz >= 0) { w0 |= F_NOISE; aux = reg_offset(row(nz), RS); }
         if (h->regs[in.r].type == FX_REG_OUTPUT && uops[i] != U_END && uops[i] != U_NOP) { // :1229-1233
             const int c = h->regs[in.r].io_index;
@@ -453,7 +453,7 @@ void encode(fx8010_gpu* h, int K, int B) {
     h->n_exec = e;
     h->h_prog[2 * e] = make_uint4((uint32_t)U_NOP, 0, 0, 0);      // pad: the kernel prefetches pc + 1
     h->h_prog[2 * e + 1] = make_uint4(0, 0, 0, 0);
-    h->enc_K = K; h->enc_B = B; h->sl_M = 0;
+    h->enc_K = K; h->enc_B = B; h->sl_M = 0; h->enc_chunk = chunk;
 }
 
 void free_state(fx8010_gpu* h) {
@@ -464,13 +464,27 @@ void free_state(fx8010_gpu* h) {
 }
 
 typedef void (*KernelFn)(const Params);
-template <int K> KernelFn pick_kernel(bool skip, bool ext) {
-    if (skip) return ext ? fx_interp_kernel<K, true, true> : fx_interp_kernel<K, true, false>;
-    return ext ? fx_interp_kernel<K, false, true> : fx_interp_kernel<K, false, false>;
+template <int K, int NI> KernelFn pick_kernel(bool skip, bool ext) {
+    if (skip) return ext ? fx_interp_kernel<K, true, true, NI> : fx_interp_kernel<K, true, false, NI>;
+    return ext ? fx_interp_kernel<K, false, true, NI> : fx_interp_kernel<K, false, false, NI>;
 }
-KernelFn pick_kernel(int K, bool skip, bool ext) {
-    return K == 4 ? pick_kernel<4>(skip, ext) : (K == 2 ? pick_kernel<2>(skip, ext) : pick_kernel<1>(skip, ext));
+template <int K> KernelFn pick_kernel(bool skip, bool ext, bool shortp) {
+    return shortp ? pick_kernel<K, SHORT_NI>(skip, ext) : pick_kernel<K, 0>(skip, ext);
 }
+KernelFn pick_kernel(int K, bool skip, bool ext, bool shortp) {
+    return K == 4 ? pick_kernel<4>(skip, ext, shortp) : (K == 2 ? pick_kernel<2>(skip, ext, shortp) : pick_kernel<1>(skip, ext, shortp));
+}
+// Encoded length of the program for the generic kernel (END/NOP are dropped when there is no SKIP).
+int encoded_length(const fx8010_gpu* h) {
+    int e = 0;
+    for (const fx8010_instr& in : h->instrs) {
+        const Uop u = uop_of(h, in);
+        if (!h->has_skip && (u == U_END || u == U_NOP)) continue;
+        ++e;
+    }
+    return e;
+}
+bool is_short(const fx8010_gpu* h) { return h->use_short && encoded_length(h) <= SHORT_NI; }
 
 // Geometry of one launch: contexts per thread, block size, time split.
 int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_cs, size_t out_cs, int n_samples, Launch& L) {
@@ -480,7 +494,7 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
         return N % K == 0 && ((uintptr_t)d_in % a) == 0 && ((uintptr_t)d_out % a) == 0 &&
                (in_cs * 4) % a == 0 && (out_cs * 4) % a == 0;
     };
-    const int min_seg = 4;
+    const int min_seg = 8;
     const long max_seg = h->stateless ? std::max(1, n_samples / min_seg) : 1;
     const long want_threads = (long)h->num_sms * 512;
     int K = 4;
@@ -488,18 +502,31 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
     // block size: spread small jobs over the SMs, keep several blocks per SM resident
     int B = 128;
-    auto fits = [&](int b, int k) { return smem_bytes(nr, C, b, k, h->n_smem_tabs) <= h->smem_optin; };
-    while (B > 32 && ((long)((N / K + B - 1) / B) * max_seg < 2L * h->num_sms || smem_bytes(nr, C, B, K, h->n_smem_tabs) > 56 * 1024)) B >>= 1;
+    // input stage depth: a recurrence has nothing but its own future inputs to keep in flight, so make the
+    // stage deep; a time-split (stateless) launch has many short segments and needs little.
+    // Roughly 48 KiB of input rows in flight per SM cover HBM latency at full bandwidth; what the resident
+    // warps do not provide through their number, each thread provides through a deeper stage.
+    int chunk = 4;
+    if (!h->stateless) {
+        const double warps_per_sm = std::min(48.0, std::max(1.0, (double)N / K / 32.0 / h->num_sms));
+        const double want = 49152.0 / (warps_per_sm * 32.0 * 4.0 * K * C);
+        while (chunk < 32 && chunk < want) chunk <<= 1;
+    }
+    if (h->tune_chunk) chunk = h->tune_chunk;
+    auto smem = [&](int b, int k, int ch) { return smem_bytes(nr, C, b, k, h->n_smem_tabs, ch); };
+    auto fits = [&](int b, int k) { return smem(b, k, chunk) <= h->smem_optin; };
+    while (B > 32 && ((long)((N / K + B - 1) / B) * max_seg < 2L * h->num_sms || smem(B, K, chunk) > 56 * 1024)) B >>= 1;
     if (h->tune_B) B = h->tune_B;
+    while (!fits(B, K) && chunk > 4) chunk >>= 1;
     while (!fits(B, K) && K > 1) K >>= 1;
     while (!fits(B, K) && B > 32) B >>= 1;
     if (!fits(B, K)) return fail(h, FX8010_ERR_CAPACITY, "register file does not fit in shared memory");
-    L.K = K; L.B = B;
-    L.smem = smem_bytes(nr, C, B, K, h->n_smem_tabs);
+    L.K = K; L.B = B; L.chunk = chunk;
+    L.smem = smem(B, K, chunk);
     L.grid_x = (N / K + B - 1) / B;
     L.n_seg = 1; L.seg_len = n_samples;
     if (h->stateless && n_samples > min_seg) {
-        KernelFn fn = pick_kernel(K, h->has_skip, h->has_ext);
+        KernelFn fn = pick_kernel(K, h->has_skip, h->has_ext, is_short(h));
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, B, L.smem);
         occ = std::max(occ, 1);
@@ -536,7 +563,7 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     while (M > 1 && sl_smem_bytes(h, B, K, M) > 48 * 1024) M >>= 1;
     while (sl_smem_bytes(h, B, K, M) > h->smem_optin && B > 32) B >>= 1;
     if (sl_smem_bytes(h, B, K, M) > h->smem_optin) return fail(h, FX8010_ERR_CAPACITY, "register file does not fit in shared memory");
-    L.K = K; L.B = B; L.M = M;
+    L.K = K; L.B = B; L.M = M; L.chunk = 0;
     L.smem = sl_smem_bytes(h, B, K, M);
     L.grid_x = (N / K + B - 1) / B;
     int occ = 1;
@@ -572,11 +599,11 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             if (rc) return rc;
             h->plan = L; h->plan_key.ns = ns; h->plan_key.align = align;
         }
-        if (h->encode_dirty || h->enc_K != L.K || h->enc_B != L.B || h->sl_M != L.M) {
+        if (h->encode_dirty || h->enc_K != L.K || h->enc_B != L.B || h->sl_M != L.M || (L.M == 0 && h->enc_chunk != L.chunk)) {
             // the previous upload must have left the pinned buffer before it is rewritten
             FX_CUDA(h, cudaStreamSynchronize(st));
             if (h->last_stream && h->last_stream != st) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));
-            if (L.M > 0) encode_stateless(h, L.K, L.B, L.M); else encode(h, L.K, L.B);
+            if (L.M > 0) encode_stateless(h, L.K, L.B, L.M); else encode(h, L.K, L.B, L.chunk);
             FX_CUDA(h, cudaMemcpyToSymbolAsync(c_prog, h->h_prog, sizeof(uint4) * 2 * (h->n_exec + 1),
                                                sizeof(uint4) * (size_t)SLOT_WORDS * h->slot, cudaMemcpyHostToDevice, st));
             if (L.M > 0) {
@@ -639,9 +666,11 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             p.itram_size = h->itram_size; p.xtram_size = h->xtram_size;
             p.n_smem_tabs = h->n_smem_tabs;
             for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
+            p.chunk = L.chunk;
             p.pdl_late_wait = late_wait;
-            KernelFn fn = pick_kernel(L.K, h->has_skip, h->has_ext);
-            bool& attr = h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][h->has_skip ? 1 : 0][h->has_ext ? 1 : 0];
+            const bool shortp = is_short(h);
+            KernelFn fn = pick_kernel(L.K, h->has_skip, h->has_ext, shortp);
+            bool& attr = h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][h->has_skip ? 1 : 0][h->has_ext ? 1 : 0][shortp ? 1 : 0];
             if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
             FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
         }
@@ -651,7 +680,7 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
         h->info.kernel_launches++;
         h->info.last_grid = L.grid_x * L.n_seg; h->info.last_block = L.B; h->info.last_time_split = L.n_seg;
         h->info.last_smem_bytes = (int)L.smem;
-        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | (L.K << 8) | (L.M << 16);
+        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | ((L.M == 0 && is_short(h)) ? 16 : 0) | (L.K << 8) | (L.M << 16);
     }
     h->last_stream = st;
     return FX8010_OK;
@@ -687,7 +716,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
         h->num_sms = prop.multiProcessorCount;
-        h->smem_optin = prop.sharedMemPerBlockOptin;
+        h->smem_optin = prop.sharedMemPerBlockOptin - 1024;   // the kernels keep a few hundred bytes of static shared memory
     }
     bool ok = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking) == cudaSuccess &&
@@ -708,7 +737,10 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     h->tune_seg = env_int("FX8010_TUNE_SEG"); h->tune_sub = env_int("FX8010_TUNE_SUB");
     if (getenv("FX8010_NO_PDL")) h->use_pdl = 0;
     if (getenv("FX8010_NO_STATELESS")) h->use_sl = 0;
+    if (getenv("FX8010_NO_SHORT")) h->use_short = 0;
     h->tune_M = env_int("FX8010_TUNE_M");
+    h->tune_chunk = env_int("FX8010_TUNE_CHUNK");
+    if (h->tune_chunk & (h->tune_chunk - 1) || h->tune_chunk > MAX_CHUNK) h->tune_chunk = 0;
     if (h->tune_M != 1 && h->tune_M != 2 && h->tune_M != 4 && h->tune_M != 8) h->tune_M = 0;
     if (h->tune_K != 1 && h->tune_K != 2 && h->tune_K != 4) h->tune_K = 0;
     if (h->tune_B != 32 && h->tune_B != 64 && h->tune_B != 128) h->tune_B = 0;

@@ -55,7 +55,9 @@ constexpr int PROG_SLOTS = 2;            // live programs per device (one slot p
 constexpr int SLOT_WORDS = 2 * (MAX_INSTR + 1);
 __constant__ uint4 c_prog[PROG_SLOTS][SLOT_WORDS];
 
-constexpr int STAGE_DEPTH = 4;           // input ring: cp.async runs STAGE_DEPTH - 1 sample periods ahead
+constexpr int MAX_CHUNK = 64;             // input stage: two buffers of `chunk` samples per channel; while one is consumed the
+                                         // other is in flight (a recurrence needs ~30 sample rows in flight per thread to
+                                         // cover HBM latency at full bandwidth)
 constexpr int MAX_SMEM_TABLES = 2;       // LOG/EXP tables replicated into shared memory
 constexpr int TAB_REPL = 8;              // replicas: one per lane of a 128-bit access phase
 constexpr int TAB_SMEM_BYTES = FX8010_TABLE_ENTRIES * TAB_REPL * 16;   // 8 KiB per table
@@ -92,6 +94,7 @@ struct Params {
     int n_latch_ch;             // entries of latch_ch
     int n_load;                 // entries of load_rows
     int load_latch, load_acc;   // the latches / the accumulator can be observed before the program rewrites them
+    int chunk;                  // samples per input-stage buffer (power of two <= MAX_CHUNK)
     int pdl_late_wait;          // programmatic dependent launch: 1 = this launch reads nothing the previous launch on
                                 // the stream writes until its own state write-back (stateless program, disjoint
                                 // buffers), so it only waits for that launch right before writing state
@@ -187,15 +190,24 @@ template <int BYTES> __device__ __forceinline__ void cp_async(void* smem, const 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// Loop invariants that come from the kernel parameter bank or from __constant__ memory: ptxas likes to
+// re-read them inside the sample loop ("rematerialisation"), and a constant-bank load in front of a
+// dependent instruction costs a lone warp tens of cycles of its per-sample chain (measured: half of a
+// one-instruction recurrence's time).  They are therefore bounced through shared memory once and read
+// back with VOLATILE loads before the loop: a volatile access cannot be repeated, so the value has to
+// stay in a register.
+constexpr int INV_WORDS = 8 + 8 * 4;     // scalars + up to 4 hoisted instructions of 8 words
+__device__ __forceinline__ uint32_t inv_read(const uint32_t* s_inv, int i) { return *reinterpret_cast<const volatile uint32_t*>(s_inv + i); }
+
 // Shared-memory layout of one block (host and device agree through these formulas):
-//   [ tables ][ registers n_regs ][ latches C ][ input ring C x STAGE_DEPTH ]   (the last three per column)
-__host__ __device__ inline size_t smem_bytes(int n_regs, int C, int B, int K, int n_smem_tabs) {
+//   [ tables ][ registers n_regs ][ latches C ][ input stage C x 2 x chunk ]   (the last three per column)
+__host__ __device__ inline size_t smem_bytes(int n_regs, int C, int B, int K, int n_smem_tabs, int chunk) {
     return (size_t)n_smem_tabs * TAB_SMEM_BYTES +
-           (size_t)B * K * sizeof(float) * ((size_t)n_regs + C + (size_t)C * STAGE_DEPTH);
+           (size_t)B * K * sizeof(float) * ((size_t)n_regs + C + 2 * (size_t)C * chunk);
 }
 __host__ __device__ inline uint32_t reg_offset(int r, int RS) { return (uint32_t)r * RS * 4u; }
 __host__ __device__ inline uint32_t latch_offset(int n_regs, int c, int RS) { return (uint32_t)(n_regs + c) * RS * 4u; }
-__host__ __device__ inline uint32_t stage_offset(int n_regs, int C, int c, int RS) { return (uint32_t)(n_regs + C + c * STAGE_DEPTH) * RS * 4u; }
+__host__ __device__ inline uint32_t stage_offset(int n_regs, int C, int c, int RS, int chunk) { return (uint32_t)(n_regs + C + c * 2 * chunk) * RS * 4u; }
 
 // ---- the kernel ------------------------------------------------------------------------------
 //
@@ -203,7 +215,13 @@ __host__ __device__ inline uint32_t stage_offset(int n_regs, int C, int c, int R
 //   SKIP: the program contains SKIP (per-context predicate, extra passes when END is skipped)
 //   EXT : the program uses TRAM, the noise LFSR or MACMV (their state stays out of the registers
 //         of simpler programs)
-template <int K, bool SKIP, bool EXT>
+//   NI  : 0 = fetch every instruction from __constant__ memory inside the sample loop (any length);
+//         NI > 0 = short program (n_exec <= NI): its decoded words are read ONCE into registers and the
+//         instruction loop is unrolled, so fetch, decode and operand address arithmetic leave the
+//         per-sample dependency chain (recurrences such as a one-pole filter or a feedback delay are
+//         bound by exactly that chain).
+constexpr int SHORT_NI = 4;
+template <int K, bool SKIP, bool EXT, int NI>
 __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int B = blockDim.x;
@@ -230,28 +248,27 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
     unsigned char* const col = smem_raw + (size_t)p.n_smem_tabs * TAB_SMEM_BYTES + (size_t)tid * K * 4;   // this thread's column
     auto at = [&](uint32_t byte_off) { return reinterpret_cast<float*>(col + byte_off); };
     const uint32_t latch0 = latch_offset(p.n_regs, 0, RS);
-    const uint32_t stage0 = stage_offset(p.n_regs, C, 0, RS);
+    const uint32_t stage0 = stage_offset(p.n_regs, C, 0, RS, p.chunk);
     const uint32_t row_bytes = (uint32_t)RS * 4u;
 
-    // input ring: slot (s - s_begin) % STAGE_DEPTH of channel c holds sample s; one cp.async group per sample
+    // input stage: chunk starting at sample s0 -> buffer `buf` of every channel; one cp.async group per chunk
     const bool has_in = (p.in != nullptr);
-    const float* in_s = has_in ? p.in + (size_t)s_begin * N + inst0 : nullptr;     // sample to fetch next
-    int fetch_s = s_begin;
-    auto fetch_next = [&]() {
-        if (has_in && fetch_s < s_end) {
-            const uint32_t slot = (uint32_t)(fetch_s - s_begin) & (STAGE_DEPTH - 1);
-            cp_async<4 * K>(at(stage0 + slot * row_bytes), in_s);
-            if (C > 1) {
-                const float* g = in_s;
-                for (int c = 1; c < C; ++c) { g += p.in_cstride; cp_async<4 * K>(at(stage0 + (uint32_t)(c * STAGE_DEPTH + slot) * row_bytes), g); }
+    const int chunk = p.chunk;
+    const uint32_t buf_bytes = (uint32_t)chunk * row_bytes;
+    auto fetch_chunk = [&](int s0, uint32_t boff) {
+        if (has_in && s0 < s_end) {
+            const int n = min(chunk, s_end - s0);
+            const float* g = p.in + (size_t)s0 * N + inst0;
+            for (int c = 0; c < C; ++c, g += p.in_cstride) {
+                unsigned char* d = reinterpret_cast<unsigned char*>(at(stage0 + (uint32_t)c * 2u * buf_bytes + boff));
+                const float* gs = g;
+#pragma unroll 4
+                for (int m = 0; m < n; ++m, d += row_bytes, gs += N) cp_async<4 * K>(d, gs);
             }
-            in_s += N;
         }
-        ++fetch_s;
         cp_async_commit();
     };
-#pragma unroll
-    for (int d = 0; d < STAGE_DEPTH - 1; ++d) fetch_next();
+    fetch_chunk(s_begin, 0);
 
     // literal-selector LOG/EXP tables -> shared, replicated so that lane (l & 7) of a 128-bit access
     // phase always reads bank group (l & 7): entry e of replica q lives at slot e * TAB_REPL + q.
@@ -295,27 +312,48 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
         }
     }
     unsigned int flags = 0;
-    __syncthreads();                  // s_tab visible (the only block-wide dependency)
+    __shared__ uint32_t s_inv[INV_WORDS];
+    if (tid == 0) {
+        s_inv[0] = (uint32_t)p.n_exec; s_inv[1] = (uint32_t)p.n_latch_ch; s_inv[2] = (uint32_t)(p.n_samples - 1);
+        s_inv[3] = (uint32_t)(p.out_cstride & 0xffffffffu); s_inv[4] = (uint32_t)(p.out_cstride >> 32);
+        s_inv[5] = (uint32_t)p.N;
+    }
+    if (NI > 0 && tid < 2 * NI) {
+        const uint4 w = prog[tid];
+        s_inv[8 + 4 * tid] = w.x; s_inv[9 + 4 * tid] = w.y; s_inv[10 + 4 * tid] = w.z; s_inv[11 + 4 * tid] = w.w;
+    }
+    __syncthreads();                  // s_tab / s_inv visible (the only block-wide dependency)
+    const int n_exec = (int)inv_read(s_inv, 0), n_latch_ch = (int)inv_read(s_inv, 1), last_s = (int)inv_read(s_inv, 2);
+    const size_t out_cstride = (size_t)inv_read(s_inv, 3) | ((size_t)inv_read(s_inv, 4) << 32);
+    const int Nv = (int)inv_read(s_inv, 5);        // N for use inside the sample loop
 
+    uint4 WA[NI > 0 ? NI : 1], WB[NI > 0 ? NI : 1];
+    if (NI > 0) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {             // slots past n_exec hold padding
+            WA[i] = make_uint4(inv_read(s_inv, 8 + 8 * i), inv_read(s_inv, 9 + 8 * i), inv_read(s_inv, 10 + 8 * i), inv_read(s_inv, 11 + 8 * i));
+            WB[i] = make_uint4(inv_read(s_inv, 12 + 8 * i), inv_read(s_inv, 13 + 8 * i), inv_read(s_inv, 14 + 8 * i), inv_read(s_inv, 15 + 8 * i));
+        }
+    }
     const int lane_rep = tid & (TAB_REPL - 1);
     float* out_s = p.out + (size_t)s_begin * N + inst0;   // this thread's slot in the current output row
-    uint32_t stage_s = 0;                                  // byte offset of the current sample's ring slot
-    for (int sidx = s_begin; sidx < s_end; ++sidx, out_s += N) {
+    uint32_t boff = 0;                                     // byte offset of the stage buffer being consumed
+    for (int c0 = s_begin; c0 < s_end; c0 += chunk, boff ^= buf_bytes) {
+      fetch_chunk(c0 + chunk, boff ^ buf_bytes);
+      cp_async_wait<1>();                                          // the chunk starting at c0 has landed
+      const int c_end = min(s_end, c0 + chunk);
+      uint32_t stage_s = boff;                                     // byte offset of the current sample's stage row
+      for (int sidx = c0; sidx < c_end; ++sidx, out_s += Nv, stage_s += row_bytes) {
         {
-            fetch_next();
-            cp_async_wait<STAGE_DEPTH - 1>();                      // the group of sample sidx has landed
             // ---- one sample period: FX8010::process, source/FX8010.cpp:1023-1249 ----
             // The final CCR / latch must be in shared memory when the batch ends (state write-back).
-            const bool last_sample = (sidx == p.n_samples - 1);
+            const bool last_sample = (sidx == last_s);
             bool saw_end[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) { skip[k] = 0; saw_end[k] = false; }
             int pass = 0;
             do {
-                uint4 nA = prog[0], nB = prog[1];
-                for (int pc = 0; pc < p.n_exec; ++pc) {
-                    const uint4 wA = nA, wB = nB;
-                    nA = prog[2 * pc + 2]; nB = prog[2 * pc + 3];     // the slot is padded with one extra instruction
+                auto exec_instr = [&](const uint4 wA, const uint4 wB) {
                     const uint32_t w0 = wA.x;
                     const uint32_t uop = w0 & 0xffu;
                     bool act[K];
@@ -501,10 +539,22 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                         if (!SKIP && (w0 & F_OUT_DIRECT)) {
                             // R was just written by this instruction and nothing later in the sample period
                             // touches the channel: the value is the period's output (:1248)
-                            if (valid) vstore<K>(out_s + (size_t)(w0 >> 24) * p.out_cstride, r);
+                            if (valid) vstore<K>(out_s + (size_t)(w0 >> 24) * out_cstride, r);
                             if (last_sample) vstore<K>(at(wB.w), r);
                         } else if (!SKIP) vstore<K>(at(wB.w), vload<K>(pr));
                         else { float* const pl = at(wB.w); FX_EACH { if (act[k]) pl[k] = pr[k]; } }
+                    }
+                };
+                if (NI > 0) {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i)
+                        if (i < n_exec) exec_instr(WA[i], WB[i]);
+                } else {
+                    uint4 nA = prog[0], nB = prog[1];
+                    for (int pc = 0; pc < n_exec; ++pc) {
+                        const uint4 wA = nA, wB = nB;
+                        nA = prog[2 * pc + 2]; nB = prog[2 * pc + 3]; // the slot is padded with one extra instruction
+                        exec_instr(wA, wB);
                     }
                 }
                 ++pass;
@@ -521,12 +571,12 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                 if (!__any_sync(0xffffffffu, again)) break;
             } while (true);
             if (valid)                                                // :1248 — coalesced, lane = K adjacent instances
-                for (int j = 0; j < p.n_latch_ch; ++j) {
+                for (int j = 0; j < n_latch_ch; ++j) {
                     const uint32_t c = p.latch_ch[j];
-                    vstore<K>(out_s + (size_t)c * p.out_cstride, vload<K>(at(latch0 + c * RS * 4u)));
+                    vstore<K>(out_s + (size_t)c * out_cstride, vload<K>(at(latch0 + c * RS * 4u)));
                 }
-            stage_s = (stage_s + row_bytes) & (STAGE_DEPTH * row_bytes - 1);
         }
+      }
     }
 #undef FX_EACH
 

@@ -58,7 +58,8 @@ template <int K> struct SLCtx {
     const TableEntry* s_tab;        // + lane replica
     const uint4* prog;
     float* out_b;                   // output row of the batch's first sample, this thread's instances
-    int N, inst0;
+    int N, inst0, n_exec;
+    size_t out_cstride;
     bool valid;
     uint32_t boff;                  // byte offset of the current input-stage buffer
     unsigned int flags;
@@ -75,7 +76,8 @@ template <int K> struct SLCtx {
 template <int K, bool FINAL>
 __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const int m_lo, const int m_hi) {
     uint4 nA = cx.prog[0], nB = cx.prog[1];
-    for (int pc = 0; pc < p.n_exec; ++pc) {
+    const int n_exec = cx.n_exec;
+    for (int pc = 0; pc < n_exec; ++pc) {
         const uint4 wA = nA, wB = nB;
         nA = cx.prog[2 * pc + 2]; nB = cx.prog[2 * pc + 3];
         const uint32_t w0 = wA.x;
@@ -91,7 +93,7 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
         const bool st_r = FINAL || !(w0 & F_ST_LAST);
         const bool st_c = FINAL || (w0 & F_CCR);
         const bool st_o = (w0 & F_OUT_DIRECT) && cx.valid;
-        float* const out_c = cx.out_b + (size_t)(w0 >> 24) * p.out_cstride;
+        float* const out_c = cx.out_b + (size_t)(w0 >> 24) * cx.out_cstride;
 #define SL_LD(ptr, stride) vload<K>(reinterpret_cast<const float*>((ptr) + (uint32_t)m * (stride)))
 #define SL_EACH _Pragma("unroll") for (int k = 0; k < K; ++k)
 #define SL_FOR_M _Pragma("unroll 1") for (int m = m_lo; m < m_hi; ++m)
@@ -242,6 +244,7 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
     SLCtx<K> cx;
     cx.col = col; cx.s_tab = s_tab + (tid & (TAB_REPL - 1)); cx.prog = c_prog[p.slot];
     cx.N = N; cx.inst0 = inst0; cx.valid = valid; cx.boff = 0; cx.flags = 0;
+    cx.n_exec = p.n_exec; cx.out_cstride = p.out_cstride;
 #pragma unroll
     for (int k = 0; k < K; ++k) cx.acc_last[k] = 0.0f;
     cx.out_b = p.out + (size_t)s_begin * N + inst0;
