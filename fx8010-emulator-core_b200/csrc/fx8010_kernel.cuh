@@ -59,8 +59,9 @@ constexpr int MAX_CHUNK = 64;             // input stage: two buffers of `chunk`
                                          // other is in flight (a recurrence needs ~30 sample rows in flight per thread to
                                          // cover HBM latency at full bandwidth)
 constexpr int MAX_SMEM_TABLES = 2;       // LOG/EXP tables replicated into shared memory
-constexpr int TAB_REPL = 8;              // replicas: one per lane of a 128-bit access phase
-constexpr int TAB_SMEM_BYTES = FX8010_TABLE_ENTRIES * TAB_REPL * 16;   // 8 KiB per table
+constexpr int TAB_REPL = 2;              // replicas per table entry (lane parity picks one): measured best of 1/2/4/8 — more replicas cut gather
+                                         // bank conflicts but cost more per-block start-up copy than they save
+constexpr int TAB_SMEM_BYTES = FX8010_TABLE_ENTRIES * TAB_REPL * 16;   // 2 KiB per table
 
 struct __align__(16) TableEntry { double y1, slope; }; // T[i], (T[i+1]-T[i])/(x2-x1) — host-computed in IEEE double
 
@@ -270,8 +271,8 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
     };
     fetch_chunk(s_begin, 0);
 
-    // literal-selector LOG/EXP tables -> shared, replicated so that lane (l & 7) of a 128-bit access
-    // phase always reads bank group (l & 7): entry e of replica q lives at slot e * TAB_REPL + q.
+    // literal-selector LOG/EXP tables -> shared; entry e of replica q lives at slot e * TAB_REPL + q and lane l
+    // reads replica l % TAB_REPL, which spreads the 128-bit gathers over more bank groups.
     for (int t = 0; t < p.n_smem_tabs; ++t) {
         const TableEntry* src = p.tabs + (size_t)p.smem_tab_id[t] * FX8010_TABLE_ENTRIES;
 #pragma unroll 4
