@@ -492,31 +492,38 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                             const bool isx = (uop == U_XREAD);
                             const float* const ring = isx ? p.xtram : p.itram;
                             const int size = isx ? p.xtram_size : p.itram_size;
+                            int ridx[K];
+                            bool same = true;                         // all K contexts active and at the same ring position
                             FX_EACH {
                                 int32_t& rp = isx ? xr[k] : ir[k];
-                                if (act[k]) {
-                                    const int pos = min(max(cvt_x86(y[k]), 0), size - 1);
-                                    int idx = rp - pos;
-                                    idx += (idx < 0) ? size : 0;      // rule U1: mathematical modulo
-                                    rp = (rp + 1 == size) ? 0 : rp + 1;
-                                    pa[k] = ring[(size_t)idx * N + inst0 + k];
-                                }
-                            } }
+                                const int pos = min(max(cvt_x86(y[k]), 0), size - 1);
+                                int idx = rp - pos;
+                                idx += (idx < 0) ? size : 0;          // rule U1: mathematical modulo
+                                ridx[k] = idx;
+                                if (act[k]) rp = (rp + 1 == size) ? 0 : rp + 1;
+                                same = same && act[k] && (idx == ridx[0]);
+                            }
+                            if (K > 1 && same) vstore<K>(pa, vload<K>(ring + (size_t)ridx[0] * N + inst0));   // one coalesced 8/16-byte access
+                            else { FX_EACH { if (act[k]) pa[k] = ring[(size_t)ridx[k] * N + inst0 + k]; } }
+                        }
                         writes_r = false; break;
                     case U_IWRITE: case U_XWRITE:                     // :1195-1198 / :1207-1210, writeSmallDelay :909-917
                         if (EXT) { FX_LOAD_A; FX_LOAD_Y;
                             const bool isx = (uop == U_XWRITE);
                             float* const ring = isx ? p.xtram : p.itram;
                             const int size = isx ? p.xtram_size : p.itram_size;
+                            int widx[K];
+                            bool same = true;
                             FX_EACH {
                                 int32_t& wp = isx ? xw[k] : iw[k];
-                                if (act[k]) {
-                                    const int pos = min(max(cvt_x86(y[k]), 0), size - 1);
-                                    const int idx = wp + pos;         // the reference does not wrap wp + pos: slots at or
-                                    if (idx < size && valid) ring[(size_t)idx * N + inst0 + k] = a[k]; // beyond the ring are never read back
-                                    wp = (wp + 1 == size) ? 0 : wp + 1;
-                                }
-                            } }
+                                const int pos = min(max(cvt_x86(y[k]), 0), size - 1);
+                                widx[k] = wp + pos;                   // the reference does not wrap wp + pos: slots at or beyond
+                                if (act[k]) wp = (wp + 1 == size) ? 0 : wp + 1;   // the ring are never read back -> dropped
+                                same = same && act[k] && (widx[k] == widx[0]);
+                            }
+                            if (K > 1 && same) { if (widx[0] < size && valid) vstore<K>(ring + (size_t)widx[0] * N + inst0, a); }
+                            else { FX_EACH { if (act[k] && widx[k] < size && valid) ring[(size_t)widx[k] * N + inst0 + k] = a[k]; } }
+                        }
                         writes_r = false; break;
                     case U_END:                                       // :1212-1215
                         FX_EACH { if (act[k]) saw_end[k] = true; }
