@@ -342,3 +342,95 @@ def test_facade_per_sample_process_matches_reference_driver(fx, po):
     assert p.instruction_counter == 64
     assert p.get_register("nonexistent") == 1.0 and p.set_register("nonexistent", 0.0) == 1
     p.close()
+
+
+# ---- edge cases ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5])
+def test_tiny_instance_counts(fx, po, n):
+    rng = np.random.default_rng(20 + n)
+    run_case(fx, po, progs.CFG2_LOG_GAIN, n, [9, 1, 30], rng, controls={"volume": rng.random(n).astype(np.float32)}, what=f"cfg2 n={n}")
+    run_case(fx, po, progs.random_program(rng, 40, xtram=True), n, [17, 8], rng, what=f"random n={n}")
+
+
+def test_zero_samples_and_long_batch(fx, po):
+    rng = np.random.default_rng(30)
+    prog, img, orc, gpu = make_pair(fx, po, progs.CFG4_ONEPOLE, 8)
+    try:
+        assert gpu.process_host(np.zeros((1, 0, 8), np.float32)).shape == (1, 0, 8)
+        x = (1.8 * rng.random((1, 5000, 8)) - 0.9).astype(np.float32)
+        assert_bits_equal(gpu.process_host(x), orc.process(x), "5000-sample batch")
+        compare_state(gpu, orc, img, "long batch")
+    finally:
+        gpu.close()
+
+
+def test_maximum_program_length(fx, po):
+    """1 000 instructions (FX8010_MAX_INSTRUCTIONS) run; one more is refused with ERR_CAPACITY."""
+    rng = np.random.default_rng(31)
+    text = progs.random_program(rng, 999 - 1, skip=True, tram=True, noise=True)      # + 1 output driver + END = 1000
+    prog = fx.Program(text)
+    assert prog.loaded and len(prog.instructions()) == 1000
+    run_case(fx, po, text, 32, [6], rng, what="1000 instructions")
+    big = fx.Program(progs.random_program(rng, 999, skip=False, tram=False, noise=False))
+    assert big.loaded and len(big.instructions()) == 1001
+    g = fx.Gpu(4, 1)
+    try:
+        with pytest.raises(fx.FxError) as e:
+            g.load_program(big)
+        assert e.value.code == 5
+    finally:
+        g.close()
+
+
+def test_program_slots_are_limited_and_recycled(fx):
+    """Two constant-memory program slots per device: a third loaded handle is refused until one is destroyed."""
+    p = fx.Program(progs.CFG1A_TESTCODE)
+    a, b, c = fx.Gpu(4, 1), fx.Gpu(4, 1), fx.Gpu(4, 1)
+    try:
+        a.load_program(p); b.load_program(p)
+        with pytest.raises(fx.FxError) as e:
+            c.load_program(p)
+        assert e.value.code == 5
+        a.close()
+        c.load_program(p)
+        x = np.full((1, 3, 4), 0.5, np.float32)
+        assert np.array_equal(b.process_host(x), c.process_host(x))
+    finally:
+        a.close(); b.close(); c.close()
+
+
+def test_full_size_xtram(fx, po):
+    """xtramsize 1048576 (MAX_XDELAY_SIZE, include/FX8010.h:42): 4 MiB ring per instance."""
+    rng = np.random.default_rng(32)
+    text = ("static a\nstatic rd\ninput in_l 0\noutput out_l 0\nxtramsize 1048576 \nxdelay read, rd, at, 0\nmacs a, in_l, rd, 0.5\n"
+            "xdelay write, a, at, 0\nxdelay read, rd, at, 5\nmacs out_l, in_l, rd, 0.5\nend")
+    prog, img, orc, gpu = make_pair(fx, po, text, 8)
+    try:
+        ptr = np.zeros((4, 8), np.int32); ptr[2] = 1048570; ptr[3] = 1048572      # pointers about to wrap
+        gpu.set_scalars(ptrs=ptr); orc.tram_ptrs[:] = ptr
+        x = (1.8 * rng.random((1, 40, 8)) - 0.9).astype(np.float32)
+        assert_bits_equal(gpu.process_host(x), orc.process(x), "xtram outputs")
+        compare_state(gpu, orc, img, "xtram", tram_instances=(0, 7))
+    finally:
+        gpu.close()
+
+
+def test_literal_register_overwritten_through_api(fx, po):
+    """setRegisterValue can write ANY register, literals included (source/FX8010.cpp:236-253).  The LOG selector
+    '3' and the MACS addend '0' are folded at encode time while they are uniform; writing them must undo that."""
+    rng = np.random.default_rng(33)
+    n = 128
+    prog, img, orc, gpu = make_pair(fx, po, progs.CFG1B_LOGTUBE, n)
+    try:
+        x = (1.8 * rng.random((1, 20, n)) - 0.9).astype(np.float32)
+        assert_bits_equal(gpu.process_host(x), orc.process(x), "before")
+        sel = rng.integers(0, 32, n).astype(np.float32); add = (0.2 * rng.random(n)).astype(np.float32)
+        for name, v in (("3", sel), ("0", add)):
+            gpu.set_controls(prog.reg_index(name), v); orc.set_register(name, v)
+        assert_bits_equal(gpu.process_host(x), orc.process(x), "per-instance literals")
+        gpu.set_controls(prog.reg_index("3"), [7.0], broadcast=True); orc.set_register("3", np.full(n, 7.0, np.float32))
+        assert_bits_equal(gpu.process_host(x), orc.process(x), "broadcast literal")
+        compare_state(gpu, orc, img, "literals")
+    finally:
+        gpu.close()
