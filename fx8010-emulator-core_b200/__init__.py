@@ -78,6 +78,7 @@ GPU_SYMBOLS = {
     "fx8010_gpu_get_register": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "fx8010_gpu_process_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fx8010_gpu_process_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "fx8010_gpu_process_batch_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fx8010_gpu_host_alloc": (C.c_void_p, [C.c_size_t]),
     "fx8010_gpu_host_free": (None, [C.c_void_p]),
     "fx8010_gpu_synchronize": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -382,8 +383,9 @@ class Gpu:
         self._check(self.L.fx8010_gpu_process_batch_host(self.h, _ptr(x), _ptr(out), n_samples))
         return out
 
-    def process_host_ptr(self, in_ptr: int, out_ptr: int, n_samples: int):
-        self._check(self.L.fx8010_gpu_process_batch_host(self.h, in_ptr, out_ptr, n_samples))
+    def process_host_ptr(self, in_ptr: int, out_ptr: int, n_samples: int, wait: bool = True):
+        f = self.L.fx8010_gpu_process_batch_host if wait else self.L.fx8010_gpu_process_batch_host_async
+        self._check(f(self.h, in_ptr, out_ptr, n_samples))
 
     def synchronize(self, stream=None):
         self._check(self.L.fx8010_gpu_synchronize(self.h, stream))

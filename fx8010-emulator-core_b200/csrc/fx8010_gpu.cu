@@ -89,6 +89,7 @@ struct fx8010_gpu {
     cudaEvent_t ev_h2d[HOST_PIPE_BUFS] = {}, ev_comp[HOST_PIPE_BUFS] = {}, ev_d2h[HOST_PIPE_BUFS] = {};
     float* d_stage_in[HOST_PIPE_BUFS] = {}; float* d_stage_out[HOST_PIPE_BUFS] = {};
     size_t stage_floats = 0;
+    unsigned long long pipe_seq = 0;             // sub-blocks pushed through the staging buffers so far
     // tuning overrides (0 = heuristic)
     int tune_K = 0, tune_B = 0, tune_seg = 0, tune_sub = 0;
     std::string err;
@@ -931,10 +932,12 @@ int fx8010_gpu_process_batch(fx8010_gpu* h, const float* d_in, float* d_out, int
     FX_NEED_PROGRAM(h);
     if (!d_out || n_samples < 0) return fail(h, FX8010_ERR_ARG, "d_out is NULL or n_samples negative");
     const size_t cs = (size_t)n_samples * h->N;
+    // queued host-buffer batches (process_batch_host_async) run on an internal stream: they come first
+    if (h->last_stream == h->s_comp && (cudaStream_t)stream != h->s_comp) FX_CUDA(h, cudaStreamSynchronize(h->s_comp));
     return launch_block(h, d_in, d_out, cs, cs, n_samples, (cudaStream_t)stream);
 }
 
-int fx8010_gpu_process_batch_host(fx8010_gpu* h, const float* in, float* out, int n_samples) {
+static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_samples, bool wait) {
     FX_NEED_PROGRAM(h);
     if (!out || n_samples < 0) return fail(h, FX8010_ERR_ARG, "out is NULL or n_samples negative");
     if (n_samples == 0) return FX8010_OK;
@@ -951,29 +954,28 @@ int fx8010_gpu_process_batch_host(fx8010_gpu* h, const float* in, float* out, in
             cudaFree(h->d_stage_in[i]); cudaFree(h->d_stage_out[i]);
             h->d_stage_in[i] = h->d_stage_out[i] = nullptr;
         }
-        h->stage_floats = 0;
+        h->stage_floats = 0; h->pipe_seq = 0;
         for (int i = 0; i < HOST_PIPE_BUFS; ++i) {
             FX_CUDA(h, cudaMalloc(&h->d_stage_in[i], sizeof(float) * need));
             FX_CUDA(h, cudaMalloc(&h->d_stage_out[i], sizeof(float) * need));
         }
         h->stage_floats = need;
     }
-    if (h->last_stream) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));   // earlier device-side batches come first
-    int b = 0;
-    for (long s0 = 0; s0 < n_samples; s0 += sub, ++b) {
-        const int buf = b % HOST_PIPE_BUFS;
+    if (h->last_stream && h->last_stream != h->s_comp) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));   // earlier device-side batches come first
+    // pipe_seq counts sub-blocks over the life of the staging buffers, so that asynchronous calls chain:
+    // sub-block q reuses the buffers of sub-block q - HOST_PIPE_BUFS once those have been consumed / drained
+    for (long s0 = 0; s0 < n_samples; s0 += sub, ++h->pipe_seq) {
+        const int buf = (int)(h->pipe_seq % HOST_PIPE_BUFS);
         const long len = std::min<long>(sub, n_samples - s0);
-        if (b >= HOST_PIPE_BUFS) FX_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_comp[buf], 0));     // stage_in[buf] consumed
+        if (h->pipe_seq >= HOST_PIPE_BUFS) FX_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_comp[buf], 0));     // stage_in[buf] consumed
         if (in)
             for (size_t c = 0; c < C; ++c)
                 FX_CUDA(h, cudaMemcpyAsync(h->d_stage_in[buf] + c * (size_t)sub * N, in + (c * (size_t)n_samples + s0) * N,
                                            sizeof(float) * len * N, cudaMemcpyHostToDevice, h->s_h2d));
         FX_CUDA(h, cudaEventRecord(h->ev_h2d[buf], h->s_h2d));
         FX_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_h2d[buf], 0));
-        if (b >= HOST_PIPE_BUFS) FX_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_d2h[buf], 0));    // stage_out[buf] drained
-        const cudaStream_t keep = h->last_stream;
+        if (h->pipe_seq >= HOST_PIPE_BUFS) FX_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_d2h[buf], 0));    // stage_out[buf] drained
         const int rc = launch_block(h, in ? h->d_stage_in[buf] : nullptr, h->d_stage_out[buf], (size_t)sub * N, (size_t)sub * N, (int)len, h->s_comp);
-        h->last_stream = keep;
         if (rc) return rc;
         FX_CUDA(h, cudaEventRecord(h->ev_comp[buf], h->s_comp));
         FX_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[buf], 0));
@@ -982,8 +984,15 @@ int fx8010_gpu_process_batch_host(fx8010_gpu* h, const float* in, float* out, in
                                        sizeof(float) * len * N, cudaMemcpyDeviceToHost, h->s_d2h));
         FX_CUDA(h, cudaEventRecord(h->ev_d2h[buf], h->s_d2h));
     }
-    FX_CUDA(h, cudaStreamSynchronize(h->s_d2h));
+    if (wait) FX_CUDA(h, cudaStreamSynchronize(h->s_d2h));
     return FX8010_OK;
+}
+
+int fx8010_gpu_process_batch_host(fx8010_gpu* h, const float* in, float* out, int n_samples) {
+    return process_host_impl(h, in, out, n_samples, true);
+}
+int fx8010_gpu_process_batch_host_async(fx8010_gpu* h, const float* in, float* out, int n_samples) {
+    return process_host_impl(h, in, out, n_samples, false);
 }
 
 int fx8010_gpu_synchronize(fx8010_gpu* h, void* stream) {

@@ -143,6 +143,11 @@ FX8010_API int fx8010_gpu_process_batch(fx8010_gpu* h, const float* d_in, float*
  * device→host copy are pipelined over sample sub-blocks on internal streams; returns when
  * `out` is complete. */
 FX8010_API int fx8010_gpu_process_batch_host(fx8010_gpu* h, const float* in, float* out, int n_samples);
+/* Same, but returns as soon as the work is queued: `in` must stay untouched and `out` unread until
+ * fx8010_gpu_synchronize(h, NULL).  Consecutive calls chain in order on the handle's internal streams, so the
+ * host->device copy of one block overlaps the device->host copy of the previous one (needs page-locked
+ * buffers; with pageable memory the driver makes the copies synchronous anyway). */
+FX8010_API int fx8010_gpu_process_batch_host_async(fx8010_gpu* h, const float* in, float* out, int n_samples);
 
 /* Page-locked host memory for process_batch_host buffers: with these the host<->device copies run
  * asynchronously at full PCIe rate (pageable buffers work too, through the driver's staging). */

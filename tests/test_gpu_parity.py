@@ -434,3 +434,30 @@ def test_literal_register_overwritten_through_api(fx, po):
         compare_state(gpu, orc, img, "literals")
     finally:
         gpu.close()
+
+
+def test_async_host_batches_chain_in_order(fx, po):
+    """fx8010_gpu_process_batch_host_async: queued calls on a stateful program keep their order and their
+    state; outputs are complete after fx8010_gpu_synchronize; a device-pointer call afterwards waits for them."""
+    import torch
+    rng = np.random.default_rng(40)
+    n, s, calls = 512, 300, 7
+    text = progs.random_program(rng, 30, xtram=True)
+    prog, img, orc, gpu = make_pair(fx, po, text, n)
+    try:
+        ins = [fx.pinned_array((1, s, n)) for _ in range(calls)]
+        outs = [fx.pinned_array((1, s, n)) for _ in range(calls)]
+        for a, _ in ins:
+            a[...] = (1.8 * rng.random((1, s, n)) - 0.9).astype(np.float32)
+        for (a, _), (b, _) in zip(ins, outs):
+            gpu.process_host_ptr(a.ctypes.data, b.ctypes.data, s, wait=False)
+        d_x = torch.from_numpy(ins[0][0].copy()).cuda(); d_y = torch.empty_like(d_x)
+        torch.cuda.synchronize()
+        gpu.process_device(d_x, d_y, s, None)                 # must run after the queued host batches
+        gpu.synchronize(None)
+        for k, ((a, _), (b, _)) in enumerate(zip(ins, outs)):
+            assert_bits_equal(b, orc.process(a), f"async call {k}")
+        assert_bits_equal(d_y.cpu().numpy(), orc.process(ins[0][0]), "device call after async")
+        compare_state(gpu, orc, img, "async")
+    finally:
+        gpu.close()
