@@ -561,7 +561,7 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     int B = h->tune_B ? h->tune_B : 128;
     while (B > 32 && (N / K + B - 1) / B * B >= 2 * (N / K) && N / K <= B / 2) B >>= 1;      // tiny N: do not launch mostly-idle blocks
     int M = h->tune_M ? h->tune_M : 4;
-    while (M > 1 && sl_smem_bytes(h, B, K, M) > 48 * 1024) M >>= 1;
+    while (!h->tune_M && M > 1 && sl_smem_bytes(h, B, K, M) > 48 * 1024) M >>= 1;
     while (sl_smem_bytes(h, B, K, M) > h->smem_optin && B > 32) B >>= 1;
     if (sl_smem_bytes(h, B, K, M) > h->smem_optin) return fail(h, FX8010_ERR_CAPACITY, "register file does not fit in shared memory");
     L.K = K; L.B = B; L.M = M; L.chunk = 0;
@@ -570,7 +570,9 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_sl_kernel(K), B, L.smem);
     occ = std::max(occ, 1);
-    long n_seg = std::max(1L, (long)h->num_sms * occ / L.grid_x);
+    // half a wave per launch: with programmatic dependent launch two consecutive launches share the SMs, and
+    // fewer, longer segments spend fewer instructions on per-thread start-up
+    long n_seg = std::max(1L, (long)h->num_sms * occ / (2 * L.grid_x));
     if (h->tune_seg) n_seg = h->tune_seg;
     n_seg = std::min<long>(n_seg, std::max(1, n_samples / M));
     int seg_len = (int)((n_samples + n_seg - 1) / n_seg);

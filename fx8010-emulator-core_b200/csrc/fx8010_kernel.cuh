@@ -127,6 +127,24 @@ template <int K> __device__ __forceinline__ void vstore(float* p, const Vec<K>& 
     *reinterpret_cast<typename VT<K>::T*>(p) = t;
 }
 
+// Explicit shared-space accessors on 32-bit shared addresses: no generic->shared window arithmetic in the
+// inner loops (ptxas otherwise rebuilds the window base from SR_CgaCtaId next to many accesses).
+template <int K> __device__ __forceinline__ Vec<K> lds(uint32_t a) {
+    Vec<K> r;
+    if (K == 4) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[K > 1 ? 1 : 0]), "=f"(r.v[K > 2 ? 2 : 0]), "=f"(r.v[K > 3 ? 3 : 0]) : "r"(a));
+    else if (K == 2) asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[K > 1 ? 1 : 0]) : "r"(a));
+    else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r.v[0]) : "r"(a));
+    return r;
+}
+template <int K> __device__ __forceinline__ void sts(uint32_t a, const Vec<K>& r) {
+    if (K == 4) asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(r.v[0]), "f"(r.v[K > 1 ? 1 : 0]), "f"(r.v[K > 2 ? 2 : 0]), "f"(r.v[K > 3 ? 3 : 0]) : "memory");
+    else if (K == 2) asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(r.v[0]), "f"(r.v[K > 1 ? 1 : 0]) : "memory");
+    else asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(r.v[0]) : "memory");
+}
+__device__ __forceinline__ void lds_f64x2(uint32_t a, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+
 // ---- exact scalar semantics ----------------------------------------------------------------
 
 // static_cast<int32_t>(float) on x86-64 (cvttss2si): NaN / out of range -> 0x80000000

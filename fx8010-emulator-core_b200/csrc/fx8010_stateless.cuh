@@ -54,8 +54,8 @@ struct SLParams {
 
 // Per-thread context of the stateless kernel, handed to the batch executor.
 template <int K> struct SLCtx {
-    unsigned char* col;             // this thread's shared-memory column
-    const TableEntry* s_tab;        // + lane replica
+    uint32_t col_s;                 // this thread's shared-memory column (32-bit shared address)
+    uint32_t tab_s;                 // staged tables + this lane's replica (32-bit shared address)
     const uint4* prog;
     float* out_b;                   // output row of the batch's first sample, this thread's instances
     int N, inst0, n_exec;
@@ -73,87 +73,87 @@ template <int K> struct SLCtx {
 //                  write-back needs (all result registers, CCR, output latch, accumulator) and nothing
 //                  to the output block.  Stateless programs are idempotent per sample, so the re-run
 //                  reproduces the same values.
+// All operand addresses are running 32-bit shared addresses (one add per operand and sample).
 template <int K, bool FINAL>
 __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const int m_lo, const int m_hi) {
     uint4 nA = cx.prog[0], nB = cx.prog[1];
     const int n_exec = cx.n_exec;
+    const int n_m = m_hi - m_lo;
     for (int pc = 0; pc < n_exec; ++pc) {
         const uint4 wA = nA, wB = nB;
         nA = cx.prog[2 * pc + 2]; nB = cx.prog[2 * pc + 3];
         const uint32_t w0 = wA.x;
         const uint32_t uop = w0 & 0xffu;
-        // decode once per batch: base address and per-sample stride of every operand, store modes
-#define SL_BASE(w) (cx.col + ((w) & SL_OFF_MASK) + (((w) & SL_BUF) ? cx.boff : 0u))
+        // decode once per batch: address of sample m_lo and per-sample stride of every operand, store modes
 #define SL_STRIDE(w) ((((w) >> SL_STRIDE_SHIFT) & 0x7ffu) << 4)
-        unsigned char* const pr = SL_BASE(wA.y); const uint32_t sr = SL_STRIDE(wA.y);
-        const unsigned char* const pa = SL_BASE(wA.z); const uint32_t sa = SL_STRIDE(wA.z);
-        const unsigned char* const px = SL_BASE(wA.w); const uint32_t sx = SL_STRIDE(wA.w);
-        const unsigned char* const py = SL_BASE(wB.x); const uint32_t sy = SL_STRIDE(wB.x);
-        unsigned char* const pccr = SL_BASE(wB.z); const uint32_t sccr = SL_STRIDE(wB.z);
+#define SL_ADDR(w) (cx.col_s + ((w) & SL_OFF_MASK) + (((w) & SL_BUF) ? cx.boff : 0u) + (uint32_t)m_lo * SL_STRIDE(w))
+        const uint32_t sr = SL_STRIDE(wA.y), sa = SL_STRIDE(wA.z), sx = SL_STRIDE(wA.w), sy = SL_STRIDE(wB.x), sccr = SL_STRIDE(wB.z);
+        uint32_t qr = SL_ADDR(wA.y), qa = SL_ADDR(wA.z), qx = SL_ADDR(wA.w), qy = SL_ADDR(wB.x), qccr = SL_ADDR(wB.z);
         const bool st_r = FINAL || !(w0 & F_ST_LAST);
         const bool st_c = FINAL || (w0 & F_CCR);
         const bool st_o = (w0 & F_OUT_DIRECT) && cx.valid;
-        float* const out_c = cx.out_b + (size_t)(w0 >> 24) * cx.out_cstride;
-#define SL_LD(ptr, stride) vload<K>(reinterpret_cast<const float*>((ptr) + (uint32_t)m * (stride)))
+        float* qo = cx.out_b + (size_t)(w0 >> 24) * cx.out_cstride + (size_t)m_lo * cx.N;
+        const int N = cx.N;
 #define SL_EACH _Pragma("unroll") for (int k = 0; k < K; ++k)
-#define SL_FOR_M _Pragma("unroll 1") for (int m = m_lo; m < m_hi; ++m)
-        // R store (:1079-1082 etc.), setCCR (:211-232), output (:1229-1233, :1248) for sample m of the batch
+#define SL_FOR_M _Pragma("unroll 1") for (int m = 0; m < n_m; ++m, qr += sr, qa += sa, qx += sx, qy += sy, qccr += sccr, qo += N)
+        // R store (:1079-1082 etc.), setCCR (:211-232), output (:1229-1233, :1248) for the current sample
 #define SL_WRITE(SETS_ACC)                                                                                       \
         {                                                                                                        \
-            if (st_r) vstore<K>(reinterpret_cast<float*>(pr + (uint32_t)m * sr), r);                              \
-            if (st_c) { Vec<K> c; SL_EACH { c[k] = ccr_of(r[k]); }                                                \
-                        vstore<K>(reinterpret_cast<float*>(pccr + (uint32_t)m * sccr), c); }                      \
-            if (!FINAL) { if (st_o) vstore<K>(out_c + (size_t)m * cx.N, r); }                                     \
+            if (st_r) sts<K>(qr, r);                                                                             \
+            if (st_c) { Vec<K> c; SL_EACH { c[k] = ccr_of(r[k]); } sts<K>(qccr, c); }                             \
+            if (!FINAL) { if (st_o) vstore<K>(qo, r); }                                                          \
             else {                                                                                               \
                 if (st_o) vstore<K>(p.latch + (size_t)(w0 >> 24) * cx.N + cx.inst0, r);                           \
                 if (SETS_ACC) cx.acc_last = accv;                                                                \
             }                                                                                                    \
         }
+#define SL_LOAD3 const Vec<K> a = lds<K>(qa), x = lds<K>(qx), y = lds<K>(qy); Vec<K> r, accv;
         switch (uop) {
-        case U_MACS: SL_FOR_M { const Vec<K> a = SL_LD(pa, sa), x = SL_LD(px, sx), y = SL_LD(py, sy); Vec<K> r, accv;
+        case U_MACS: SL_FOR_M { SL_LOAD3
             SL_EACH { accv[k] = __fadd_rn(a[k], __fmul_rn(x[k], y[k])); r[k] = sat1(accv[k]); } SL_WRITE(true) } break;
-        case U_MACSN: SL_FOR_M { const Vec<K> a = SL_LD(pa, sa), x = SL_LD(px, sx), y = SL_LD(py, sy); Vec<K> r, accv;
+        case U_MACSN: SL_FOR_M { SL_LOAD3
             SL_EACH { accv[k] = __fsub_rn(a[k], __fmul_rn(x[k], y[k])); r[k] = sat1(accv[k]); } SL_WRITE(true) } break;
-        case U_ACC3: SL_FOR_M { const Vec<K> a = SL_LD(pa, sa), x = SL_LD(px, sx), y = SL_LD(py, sy); Vec<K> r, accv;
+        case U_ACC3: SL_FOR_M { SL_LOAD3
             SL_EACH { accv[k] = __fadd_rn(__fadd_rn(a[k], x[k]), y[k]); r[k] = sat1(accv[k]); } SL_WRITE(true) } break;
-        case U_MACW: SL_FOR_M { const Vec<K> a = SL_LD(pa, sa), x = SL_LD(px, sx), y = SL_LD(py, sy); Vec<K> r, accv;
+        case U_MACW: SL_FOR_M { SL_LOAD3
             SL_EACH { r[k] = __fadd_rn(a[k], wrap1(__fmul_rn(x[k], y[k]))); accv[k] = r[k]; } SL_WRITE(true) } break;
-        case U_MACWN: SL_FOR_M { const Vec<K> a = SL_LD(pa, sa), x = SL_LD(px, sx), y = SL_LD(py, sy); Vec<K> r, accv;
+        case U_MACWN: SL_FOR_M { SL_LOAD3
             SL_EACH { r[k] = __fsub_rn(a[k], wrap1(__fmul_rn(x[k], y[k]))); accv[k] = r[k]; } SL_WRITE(true) } break;
-        case U_MACINTW: SL_FOR_M { const Vec<K> a = SL_LD(pa, sa), x = SL_LD(px, sx), y = SL_LD(py, sy); Vec<K> r, accv;
+        case U_MACINTW: SL_FOR_M { SL_LOAD3
             SL_EACH { r[k] = wrap1(__fadd_rn(a[k], __fmul_rn(x[k], y[k]))); accv[k] = r[k]; } SL_WRITE(true) } break;
-        case U_ANDXOR: SL_FOR_M { const Vec<K> a = SL_LD(pa, sa), x = SL_LD(px, sx), y = SL_LD(py, sy); Vec<K> r, accv;
+        case U_ANDXOR: SL_FOR_M { SL_LOAD3
             SL_EACH { r[k] = __int2float_rn(logic_ops(a[k], x[k], y[k])); accv[k] = 0.0f; } SL_WRITE(false) } break;
-        case U_TSTNEG: SL_FOR_M { const Vec<K> a = SL_LD(pa, sa), x = SL_LD(px, sx), y = SL_LD(py, sy); Vec<K> r, accv;
+        case U_TSTNEG: SL_FOR_M { SL_LOAD3
             SL_EACH {
                 const int32_t q = cvt_x86(__fmul_rn(x[k], 2147483648.0f));
                 r[k] = (a[k] >= y[k]) ? x[k] : __fmul_rn(__int2float_rn(~q), 4.656612873077392578125e-10f); accv[k] = r[k];
             } SL_WRITE(true) } break;
-        case U_LIMIT: SL_FOR_M { const Vec<K> a = SL_LD(pa, sa), x = SL_LD(px, sx), y = SL_LD(py, sy); Vec<K> r, accv;
+        case U_LIMIT: SL_FOR_M { SL_LOAD3
             SL_EACH { r[k] = (a[k] >= y[k]) ? x[k] : y[k]; accv[k] = r[k]; } SL_WRITE(true) } break;
-        case U_LIMITN: SL_FOR_M { const Vec<K> a = SL_LD(pa, sa), x = SL_LD(px, sx), y = SL_LD(py, sy); Vec<K> r, accv;
+        case U_LIMITN: SL_FOR_M { SL_LOAD3
             SL_EACH { r[k] = (a[k] < y[k]) ? x[k] : y[k]; accv[k] = r[k]; } SL_WRITE(true) } break;
-        case U_INTERP: SL_FOR_M { const Vec<K> a = SL_LD(pa, sa), x = SL_LD(px, sx), y = SL_LD(py, sy); Vec<K> r, accv;
+        case U_INTERP: SL_FOR_M { SL_LOAD3
             SL_EACH {
                 const double d = __dadd_rn(__dmul_rn(__dsub_rn(1.0, (double)x[k]), (double)a[k]), (double)__fmul_rn(x[k], y[k]));
                 accv[k] = __double2float_rn(d); r[k] = sat1(accv[k]);
             } SL_WRITE(true) } break;
         case U_LOG:
         case U_EXP: {
-            const TableEntry* const tb_s = cx.s_tab + (size_t)(wB.y >> 24) * (FX8010_TABLE_ENTRIES * TAB_REPL);
+            const uint32_t tb_s = cx.tab_s + (wB.y >> 24) * (uint32_t)TAB_SMEM_BYTES;
             SL_FOR_M {
-                const Vec<K> a = SL_LD(pa, sa);
+                const Vec<K> a = lds<K>(qa);
                 Vec<K> r, accv;
                 int idx[K];
+                double xd[K];
                 bool wild = false;
-                SL_EACH { wild |= !(fabsf(a[k]) <= 1.0f); }
-                if (!wild) { SL_EACH { idx[k] = table_index_inrange((double)a[k]); } }
+                SL_EACH { wild |= !(fabsf(a[k]) <= 1.0f); xd[k] = (double)a[k]; }
+                if (!wild) { SL_EACH { idx[k] = table_index_inrange(xd[k]); } }
                 else { SL_EACH { idx[k] = table_index_wild(a[k]); if (!(fabsf(a[k]) <= 1.0f)) cx.flags |= FX8010_RT_TABLE_RANGE; } }   // rule U6
                 if (w0 & F_TAB_SMEM) {
-                    SL_EACH { const TableEntry e = tb_s[idx[k] * TAB_REPL]; r[k] = table_finish((double)a[k], idx[k], e.y1, e.slope); }
+                    SL_EACH { double y1, slope; lds_f64x2(tb_s + (uint32_t)idx[k] * (TAB_REPL * 16u), y1, slope); r[k] = table_finish(xd[k], idx[k], y1, slope); }
                 } else {
                     Vec<K> x;
-                    if (!(w0 & F_TAB_IMM)) x = SL_LD(px, sx);
+                    if (!(w0 & F_TAB_IMM)) x = lds<K>(qx);
                     SL_EACH {
                         int tsel;
                         if (w0 & F_TAB_IMM) tsel = (int)(wB.y >> 24);
@@ -163,7 +163,7 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
                             tsel = (uop == U_EXP ? FX8010_TABLE_COUNT : 0) + sel;
                         }
                         const double2 e = __ldg(reinterpret_cast<const double2*>(p.tabs + tsel * FX8010_TABLE_ENTRIES + idx[k]));
-                        r[k] = table_finish((double)a[k], idx[k], e.x, e.y);
+                        r[k] = table_finish(xd[k], idx[k], e.x, e.y);
                     }
                 }
                 SL_EACH { accv[k] = r[k]; }
@@ -172,10 +172,11 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
             break; }
         default: break;      // nothing else can appear in a stateless program's encoded stream
         }
-#undef SL_LD
 #undef SL_EACH
 #undef SL_FOR_M
 #undef SL_WRITE
+#undef SL_LOAD3
+#undef SL_ADDR
     }
 }
 
@@ -242,7 +243,9 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
     __syncthreads();
 
     SLCtx<K> cx;
-    cx.col = col; cx.s_tab = s_tab + (tid & (TAB_REPL - 1)); cx.prog = c_prog[p.slot];
+    cx.col_s = (uint32_t)__cvta_generic_to_shared(col);
+    cx.tab_s = (uint32_t)__cvta_generic_to_shared(s_tab) + (uint32_t)(tid & (TAB_REPL - 1)) * 16u;
+    cx.prog = c_prog[p.slot];
     cx.N = N; cx.inst0 = inst0; cx.valid = valid; cx.boff = 0; cx.flags = 0;
     cx.n_exec = p.n_exec; cx.out_cstride = p.out_cstride;
 #pragma unroll
@@ -273,7 +276,6 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
         cx.boff ^= buf_bytes;
     }
     if (cx.flags) atomicOr(p.rt_flags, cx.flags);
-#undef SL_BASE
 #undef SL_STRIDE
 }
 
