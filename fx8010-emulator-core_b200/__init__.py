@@ -59,6 +59,10 @@ class CLaunchInfo(C.Structure):
                 ("last_time_split", C.c_int32), ("last_smem_bytes", C.c_int32), ("kernel_variant", C.c_int32)]
 
 
+TRACE_DTYPE = np.dtype([("index", np.int32), ("executed", np.int32), ("r", np.float32), ("a", np.float32), ("x", np.float32),
+                        ("y", np.float32), ("ccr", np.float32), ("opcode", np.int32), ("acc", np.float64)])
+
+
 def build(force: bool = False) -> None:
     """Compile both libraries in-tree through the package Makefile (nvcc cross-compiles sm_100a)."""
     if force:
@@ -93,6 +97,7 @@ GPU_SYMBOLS = {
     "fx8010_gpu_set_tram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fx8010_gpu_get_runtime_flags": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), C.c_int]),
     "fx8010_gpu_last_error": (C.c_char_p, [C.c_void_p]),
+    "fx8010_gpu_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fx8010_gpu_get_launch_info": (C.c_int, [C.c_void_p, C.POINTER(CLaunchInfo)]),
 }
 
@@ -103,6 +108,7 @@ HOST_SYMBOLS = {
     "fx8010_host_load_file": (C.c_int, [C.c_void_p, C.c_char_p]),
     "fx8010_host_load_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "fx8010_host_ready": (C.c_int, [C.c_void_p]),
+    "fx8010_host_set_relaxed": (None, [C.c_void_p, C.c_int]),
     "fx8010_host_num_registers": (C.c_int, [C.c_void_p]),
     "fx8010_host_register_info": (None, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float),
                                          C.POINTER(C.c_int), C.c_char_p, C.c_int]),
@@ -170,13 +176,15 @@ class Program:
     """The host front-end (class Klangraum::FX8010 through include/fx8010_host.h)."""
 
     def __init__(self, text: str | bytes | None = None, channels: int = 1, instances: int = 1, device: int = 0,
-                 path: str | None = None):
+                 path: str | None = None, relaxed: bool = False):
         self.L = host_lib()
         self.channels, self.instances, self.device = channels, instances, device
         self.h = self.L.fx8010_host_create(channels, instances, device)
         if not self.h:
             raise ValueError("bad channel / instance count")
         self.loaded = None
+        if relaxed:
+            self.L.fx8010_host_set_relaxed(self.h, 1)
         if text is not None or path is not None:
             self.loaded = self.load(text=text, path=path)
 
@@ -434,6 +442,16 @@ class Gpu:
         f = C.c_uint(0)
         self._check(self.L.fx8010_gpu_get_runtime_flags(self.h, C.byref(f), 1 if clear else 0))
         return int(f.value)
+
+    def trace(self, x, instance: int, n_samples=None):
+        """Runs the block like process_host and returns (out [C][S][N], records [S][n_instrs]) for one instance."""
+        if x is not None:
+            x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.c, -1, self.n)
+            n_samples = x.shape[1]
+        out = np.zeros((self.c, n_samples, self.n), dtype=np.float32)
+        rec = np.zeros((n_samples, self.dims().n_instrs), dtype=TRACE_DTYPE)
+        self._check(self.L.fx8010_gpu_trace(self.h, _ptr(x), out.ctypes.data, n_samples, instance, rec.ctypes.data))
+        return out, rec
 
     def launch_info(self) -> CLaunchInfo:
         i = CLaunchInfo()

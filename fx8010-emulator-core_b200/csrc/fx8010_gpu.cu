@@ -67,6 +67,8 @@ struct fx8010_gpu {
     struct Span { const char* out_lo = nullptr; const char* out_hi = nullptr; const char* in_lo = nullptr; const char* in_hi = nullptr;
                   cudaStream_t stream = nullptr; bool valid = false; } prev[2];   // [0] = latest
     int use_pdl = 1;
+    bool trace_mode = false;                     // fx8010_gpu_trace in progress: debug geometry and encoding
+    fx8010_trace_entry* d_trace = nullptr; int trace_inst = 0;
     // stateless fast path (fx8010_stateless.cuh)
     bool sl_ok = false;                          // program qualifies
     int use_sl = 1, tune_M = 0, use_short = 1, tune_chunk = 0;
@@ -369,6 +371,7 @@ void select_tables(fx8010_gpu* h) {
 // Encodes the program for the kernel: micro-ops, flags, CCR liveness, table placement.
 void encode(fx8010_gpu* h, int K, int B, int chunk) {
     const int n = (int)h->instrs.size();
+    const bool skipv = h->has_skip || h->trace_mode;   // trace mode keeps END/NOP and the latch path (SKIP-variant kernel)
     const int RS = K * B, nr = (int)h->reg_map.size(), C = h->C;
     auto row = [&](int r) { return h->row_of[r] < 0 ? 0 : h->row_of[r]; };   // unused operands (R of SKIP/TRAM ops) are never touched
     std::vector<Uop> uops(n);
@@ -413,7 +416,7 @@ void encode(fx8010_gpu* h, int K, int B, int chunk) {
     // (earlier latch updates are dead), so that writer stores straight to the output block; channels
     // nobody writes — and every channel of a program with SKIP — are served from the latch.
     std::vector<int> last_writer(C, -1);
-    if (!h->has_skip)
+    if (!skipv)
         for (int i = 0; i < n; ++i)
             if (h->regs[h->instrs[i].r].type == FX_REG_OUTPUT && writes_r(uops[i]))
                 last_writer[h->regs[h->instrs[i].r].io_index] = i;
@@ -423,19 +426,19 @@ void encode(fx8010_gpu* h, int K, int B, int chunk) {
     int e = 0;
     for (int i = 0; i < n; ++i) {
         const fx8010_instr& in = h->instrs[i];
-        if (!h->has_skip && (uops[i] == U_END || uops[i] == U_NOP)) continue;    // no-ops unless a SKIP counts them
+        if (!skipv && (uops[i] == U_END || uops[i] == U_NOP)) continue;    // no-ops unless a SKIP counts them
         bool pa, px, py; int nz;
         pre_targets(h, in, pa, px, py, nz);
         uint32_t w0 = (uint32_t)uops[i];
         if (pa) w0 |= F_PRE_A;
         if (px) w0 |= F_PRE_X;
         if (py) w0 |= F_PRE_Y;
-        uint32_t pre_off = 0, out_off = 0, aux = 0;
+        uint32_t pre_off = 0, out_off = 0, aux = (uint32_t)(in.opcode & 0xff) << 24;   // bits 24..31: table slot/id, else the opcode (trace)
         if (pa || px || py) pre_off = stage_offset(nr, C, h->regs[in.a].io_index, RS, chunk);      // X and Y use A's IOIndex (:1057-1060)
-        if (nz >= 0) { w0 |= F_NOISE; aux = reg_offset(row(nz), RS); }
+        if (nz >= 0) { w0 |= F_NOISE; aux |= reg_offset(row(nz), RS); }
         if (h->regs[in.r].type == FX_REG_OUTPUT && uops[i] != U_END && uops[i] != U_NOP) { // :1229-1233
             const int c = h->regs[in.r].io_index;
-            if (h->has_skip) w0 |= F_OUT;
+            if (skipv) w0 |= F_OUT;
             else if (last_writer[c] == i) w0 |= F_OUT | F_OUT_DIRECT;
             w0 |= (uint32_t)c << 24;
             out_off = latch_offset(nr, c, RS);
@@ -444,6 +447,7 @@ void encode(fx8010_gpu* h, int K, int B, int chunk) {
         if (h->tab_of[i] >= 0) {
             int slot = -1;
             for (int t = 0; t < h->n_smem_tabs; ++t) if (h->smem_tab_id[t] == h->tab_of[i]) slot = t;
+            aux &= 0xffffffu;
             if (slot >= 0) { w0 |= F_TAB_SMEM; aux |= (uint32_t)slot << 24; }
             else { w0 |= F_TAB_IMM; aux |= (uint32_t)h->tab_of[i] << 24; }
         }
@@ -501,6 +505,7 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     int K = 4;
     while (K > 1 && (!aligned(K) || ((long)(N / K) * max_seg < want_threads && N / K < h->num_sms * 128))) K >>= 1;
     if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
+    if (h->trace_mode) K = 1;
     // block size: spread small jobs over the SMs, keep several blocks per SM resident
     int B = 128;
     // input stage depth: a recurrence has nothing but its own future inputs to keep in flight, so make the
@@ -526,7 +531,7 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     L.smem = smem(B, K, chunk);
     L.grid_x = (N / K + B - 1) / B;
     L.n_seg = 1; L.seg_len = n_samples;
-    if (h->stateless && n_samples > min_seg) {
+    if (h->stateless && n_samples > min_seg && !h->trace_mode) {
         KernelFn fn = pick_kernel(K, h->has_skip, h->has_ext, is_short(h));
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, B, L.smem);
@@ -598,7 +603,7 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
         if (h->plan_key.ns == ns && h->plan_key.align == align) L = h->plan;
         else {
             L.M = 0;
-            const int rc = (h->sl_ok && h->use_sl) ? plan_stateless(h, in, out, in_cs, out_cs, ns, L) : plan_launch(h, in, out, in_cs, out_cs, ns, L);
+            const int rc = (h->sl_ok && h->use_sl && !h->trace_mode) ? plan_stateless(h, in, out, in_cs, out_cs, ns, L) : plan_launch(h, in, out, in_cs, out_cs, ns, L);
             if (rc) return rc;
             h->plan = L; h->plan_key.ns = ns; h->plan_key.align = align;
         }
@@ -671,9 +676,11 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
             p.chunk = L.chunk;
             p.pdl_late_wait = late_wait;
-            const bool shortp = is_short(h);
-            KernelFn fn = pick_kernel(L.K, h->has_skip, h->has_ext, shortp);
-            bool& attr = h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][h->has_skip ? 1 : 0][h->has_ext ? 1 : 0][shortp ? 1 : 0];
+            const bool shortp = is_short(h) && !h->trace_mode;
+            const bool kskip = h->has_skip || h->trace_mode, kext = h->has_ext || h->trace_mode;
+            p.trace = h->trace_mode ? h->d_trace : nullptr; p.trace_inst = h->trace_inst;
+            KernelFn fn = pick_kernel(L.K, kskip, kext, shortp);
+            bool& attr = h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][kskip ? 1 : 0][kext ? 1 : 0][shortp ? 1 : 0];
             if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
             FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
         }
@@ -1124,6 +1131,35 @@ int fx8010_gpu_get_runtime_flags(fx8010_gpu* h, unsigned int* flags, int clear) 
     FX_CUDA(h, cudaMemcpy(flags, h->d_flags, sizeof(unsigned int), cudaMemcpyDeviceToHost));
     if (clear) FX_CUDA(h, cudaMemset(h->d_flags, 0, sizeof(unsigned int)));
     return FX8010_OK;
+}
+
+int fx8010_gpu_trace(fx8010_gpu* h, const float* in, float* out, int n_samples, int instance, fx8010_trace_entry* entries) {
+    FX_NEED_PROGRAM(h);
+    if (!entries || n_samples <= 0 || instance < 0 || instance >= h->N) return fail(h, FX8010_ERR_ARG, "bad instance / n_samples or NULL entries");
+    int rc = sync_all(h);
+    if (rc) return rc;
+    const size_t n_rec = (size_t)n_samples * h->instrs.size(), io = (size_t)h->C * n_samples * h->N;
+    float* d_in = nullptr; float* d_out = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(h->d_trace); h->d_trace = nullptr; cudaFree(d_in); cudaFree(d_out);
+        h->trace_mode = false; h->encode_dirty = true; h->plan_key.ns = -1;
+    };
+    h->trace_mode = true; h->trace_inst = instance; h->encode_dirty = true; h->plan_key.ns = -1;
+    cudaError_t e = cudaMalloc(&h->d_trace, sizeof(fx8010_trace_entry) * n_rec);
+    if (e == cudaSuccess) e = cudaMemset(h->d_trace, 0, sizeof(fx8010_trace_entry) * n_rec);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(float) * io);
+    if (e == cudaSuccess && in) { e = cudaMalloc(&d_in, sizeof(float) * io); if (e == cudaSuccess) e = cudaMemcpy(d_in, in, sizeof(float) * io, cudaMemcpyHostToDevice); }
+    if (e != cudaSuccess) { cleanup(); return fail(h, FX8010_ERR_CUDA, std::string("trace buffers: ") + cudaGetErrorString(e)); }
+    const size_t cs = (size_t)n_samples * h->N;
+    rc = launch_block(h, d_in, d_out, cs, cs, n_samples, h->s_comp);
+    if (!rc) {
+        e = cudaStreamSynchronize(h->s_comp);
+        if (e == cudaSuccess) e = cudaMemcpy(entries, h->d_trace, sizeof(fx8010_trace_entry) * n_rec, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && out) e = cudaMemcpy(out, d_out, sizeof(float) * io, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(h, FX8010_ERR_CUDA, std::string("trace: ") + cudaGetErrorString(e));
+    }
+    cleanup();
+    return rc;
 }
 
 const char* fx8010_gpu_last_error(fx8010_gpu* h) { return h ? h->err.c_str() : g_create_error.c_str(); }

@@ -96,6 +96,8 @@ struct Params {
     int n_load;                 // entries of load_rows
     int load_latch, load_acc;   // the latches / the accumulator can be observed before the program rewrites them
     int chunk;                  // samples per input-stage buffer (power of two <= MAX_CHUNK)
+    fx8010_trace_entry* trace;  // debug: [n_samples][n_exec] records for instance trace_inst (only the <1,true,true,0> variant looks)
+    int trace_inst;
     int pdl_late_wait;          // programmatic dependent launch: 1 = this launch reads nothing the previous launch on
                                 // the stream writes until its own state write-back (stateless program, disjoint
                                 // buffers), so it only waits for that launch right before writing state
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
             WB[i] = make_uint4(inv_read(s_inv, 12 + 8 * i), inv_read(s_inv, 13 + 8 * i), inv_read(s_inv, 14 + 8 * i), inv_read(s_inv, 15 + 8 * i));
         }
     }
+    const bool tracing = (K == 1 && SKIP && EXT && NI == 0) && p.trace != nullptr && valid && inst0 == p.trace_inst;
     const int lane_rep = tid & (TAB_REPL - 1);
     float* out_s = p.out + (size_t)s_begin * N + inst0;   // this thread's slot in the current output row
     uint32_t boff = 0;                                     // byte offset of the stage buffer being consumed
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
             for (int k = 0; k < K; ++k) { skip[k] = 0; saw_end[k] = false; }
             int pass = 0;
             do {
+                int trace_pc = 0;
                 auto exec_instr = [&](const uint4 wA, const uint4 wB) {
                     const uint32_t w0 = wA.x;
                     const uint32_t uop = w0 & 0xffu;
@@ -569,6 +573,17 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                             if (last_sample) vstore<K>(at(wB.w), r);
                         } else if (!SKIP) vstore<K>(at(wB.w), vload<K>(pr));
                         else { float* const pl = at(wB.w); FX_EACH { if (act[k]) pl[k] = pr[k]; } }
+                    }
+                    if (K == 1 && SKIP && EXT && NI == 0) {          // debug trace (fx8010_gpu_trace), compiled into one variant only
+                        if (tracing) {
+                            fx8010_trace_entry e;
+                            e.index = trace_pc; e.executed = act[0] ? 1 : 0;
+                            e.r = pr[0]; e.a = pa[0]; e.x = px[0]; e.y = py[0]; e.ccr = at(0)[0];
+                            e.opcode = (w0 & (F_TAB_SMEM | F_TAB_IMM)) ? (uop == U_LOG ? FX_LOG : FX_EXP) : (int32_t)(wB.y >> 24);
+                            e.acc = acc_is_f[0] ? (double)acc_f[0] : acc_d[0];
+                            p.trace[(size_t)sidx * p.n_exec + trace_pc] = e;
+                        }
+                        ++trace_pc;
                     }
                 };
                 if (NI > 0) {

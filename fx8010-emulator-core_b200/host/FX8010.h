@@ -48,6 +48,7 @@ public:
     // ---- batched extension ------------------------------------------------------------------------
     FX8010(int numChannels, int numInstances, int device);
     bool loadText(const std::string& source);
+    void setRelaxedSyntax(bool on) { front_.setRelaxed(on); }   // accept the README's forms too (see fx8010_frontend.h)
     int getInstances() const { return instances_; }
     // per-instance control values, values[numInstances]; 0 ok / 1 unknown name
     int setRegisterValues(const std::string& key, const float* values);

@@ -217,7 +217,7 @@ bool Frontend::parseTramSize(const std::string& s, bool& matched) {
     while (r < s.size() && is_digit(s[r])) ++r;
     std::string digits;
     if (r > q) {
-        if (!(r + 1 == s.size() && is_space(s[r]))) return false;
+        if (relaxed_ ? !all_space(s, r) : !(r + 1 == s.size() && is_space(s[r]))) return false;
         digits = s.substr(q, r - q);
     } else {
         if (!(q == s.size() && q - kw_end >= 2)) return false;            // "itramsize  ": matches with an empty number
@@ -324,7 +324,15 @@ bool Frontend::loadText(const std::string& text) {
         const size_t c = line.find(';');                                  // comments run to the end of the line (:794-798)
         if (c != std::string::npos) line.resize(c);
         for (char& ch : line) if (ch >= 'A' && ch <= 'Z') ch = (char)(ch - 'A' + 'a');   // :805-808
+        if (relaxed_ && !line.empty() && line.back() == '\r') line.pop_back();
         lines.push_back(line);
+    }
+    if (relaxed_) {                                                       // blank lines after / blanks around the final `end`
+        while (!lines.empty() && all_space(lines.back(), 0)) lines.pop_back();
+        if (!lines.empty()) {
+            size_t e;
+            if (first_word(lines.back(), e) == "end" && all_space(lines.back(), e)) lines.back() = "end";
+        }
     }
     for (const std::string& l : lines) { parseLine(l); ++row_counter_; }  // errors do not stop the scan (:819-825)
     if (lines.empty() || lines.back() != "end") report(ERR_NO_END_FOUND); // exact match: no blanks, no CR (:829-838)

@@ -61,6 +61,11 @@ public:
     int channels() const { return num_channels_; }
     void setChannels(int c) { num_channels_ = c; }
     bool ready() const { return ready_; }
+    // Relaxed mode (off by default = the reference's exact accept/reject behaviour): also accepts what the
+    // reference's README shows but its patterns reject: `itramsize N` with any or no
+    // trailing blanks, CR-LF line ends, blanks around and blank lines after the final `end`.
+    void setRelaxed(bool on) { relaxed_ = on; }
+    bool relaxed() const { return relaxed_; }
     int findRegister(const std::string& name) const;     // -1 when absent (first match wins)
 
     // LOG / EXP tables, [32][64] doubles each (reference source/FX8010.cpp:63-105, 129-199).
@@ -90,6 +95,7 @@ private:
     int row_counter_ = 1;             // reference errorCounter: never reset between loads
     int itram_size_ = 0, xtram_size_ = 0;
     bool ready_ = false;
+    bool relaxed_ = false;
     std::vector<double> log_tables_, exp_tables_;
     std::vector<fx8010_reg> image_regs_;
     fx8010_program_image image_ = {};

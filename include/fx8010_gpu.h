@@ -191,6 +191,25 @@ FX8010_API int fx8010_gpu_get_runtime_flags(fx8010_gpu* h, unsigned int* flags, 
 
 /* ---- diagnostics -------------------------------------------------------------------------- */
 
+/* One record per program instruction and sample period for ONE instance: the GPU counterpart of the
+ * reference's PRINT_REGISTERS dump (printRegisters, source/FX8010.cpp:970-984, called at :1225-1226
+ * after each executed instruction).  Values are those in the register file right after the instruction. */
+typedef struct fx8010_trace_entry {
+    int32_t index;               /* instruction index in the program (END included)                      */
+    int32_t executed;            /* 0 = skipped by a SKIP (values then show the untouched registers)       */
+    float r, a, x, y;            /* R, A, X, Y register values                                             */
+    float ccr;                   /* GPR 0                                                                  */
+    int32_t opcode;              /* enum fx8010_opcode                                                     */
+    double acc;                  /* accumulator                                                            */
+} fx8010_trace_entry;
+/* Runs n_samples sample periods exactly like fx8010_gpu_process_batch_host (state advances, `out` may be
+ * NULL) and fills entries[n_samples][n_instrs] (host memory) for `instance`.  Debug path: one instance per
+ * thread, every instruction fetched and recorded; when END is skipped and the program re-runs, the records
+ * of the last pass remain. */
+FX8010_API int fx8010_gpu_trace(fx8010_gpu* h, const float* in, float* out, int n_samples, int instance,
+                                fx8010_trace_entry* entries);
+
+
 /* Text of the last error on this handle (or of the last failed create when h == NULL). */
 FX8010_API const char* fx8010_gpu_last_error(fx8010_gpu* h);
 

@@ -27,6 +27,8 @@ FX8010_API const char* fx8010_host_last_error(fx8010_host* h);
 FX8010_API int fx8010_host_load_file(fx8010_host* h, const char* path);
 FX8010_API int fx8010_host_load_text(fx8010_host* h, const char* text, size_t len);
 FX8010_API int fx8010_host_ready(fx8010_host* h);                      /* getReadyStatus */
+/* extension: relaxed syntax (accepts the reference README's `itramsize 100`, CR-LF files, blank lines after `end`) */
+FX8010_API void fx8010_host_set_relaxed(fx8010_host* h, int on);
 
 /* decoded image (what loadFile leaves in the object) */
 FX8010_API int fx8010_host_num_registers(fx8010_host* h);

@@ -95,3 +95,16 @@ def test_facade_register_api_without_gpu(fx):
     assert p.controls() == ["volume", "pan", "filter_cutoff"]
     assert p.metadata()["name"] == "testcode"
     assert p.instruction_counter == 0
+
+
+def test_relaxed_mode_accepts_the_readme_forms(fx):
+    """Strict mode = the reference (README example is rejected); relaxed mode loads it and
+    decodes it like the strictly spelled source."""
+    readme = "static a\r\nitramsize 100\r\ninput in_l 0\r\noutput out_l 0\r\nlog a, in_l, 3, 0\r\nmacs out_l, 0, a, 1.0\r\n  END  \r\n\r\n\r\n"
+    strict_src = "static a\nitramsize 100 \ninput in_l 0\noutput out_l 0\nlog a, in_l, 3, 0\nmacs out_l, 0, a, 1.0\nend"
+    assert not fx.Program(readme).loaded
+    r, s = fx.Program(readme, relaxed=True), fx.Program(strict_src)
+    assert r.loaded and s.loaded, r.errors()
+    assert r.registers() == s.registers() and r.instructions() == s.instructions() and r.itram_size == s.itram_size == 100
+    assert fx.Program("static a\nitramsize 64   \nend", relaxed=True).loaded
+    assert not fx.Program("static a\nbogus line\nend\n\n", relaxed=True).loaded          # still an error, just not about END

@@ -461,3 +461,33 @@ def test_async_host_batches_chain_in_order(fx, po):
         compare_state(gpu, orc, img, "async")
     finally:
         gpu.close()
+
+
+def test_trace_matches_execution(fx, po):
+    """fx8010_gpu_trace: same outputs and state as a normal run; per-instruction records are consistent with
+    the oracle (executed-instruction count, the values the output drivers leave, the final register file)."""
+    rng = np.random.default_rng(50)
+    for text in (progs.CFG2_LOG_GAIN, progs.SNIPPETS["skip"], progs.random_program(rng, 40, xtram=True)):
+        n, s, inst = 24, 9, 5
+        prog, img, orc, gpu = make_pair(fx, po, text, n)
+        try:
+            x = (1.8 * rng.random((1, s, n)) - 0.9).astype(np.float32)
+            out, rec = gpu.trace(x, inst)
+            assert_bits_equal(out, orc.process(x), "trace outputs")
+            compare_state(gpu, orc, img, "trace state")
+            instrs = prog.instructions()
+            assert rec.shape == (s, len(instrs))
+            assert [int(v) for v in rec["index"][0]] == list(range(len(instrs)))
+            assert [int(v) for v in rec["opcode"][0]] == [i[0] for i in instrs]
+            assert int(rec["executed"].sum()) == int(orc.counts[inst])
+            regs = prog.registers()
+            last = rec[-1]
+            for k, ins in enumerate(instrs):                    # a register nobody touches afterwards keeps its traced value
+                later = {j[1] for j in instrs[k + 1:]} | {j[2] for j in instrs[k + 1:]}
+                if last["executed"][k] and ins[0] < 15 and ins[1] not in later and ins[1] != 0 and regs[ins[1]][0] != 3:
+                    assert np.float32(last["r"][k]).view(np.uint32) == orc.registers[ins[1], inst].view(np.uint32)
+            # and a normal batch afterwards continues from the traced state
+            x2 = (1.8 * rng.random((1, 7, n)) - 0.9).astype(np.float32)
+            assert_bits_equal(gpu.process_host(x2), orc.process(x2), "after trace")
+        finally:
+            gpu.close()
