@@ -17,6 +17,7 @@
 
 #include "fx8010_kernel.cuh"
 #include "fx8010_stateless.cuh"
+#include "fx8010_short.cuh"
 
 using namespace fxk;
 
@@ -70,7 +71,15 @@ struct fx8010_gpu {
     bool trace_mode = false;                     // fx8010_gpu_trace in progress: debug geometry and encoding
     fx8010_trace_entry* d_trace = nullptr; int trace_inst = 0;
     // stateless fast path (fx8010_stateless.cuh)
+    bool in_alias = false;                       // every INPUT-typed operand is preloaded by its own instruction
     bool sl_ok = false;                          // program qualifies
+    bool sl_serial = false;                      // ... with self-carried operands: one time segment, state loaded and kept
+    bool acc_writer = false;                     // some instruction sets the accumulator
+    std::vector<uint8_t> sl_carry;               // per instruction: bit o set = operand o (A, X, Y) is the instruction's own previous result
+    std::vector<uint8_t> sl_carried_reg;         // per register: some instruction carries it from sample to sample
+    int use_carry = 1;
+    bool short_ok = false;                       // SKIP-free, nobody reads ccr, no noise/MACMV, every channel written: fx_short_kernel when short enough
+    bool short_attr_set[3][2][SH_MAX_NI] = {};
     int use_sl = 1, tune_M = 0, use_short = 1, tune_chunk = 0;
     std::vector<int> sl_class, sl_index;         // per register: RowClass and index inside its class
     int sl_n_ro = 0, sl_n_wo = 0, sl_n_rw = 0;
@@ -244,12 +253,56 @@ void analyse(fx8010_gpu* h) {
         if (!h->stateless || !h->written[h->reg_map[row]]) h->load_rows.push_back((uint32_t)row);
     h->load_latch = !(h->stateless && all_ch);
     h->load_acc = !(h->stateless && acc_writer);
+    h->acc_writer = acc_writer;
 
     // Stateless fast path: additionally every channel needs a writer (its latch is never read then) and
     // every preload of an INPUT register must deliver that register's own channel, so that the input
     // stage rows can stand in for the INPUT registers (the reference loads X and Y from A's channel,
     // source/FX8010.cpp:1057-1060 — a program relying on that quirk takes the generic kernel).
-    h->sl_ok = h->stateless && all_ch;
+    h->in_alias = true;
+    for (int i = 0; i < n; ++i) {
+        const fx8010_instr& in = h->instrs[i];
+        const Uop u = uop_of(h, in);
+        if (u == U_END || u == U_NOP) continue;
+        bool pa, px, py; int nz;
+        pre_targets(h, in, pa, px, py, nz);
+        const int ops[3] = {in.a, in.x, in.y};
+        const bool pre[3] = {pa, px, py};
+        for (int o = 0; o < 3; ++o) if (h->regs[ops[o]].type == FX_REG_INPUT && !pre[o]) h->in_alias = false;   // hand-made image without has_input
+        if (nz >= 0 && h->regs[nz].type == FX_REG_INPUT) h->in_alias = false;                                    // an INPUT register named "noise"
+        if ((u == U_IREAD || u == U_XREAD) && h->regs[in.a].type == FX_REG_INPUT) h->in_alias = false;           // TRAM read into an INPUT register
+    }
+    // Short-program kernel (fx8010_short.cuh): SKIP-free, no noise, no MACMV, nobody reads `ccr` (it is produced on the
+    // call's last sample only), every channel has a writer (no per-sample latch traffic), INPUT operands aliased.
+    h->short_ok = !h->has_skip && h->in_alias && all_ch;
+    for (int i = 0; i < n; ++i) {
+        const fx8010_instr& in = h->instrs[i];
+        const Uop u = uop_of(h, in);
+        if (u == U_END || u == U_NOP) continue;
+        if (in.has_noise || u == U_MACMV) h->short_ok = false;
+        if (in.a == 0 || in.x == 0 || in.y == 0 || (writes_r(u) && in.r == 0)) h->short_ok = false;
+    }
+    // The instruction-major kernel also takes programs whose only loop-carried values are SELF recurrences: an operand
+    // that is the instruction's own result of the previous sample period (one-pole filters `interp out, out, c, in`,
+    // accumulators `macs a, a, x, y`), the register having no other writer.  Running instruction i over a batch of
+    // samples before instruction i + 1 keeps every such dependence (loop distribution); a value carried from a LATER
+    // instruction to an earlier one would not survive it, and sends the program to the sample-major kernels.
+    h->sl_ok = !h->has_skip && !h->has_ext && all_ch;
+    h->sl_serial = false;
+    h->sl_carry.assign(n, 0); h->sl_carried_reg.assign(nr, 0);
+    std::vector<int> n_writers(nr, 0);
+    for (int i = 0; i < n; ++i) {
+        const fx8010_instr& in = h->instrs[i];
+        const Uop u = uop_of(h, in);
+        if (u == U_END || u == U_NOP) continue;
+        bool pa, px, py; int nz;
+        pre_targets(h, in, pa, px, py, nz);
+        if (pa) n_writers[in.a]++;
+        if (px && in.x != in.a) n_writers[in.x]++;
+        if (py && in.y != in.a && in.y != in.x) n_writers[in.y]++;
+        if (writes_r(u)) n_writers[in.r]++;
+    }
+    std::vector<uint8_t> sl_defined(nr, 0);
     std::vector<uint8_t> is_read(nr, 0);
     for (int i = 0; i < n && h->sl_ok; ++i) {
         const fx8010_instr& in = h->instrs[i];
@@ -257,6 +310,20 @@ void analyse(fx8010_gpu* h) {
         if (u == U_END || u == U_NOP) continue;
         bool pa, px, py; int nz;
         pre_targets(h, in, pa, px, py, nz);
+        if (pa) sl_defined[in.a] = 1;
+        if (px) sl_defined[in.x] = 1;
+        if (py) sl_defined[in.y] = 1;
+        {
+            const int opr[3] = {in.a, in.x, in.y};
+            for (int o = 0; o < 3; ++o) {
+                const int g = opr[o];
+                if (!h->written[g] || sl_defined[g]) continue;          // never written, or produced earlier in this period
+                if (h->use_carry && g != 0 && writes_r(u) && in.r == g && n_writers[g] == 1 && h->regs[g].type != FX_REG_INPUT) {
+                    h->sl_carry[i] |= (uint8_t)(1u << o); h->sl_carried_reg[g] = 1; h->sl_serial = true;
+                } else h->sl_ok = false;
+            }
+            if (writes_r(u)) { sl_defined[in.r] = 1; sl_defined[0] = 1; }
+        }
         const int ch = h->regs[in.a].io_index;
         if ((pa && h->regs[in.a].io_index != ch) || (px && h->regs[in.x].io_index != ch) || (py && h->regs[in.y].io_index != ch)) h->sl_ok = false;
         // an INPUT-typed operand that is NOT preloaded here (has_input clear in a hand-made image) would read a stale row
@@ -313,6 +380,7 @@ void encode_stateless(fx8010_gpu* h, int K, int B, int M) {
         uint32_t w0 = (uint32_t)u, aux = 0;
         if (h->sl_class[in.r] == ROW_WO) w0 |= F_ST_LAST;
         if (ccr_read || in.r == 0) w0 |= F_CCR;                 // a `ccr` operand somewhere: every setCCR is kept per sample
+        w0 |= (uint32_t)h->sl_carry[i] << SL_CARRY_SHIFT;       // operands that are this instruction's own previous result
         if (h->regs[in.r].type == FX_REG_OUTPUT) {
             const int c = h->regs[in.r].io_index;
             if (last_writer[c] == i) w0 |= F_OUT | F_OUT_DIRECT;
@@ -334,6 +402,8 @@ void encode_stateless(fx8010_gpu* h, int K, int B, int M) {
     h->sl_load.clear(); h->sl_wb.clear();
     for (int r = 0; r < nr; ++r) {
         if (h->sl_class[r] == ROW_RO) h->sl_load.push_back(make_uint2(sl_word(h, r, B, K, M), (uint32_t)r));
+        else if (h->sl_carried_reg[r])   // carried in from the previous call: the row of "the sample before sample 0" is row M - 1
+            h->sl_load.push_back(make_uint2((sl_word(h, r, B, K, M) & SL_OFF_MASK) + (uint32_t)(M - 1) * (uint32_t)B * K * 4u, (uint32_t)r));
         else if (h->sl_class[r] != ROW_NONE && h->written[r]) h->sl_wb.push_back(make_uint2(sl_word(h, r, B, K, M), (uint32_t)r));
     }
     h->enc_K = K; h->enc_B = B; h->sl_M = M;
@@ -490,6 +560,23 @@ int encoded_length(const fx8010_gpu* h) {
     return e;
 }
 bool is_short(const fx8010_gpu* h) { return h->use_short && encoded_length(h) <= SHORT_NI; }
+// fx_short_kernel<K, EXT, NI>: NI = the exact number of executed instructions
+bool use_short_kernel(const fx8010_gpu* h) {
+    const int e = encoded_length(h);
+    return h->use_short && h->short_ok && !h->trace_mode && e >= 1 && e <= SH_MAX_NI;
+}
+template <int K, bool EXT> KernelFn pick_short_kernel(int ni) {
+    switch (ni) {
+    case 1: return fx_short_kernel<K, EXT, 1>;
+    case 2: return fx_short_kernel<K, EXT, 2>;
+    case 3: return fx_short_kernel<K, EXT, 3>;
+    default: return fx_short_kernel<K, EXT, 4>;
+    }
+}
+template <int K> KernelFn pick_short_kernel(bool ext, int ni) { return ext ? pick_short_kernel<K, true>(ni) : pick_short_kernel<K, false>(ni); }
+KernelFn pick_short_kernel(int K, bool ext, int ni) {
+    return K == 4 ? pick_short_kernel<4>(ext, ni) : (K == 2 ? pick_short_kernel<2>(ext, ni) : pick_short_kernel<1>(ext, ni));
+}
 
 // Geometry of one launch: contexts per thread, block size, time split.
 int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_cs, size_t out_cs, int n_samples, Launch& L) {
@@ -532,7 +619,7 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     L.grid_x = (N / K + B - 1) / B;
     L.n_seg = 1; L.seg_len = n_samples;
     if (h->stateless && n_samples > min_seg && !h->trace_mode) {
-        KernelFn fn = pick_kernel(K, h->has_skip, h->has_ext, is_short(h));
+        KernelFn fn = use_short_kernel(h) ? pick_short_kernel(K, h->has_ext, encoded_length(h)) : pick_kernel(K, h->has_skip, h->has_ext, is_short(h));
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, B, L.smem);
         occ = std::max(occ, 1);
@@ -565,8 +652,12 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
     int B = h->tune_B ? h->tune_B : 128;
     while (B > 32 && (N / K + B - 1) / B * B >= 2 * (N / K) && N / K <= B / 2) B >>= 1;      // tiny N: do not launch mostly-idle blocks
-    int M = h->tune_M ? h->tune_M : 4;
+    if (h->sl_serial && !h->tune_B)          // one time segment: only N / K threads — spread them over the SMs
+        while (B > 32 && (N / K + B - 1) / B < 2 * h->num_sms) B >>= 1;
+    // A serial launch has few warps, and the batch is also how far the input stage runs ahead: make it deep.
+    int M = h->tune_M ? h->tune_M : (h->sl_serial ? SL_MAX_M : 4);
     while (!h->tune_M && M > 1 && sl_smem_bytes(h, B, K, M) > 48 * 1024) M >>= 1;
+    if (h->sl_serial && M < 2) M = 2;        // a carried operand reads row (m - 1) mod M while row m is written
     while (sl_smem_bytes(h, B, K, M) > h->smem_optin && B > 32) B >>= 1;
     if (sl_smem_bytes(h, B, K, M) > h->smem_optin) return fail(h, FX8010_ERR_CAPACITY, "register file does not fit in shared memory");
     L.K = K; L.B = B; L.M = M; L.chunk = 0;
@@ -580,6 +671,7 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     long n_seg = std::max(1L, (long)h->num_sms * occ / (2 * L.grid_x));
     if (h->tune_seg) n_seg = h->tune_seg;
     n_seg = std::min<long>(n_seg, std::max(1, n_samples / M));
+    if (h->sl_serial) n_seg = 1;             // a recurrence cannot be cut along time
     int seg_len = (int)((n_samples + n_seg - 1) / n_seg);
     seg_len = (seg_len + M - 1) / M * M;
     L.seg_len = seg_len;
@@ -654,7 +746,7 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             p.stage0 = (uint32_t)L.B * L.K * 4u * (uint32_t)(h->sl_n_ro + h->sl_n_wo + h->sl_n_rw * L.M);
             p.n_smem_tabs = h->n_smem_tabs;
             for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
-            p.acc_writer = h->load_acc ? 0 : 1;
+            p.acc_writer = h->acc_writer ? 1 : 0;
             p.pdl_late_wait = late_wait;
             SLKernelFn fn = pick_sl_kernel(L.K);
             bool& attr = h->sl_attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)];
@@ -679,8 +771,10 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             const bool shortp = is_short(h) && !h->trace_mode;
             const bool kskip = h->has_skip || h->trace_mode, kext = h->has_ext || h->trace_mode;
             p.trace = h->trace_mode ? h->d_trace : nullptr; p.trace_inst = h->trace_inst;
-            KernelFn fn = pick_kernel(L.K, kskip, kext, shortp);
-            bool& attr = h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][kskip ? 1 : 0][kext ? 1 : 0][shortp ? 1 : 0];
+            const bool lean = use_short_kernel(h);
+            KernelFn fn = lean ? pick_short_kernel(L.K, kext, h->n_exec) : pick_kernel(L.K, kskip, kext, shortp);
+            bool& attr = lean ? h->short_attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][kext ? 1 : 0][h->n_exec - 1]
+                              : h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][kskip ? 1 : 0][kext ? 1 : 0][shortp ? 1 : 0];
             if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
             FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
         }
@@ -690,7 +784,7 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
         h->info.kernel_launches++;
         h->info.last_grid = L.grid_x * L.n_seg; h->info.last_block = L.B; h->info.last_time_split = L.n_seg;
         h->info.last_smem_bytes = (int)L.smem;
-        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | ((L.M == 0 && is_short(h)) ? 16 : 0) | (L.K << 8) | (L.M << 16);
+        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | ((L.M == 0 && is_short(h)) ? 16 : 0) | ((L.M == 0 && use_short_kernel(h)) ? 32 : 0) | (L.K << 8) | (L.M << 16);
     }
     h->last_stream = st;
     return FX8010_OK;
@@ -748,6 +842,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     if (getenv("FX8010_NO_PDL")) h->use_pdl = 0;
     if (getenv("FX8010_NO_STATELESS")) h->use_sl = 0;
     if (getenv("FX8010_NO_SHORT")) h->use_short = 0;
+    if (getenv("FX8010_NO_CARRY")) h->use_carry = 0;
     h->tune_M = env_int("FX8010_TUNE_M");
     h->tune_chunk = env_int("FX8010_TUNE_CHUNK");
     if (h->tune_chunk & (h->tune_chunk - 1) || h->tune_chunk > MAX_CHUNK) h->tune_chunk = 0;

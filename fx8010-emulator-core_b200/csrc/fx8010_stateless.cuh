@@ -27,6 +27,9 @@ constexpr int SL_STRIDE_SHIFT = 20;          // [20:31) bytes between consecutiv
 constexpr uint32_t SL_BUF = 1u << 31;        // input-stage row: add the offset of the current stage buffer
 constexpr uint32_t F_ST_LAST = 1u << 17;     // R is never read by the program: store it on the batch-final sample only
 constexpr int SL_MAX_M = 8;
+constexpr int SL_CARRY_SHIFT = 18;           // w0 bits 18..20: operand A / X / Y is this instruction's OWN result of the previous sample
+                                             // (a self recurrence): row (m - 1) mod M on the first sample of a batch, then forwarded
+                                             // in a hardware register — the recurrence never waits for shared memory
 
 // instruction: A = { uop | flags | out channel << 24, R word, A word, X word },  B = { Y word, table slot/id << 24, CCR word, 0 }
 
@@ -87,8 +90,14 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
         // decode once per batch: address of sample m_lo and per-sample stride of every operand, store modes
 #define SL_STRIDE(w) ((((w) >> SL_STRIDE_SHIFT) & 0x7ffu) << 4)
 #define SL_ADDR(w) (cx.col_s + ((w) & SL_OFF_MASK) + (((w) & SL_BUF) ? cx.boff : 0u) + (uint32_t)m_lo * SL_STRIDE(w))
-        const uint32_t sr = SL_STRIDE(wA.y), sa = SL_STRIDE(wA.z), sx = SL_STRIDE(wA.w), sy = SL_STRIDE(wB.x), sccr = SL_STRIDE(wB.z);
-        uint32_t qr = SL_ADDR(wA.y), qa = SL_ADDR(wA.z), qx = SL_ADDR(wA.w), qy = SL_ADDR(wB.x), qccr = SL_ADDR(wB.z);
+        // a carried operand: the row of the previous sample (row M - 1 before sample 0), and the pointer stays there
+#define SL_ADDR_C(w) (cx.col_s + ((w) & SL_OFF_MASK) + (uint32_t)((m_lo == 0 ? p.M : m_lo) - 1) * SL_STRIDE(w))
+        const bool ca = (w0 >> SL_CARRY_SHIFT) & 1u, cxx = (w0 >> SL_CARRY_SHIFT) & 2u, cy = (w0 >> SL_CARRY_SHIFT) & 4u;
+        const uint32_t sr = SL_STRIDE(wA.y), sa = ca ? 0u : SL_STRIDE(wA.z), sx = cxx ? 0u : SL_STRIDE(wA.w), sy = cy ? 0u : SL_STRIDE(wB.x), sccr = SL_STRIDE(wB.z);
+        uint32_t qr = SL_ADDR(wA.y), qa = ca ? SL_ADDR_C(wA.z) : SL_ADDR(wA.z), qx = cxx ? SL_ADDR_C(wA.w) : SL_ADDR(wA.w),
+                 qy = cy ? SL_ADDR_C(wB.x) : SL_ADDR(wB.x), qccr = SL_ADDR(wB.z);
+        Vec<K> rp;                                // the previous sample's result (carried operands)
+        _Pragma("unroll") for (int k = 0; k < K; ++k) rp[k] = 0.0f;
         const bool st_r = FINAL || !(w0 & F_ST_LAST);
         const bool st_c = FINAL || (w0 & F_CCR);
         const bool st_o = (w0 & F_OUT_DIRECT) && cx.valid;
@@ -100,6 +109,7 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
 #define SL_WRITE(SETS_ACC)                                                                                       \
         {                                                                                                        \
             if (st_r) sts<K>(qr, r);                                                                             \
+            rp = r;                                                                                              \
             if (st_c) { Vec<K> c; SL_EACH { c[k] = ccr_of(r[k]); } sts<K>(qccr, c); }                             \
             if (!FINAL) { if (st_o) vstore<K>(qo, r); }                                                          \
             else {                                                                                               \
@@ -107,7 +117,8 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
                 if (SETS_ACC) cx.acc_last = accv;                                                                \
             }                                                                                                    \
         }
-#define SL_LOAD3 const Vec<K> a = lds<K>(qa), x = lds<K>(qx), y = lds<K>(qy); Vec<K> r, accv;
+#define SL_LOAD3 Vec<K> a = lds<K>(qa), x = lds<K>(qx), y = lds<K>(qy); Vec<K> r, accv;                            \
+        if (m > 0) { SL_EACH { a[k] = ca ? rp[k] : a[k]; x[k] = cxx ? rp[k] : x[k]; y[k] = cy ? rp[k] : y[k]; } }
         switch (uop) {
         case U_MACS: SL_FOR_M { SL_LOAD3
             SL_EACH { accv[k] = __fadd_rn(a[k], __fmul_rn(x[k], y[k])); r[k] = sat1(accv[k]); } SL_WRITE(true) } break;
@@ -141,7 +152,8 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
         case U_EXP: {
             const uint32_t tb_s = cx.tab_s + (wB.y >> 24) * (uint32_t)TAB_SMEM_BYTES;
             SL_FOR_M {
-                const Vec<K> a = lds<K>(qa);
+                Vec<K> a = lds<K>(qa);
+                if (m > 0) { SL_EACH { a[k] = ca ? rp[k] : a[k]; } }
                 Vec<K> r, accv;
                 int idx[K];
                 double xd[K];
@@ -177,6 +189,7 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
 #undef SL_WRITE
 #undef SL_LOAD3
 #undef SL_ADDR
+#undef SL_ADDR_C
     }
 }
 
