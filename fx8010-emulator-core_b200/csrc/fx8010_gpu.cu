@@ -402,9 +402,9 @@ void encode_stateless(fx8010_gpu* h, int K, int B, int M) {
     h->sl_load.clear(); h->sl_wb.clear();
     for (int r = 0; r < nr; ++r) {
         if (h->sl_class[r] == ROW_RO) h->sl_load.push_back(make_uint2(sl_word(h, r, B, K, M), (uint32_t)r));
-        else if (h->sl_carried_reg[r])   // carried in from the previous call: the row of "the sample before sample 0" is row M - 1
+        if (h->sl_carried_reg[r])        // carried in from the previous call: the row of "the sample before sample 0" is row M - 1
             h->sl_load.push_back(make_uint2((sl_word(h, r, B, K, M) & SL_OFF_MASK) + (uint32_t)(M - 1) * (uint32_t)B * K * 4u, (uint32_t)r));
-        else if (h->sl_class[r] != ROW_NONE && h->written[r]) h->sl_wb.push_back(make_uint2(sl_word(h, r, B, K, M), (uint32_t)r));
+        if (h->sl_class[r] != ROW_RO && h->sl_class[r] != ROW_NONE && h->written[r]) h->sl_wb.push_back(make_uint2(sl_word(h, r, B, K, M), (uint32_t)r));
     }
     h->enc_K = K; h->enc_B = B; h->sl_M = M;
 }

@@ -299,6 +299,50 @@ def test_stateless_kernel_modes(fx, po, name, mode, monkeypatch):
     assert bool(info.kernel_variant & 8) == (mode != "generic"), "wrong kernel took the program"
 
 
+# Self recurrences: an operand is the instruction's own result of the previous sample period.  They run
+# instruction-major, serially in time, with the carried value forwarded in a hardware register.
+CARRIED_PROGS = {
+    "onepole": progs.CFG4_ONEPOLE,
+    "carry_x": "static a = 0.25\ninput in_l 0\noutput out_l 0\nmacs a, in_l, a, 0.9\nmacs out_l, a, in_l, 0.5\nend",
+    "carry_y": "static a = 0.5\ninput in_l 0\ncontrol g = 0.7\noutput out_l 0\nmacsn a, in_l, g, a\nlimit out_l, a, in_l, 0.25\nend",
+    # two independent recurrences, the second fed by the first; wrap-around arithmetic; the state register is also an output
+    "cascade": "static s1 = 0.1\ninput in_l 0\ncontrol c = 0.3\noutput out_l 0\ninterp s1, s1, c, in_l\ninterp out_l, out_l, c, s1\nend",
+    "macw_acc": "static ph = 0.0\ninput in_l 0\noutput out_l 0\nmacw ph, ph, in_l, 0.37\nmacintw out_l, ph, ph, 0.5\nend",
+    "square": "static a = 0.9\ninput in_l 0\noutput out_l 0\nmacs a, in_l, a, a\nacc3 out_l, a, in_l, 0.125\nend",
+    "log_rec": "static a = 0.2\ninput in_l 0\noutput out_l 0\nlog a, a, 3, 0\nmacs a, in_l, a, 0.5\nmacs out_l, a, 0.5, 0.5\nend",
+    "log_self": "static a = 0.6\ninput in_l 0\noutput out_l 0\nexp a, a, 2, 0\nmacs out_l, a, in_l, 0.5\nend",
+}
+
+
+@pytest.mark.parametrize("name", sorted(CARRIED_PROGS))
+@pytest.mark.parametrize("mode", ["auto", "M2", "M4", "K1", "K2", "nocarry", "noshort"])
+def test_carried_recurrences(fx, po, name, mode, monkeypatch):
+    if mode[0] == "M":
+        monkeypatch.setenv("FX8010_TUNE_M", mode[1:])
+    elif mode[0] == "K":
+        monkeypatch.setenv("FX8010_TUNE_K", mode[1:])
+    elif mode == "nocarry":
+        monkeypatch.setenv("FX8010_NO_CARRY", "1")
+    elif mode == "noshort":
+        monkeypatch.setenv("FX8010_NO_CARRY", "1")
+        monkeypatch.setenv("FX8010_NO_SHORT", "1")
+    rng = np.random.default_rng(21)
+    n = 264
+    ctl = {}
+    if name in ("onepole",):
+        ctl["filter_cutoff"] = (0.001 + 0.998 * rng.random(n)).astype(np.float32)
+    if name in ("cascade",):
+        ctl["c"] = rng.random(n).astype(np.float32)
+    info = run_case(fx, po, CARRIED_PROGS[name], n, [1, 2, 37, 8, 16, 3, 100, 1], rng, controls=ctl, what=f"{name} {mode}")
+    # log_rec carries `a` from the LAST instruction to the first one: not a self recurrence
+    carried = mode not in ("nocarry", "noshort") and name != "log_rec"
+    assert bool(info.kernel_variant & 8) == carried, "wrong kernel took the program"
+    if mode == "nocarry":
+        assert info.kernel_variant & 32, "expected the short-program kernel"
+    if mode == "noshort":
+        assert not (info.kernel_variant & (8 | 32))
+
+
 def test_input_channel_quirk_takes_generic_kernel(fx, po):
     """X/Y INPUT operands read A's channel (reference :1057-1060): such a program is stateless but must not
     use the stage-aliasing kernel."""
