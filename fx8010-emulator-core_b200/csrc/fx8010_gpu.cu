@@ -73,6 +73,7 @@ struct fx8010_gpu {
     // stateless fast path (fx8010_stateless.cuh)
     bool in_alias = false;                       // every INPUT-typed operand is preloaded by its own instruction
     bool sl_ok = false;                          // program qualifies
+    bool sl_ccr_live = false;                    // the uploaded stateless encoding keeps per-sample CCR stores
     bool sl_serial = false;                      // ... with self-carried operands: one time segment, state loaded and kept
     bool acc_writer = false;                     // some instruction sets the accumulator
     std::vector<uint8_t> sl_carry;               // per instruction: bit o set = operand o (A, X, Y) is the instruction's own previous result
@@ -368,6 +369,7 @@ void encode_stateless(fx8010_gpu* h, int K, int B, int M) {
     const int n = (int)h->instrs.size(), nr = (int)h->regs.size(), C = h->C;
     std::vector<int> last_writer(C, -1);
     bool ccr_read = h->sl_class[0] == ROW_RW;
+    h->sl_ccr_live = false;
     for (int i = 0; i < n; ++i) {
         const Uop u = uop_of(h, h->instrs[i]);
         if (writes_r(u) && h->regs[h->instrs[i].r].type == FX_REG_OUTPUT) last_writer[h->regs[h->instrs[i].r].io_index] = i;
@@ -379,7 +381,7 @@ void encode_stateless(fx8010_gpu* h, int K, int B, int M) {
         if (u == U_END || u == U_NOP) continue;
         uint32_t w0 = (uint32_t)u, aux = 0;
         if (h->sl_class[in.r] == ROW_WO) w0 |= F_ST_LAST;
-        if (ccr_read || in.r == 0) w0 |= F_CCR;                 // a `ccr` operand somewhere: every setCCR is kept per sample
+        if (ccr_read || in.r == 0) { w0 |= F_CCR; h->sl_ccr_live = true; }                 // a `ccr` operand somewhere: every setCCR is kept per sample
         w0 |= (uint32_t)h->sl_carry[i] << SL_CARRY_SHIFT;       // operands that are this instruction's own previous result
         if (h->regs[in.r].type == FX_REG_OUTPUT) {
             const int c = h->regs[in.r].io_index;
@@ -656,7 +658,9 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
         while (B > 32 && (N / K + B - 1) / B < 2 * h->num_sms) B >>= 1;
     // A serial launch has few warps, and the batch is also how far the input stage runs ahead: make it deep.
     int M = h->tune_M ? h->tune_M : (h->sl_serial ? SL_MAX_M : 4);
-    while (!h->tune_M && M > 1 && sl_smem_bytes(h, B, K, M) > 48 * 1024) M >>= 1;
+    // serial: all blocks are resident at once; give each its share of the SM's shared memory
+    const size_t budget = h->sl_serial ? std::min<size_t>(h->smem_optin, (size_t)200 * 1024 / std::max(1, ((N / K + B - 1) / B + h->num_sms - 1) / h->num_sms)) : 48 * 1024;
+    while (!h->tune_M && M > 1 && sl_smem_bytes(h, B, K, M) > budget) M >>= 1;
     if (h->sl_serial && M < 2) M = 2;        // a carried operand reads row (m - 1) mod M while row m is written
     while (sl_smem_bytes(h, B, K, M) > h->smem_optin && B > 32) B >>= 1;
     if (sl_smem_bytes(h, B, K, M) > h->smem_optin) return fail(h, FX8010_ERR_CAPACITY, "register file does not fit in shared memory");
@@ -747,6 +751,7 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             p.n_smem_tabs = h->n_smem_tabs;
             for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
             p.acc_writer = h->acc_writer ? 1 : 0;
+            p.ccr_live = h->sl_ccr_live ? 1 : 0;
             p.pdl_late_wait = late_wait;
             SLKernelFn fn = pick_sl_kernel(L.K);
             bool& attr = h->sl_attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)];
@@ -846,7 +851,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     h->tune_M = env_int("FX8010_TUNE_M");
     h->tune_chunk = env_int("FX8010_TUNE_CHUNK");
     if (h->tune_chunk & (h->tune_chunk - 1) || h->tune_chunk > MAX_CHUNK) h->tune_chunk = 0;
-    if (h->tune_M != 1 && h->tune_M != 2 && h->tune_M != 4 && h->tune_M != 8) h->tune_M = 0;
+    if (h->tune_M != 1 && h->tune_M != 2 && h->tune_M != 4 && h->tune_M != 8 && h->tune_M != 16 && h->tune_M != 32) h->tune_M = 0;
     if (h->tune_K != 1 && h->tune_K != 2 && h->tune_K != 4) h->tune_K = 0;
     if (h->tune_B != 32 && h->tune_B != 64 && h->tune_B != 128) h->tune_B = 0;
     *out = h;

@@ -26,7 +26,7 @@ constexpr uint32_t SL_OFF_MASK = 0xfffffu;   // [0:20)  byte offset
 constexpr int SL_STRIDE_SHIFT = 20;          // [20:31) bytes between consecutive samples of the batch, in 16-byte units
 constexpr uint32_t SL_BUF = 1u << 31;        // input-stage row: add the offset of the current stage buffer
 constexpr uint32_t F_ST_LAST = 1u << 17;     // R is never read by the program: store it on the batch-final sample only
-constexpr int SL_MAX_M = 8;
+constexpr int SL_MAX_M = 32;             // a serial (recurrent) launch has few warps: its batch is also how far the input stage runs ahead of the arithmetic
 constexpr int SL_CARRY_SHIFT = 18;           // w0 bits 18..20: operand A / X / Y is this instruction's OWN result of the previous sample
                                              // (a self recurrence): row (m - 1) mod M on the first sample of a batch, then forwarded
                                              // in a hardware register — the recurrence never waits for shared memory
@@ -52,16 +52,20 @@ struct SLParams {
     int n_smem_tabs;
     int smem_tab_id[MAX_SMEM_TABLES];
     int acc_writer;             // some instruction sets the accumulator (else it keeps its value)
+    int ccr_live;               // somebody reads `ccr`: every setCCR is materialised per sample (else only the call's last one)
     int pdl_late_wait;
 };
 
 // Per-thread context of the stateless kernel, handed to the batch executor.
+__device__ __forceinline__ uint64_t pin64s(uint64_t v) { uint64_t o; asm volatile("mov.b64 %0, %1;" : "=l"(o) : "l"(v)); return o; }
+
 template <int K> struct SLCtx {
     uint32_t col_s;                 // this thread's shared-memory column (32-bit shared address)
     uint32_t tab_s;                 // staged tables + this lane's replica (32-bit shared address)
     const uint4* prog;
     float* out_b;                   // output row of the batch's first sample, this thread's instances
     int N, inst0, n_exec;
+    uint64_t Nl;                    // N, pinned in a register (ptxas otherwise re-reads the parameter bank inside the sample loops)
     size_t out_cstride;
     bool valid;
     uint32_t boff;                  // byte offset of the current input-stage buffer
@@ -77,117 +81,173 @@ template <int K> struct SLCtx {
 //                  to the output block.  Stateless programs are idempotent per sample, so the re-run
 //                  reproduces the same values.
 // All operand addresses are running 32-bit shared addresses (one add per operand and sample).
-template <int K, bool FINAL>
+// One decoded instruction, ready to run over the samples [m_lo, m_lo + n_m) of the batch.
+struct SLInstr {
+    uint32_t w0, uop, aux;              // flags word, micro-op, table word (wB.y)
+    uint32_t qr, qa, qx, qy, qccr;      // running 32-bit shared addresses of R, A, X, Y, CCR for the current sample
+    uint32_t sr, sa, sx, sy, sccr;      // bytes between consecutive samples (0: the same row for the whole batch)
+    bool ca, cx, cy;                    // operand is this instruction's own previous result (self recurrence)
+    bool st_r, st_c, st_o;              // store R / CCR / the output block
+    float* qo;                          // output block slot of the current sample
+    int n_m;
+};
+
+// Runs ONE instruction over the batch.  CM = how results are carried from sample to sample: 0 nothing (stateless
+// instruction), 1 operand A only (the common recurrence: `interp out, out, c, in`, `macs a, a, x, y`), 2 any mix.
+// The sample loop is software-pipelined over TWO operand register sets (unrolled by two, no register moves): the
+// operands of sample m + 1 go in flight before the arithmetic of sample m, operands whose row does not change are
+// read once, and a carried operand is written straight into the next set — a recurrence's chain holds arithmetic only.
+template <int K, bool FINAL, bool CCRV, int CM>
+__device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr& I) {
+    const uint64_t Nl = cx.Nl;
+    const uint32_t w0 = I.w0, uop = I.uop;
+    const int n_m = I.n_m;
+    const bool la = I.sa != 0u, lx = I.sx != 0u, ly = I.sy != 0u;   // the operand's row changes from sample to sample
+#define SL_EACH _Pragma("unroll") for (int k = 0; k < K; ++k)
+    // R store (:1079-1082 etc.), setCCR (:211-232), output (:1229-1233, :1248) for the current sample
+#define SL_WRITE(SETS_ACC)                                                                                       \
+        if (I.st_r) sts<K>(I.qr, r);                                                                             \
+        if (FINAL || CCRV) { if (I.st_c) { Vec<K> c; SL_EACH { c[k] = ccr_of(r[k]); } sts<K>(I.qccr, c); } }      \
+        if (!FINAL) { if (I.st_o) vstore<K>(I.qo, r); }                                                          \
+        else {                                                                                                   \
+            if (I.st_o) vstore<K>(p.latch + (size_t)(w0 >> 24) * cx.N + cx.inst0, r);                             \
+            if (SETS_ACC) cx.acc_last = accv;                                                                    \
+        }
+    // one sample: operands in set CUR, the next sample's go to set NXT
+#define SL_HALF(SETS_ACC, LOADS_XY, CUR, NXT, ...)                                                               \
+    {                                                                                                            \
+        Vec<K>&a = A##CUR, &x = X##CUR, &y = Y##CUR; Vec<K> r, accv;                                             \
+        (void)x; (void)y;                                                                                        \
+        if (!FINAL && m + 1 < n_m) {                                                                             \
+            if (la) { I.qa += I.sa; A##NXT = lds<K>(I.qa); }                                                     \
+            if (LOADS_XY && lx) { I.qx += I.sx; X##NXT = lds<K>(I.qx); }                                         \
+            if (LOADS_XY && ly) { I.qy += I.sy; Y##NXT = lds<K>(I.qy); }                                         \
+        }                                                                                                        \
+        __VA_ARGS__                                                                                              \
+        SL_WRITE(SETS_ACC)                                                                                       \
+        if (CM == 1) A##NXT = r;                                                                                 \
+        else if (CM == 2) { SL_EACH { if (I.ca) A##NXT[k] = r[k]; if (I.cx) X##NXT[k] = r[k]; if (I.cy) Y##NXT[k] = r[k]; } } \
+        ++m; I.qr += I.sr; I.qccr += I.sccr; I.qo += Nl;                                                         \
+    }
+#define SL_LOOP(SETS_ACC, LOADS_XY, ...)                                                                         \
+    {                                                                                                            \
+        int m = 0;                                                                                               \
+        if (!FINAL) {                                                                                            \
+            _Pragma("unroll 1") while (m + 1 < n_m) {                                                            \
+                SL_HALF(SETS_ACC, LOADS_XY, 0, 1, __VA_ARGS__) SL_HALF(SETS_ACC, LOADS_XY, 1, 0, __VA_ARGS__)     \
+            }                                                                                                    \
+        }                                                                                                        \
+        if (m < n_m) SL_HALF(SETS_ACC, LOADS_XY, 0, 1, __VA_ARGS__)                                              \
+    }
+    const bool tab_op = (uop == U_LOG || uop == U_EXP);
+    const bool dyn_sel = tab_op && !(w0 & (F_TAB_SMEM | F_TAB_IMM));     // LOG/EXP reading its selector from X every sample
+    Vec<K> A0 = lds<K>(I.qa), X0, Y0;                                    // the first sample's operands (in both sets: rows that never change stay put)
+    if (!tab_op) { X0 = lds<K>(I.qx); Y0 = lds<K>(I.qy); }
+    else {
+        SL_EACH { X0[k] = 0.0f; Y0[k] = 0.0f; }                          // LOG/EXP never read Y (:1114 TODO), and X only as a dynamic selector
+        if (dyn_sel) X0 = lds<K>(I.qx);
+    }
+    Vec<K> A1 = A0, X1 = X0, Y1 = Y0;
+    switch (uop) {
+    case U_MACS: SL_LOOP(true, true,
+        SL_EACH { accv[k] = __fadd_rn(a[k], __fmul_rn(x[k], y[k])); r[k] = sat1(accv[k]); }) break;
+    case U_MACSN: SL_LOOP(true, true,
+        SL_EACH { accv[k] = __fsub_rn(a[k], __fmul_rn(x[k], y[k])); r[k] = sat1(accv[k]); }) break;
+    case U_ACC3: SL_LOOP(true, true,
+        SL_EACH { accv[k] = __fadd_rn(__fadd_rn(a[k], x[k]), y[k]); r[k] = sat1(accv[k]); }) break;
+    case U_MACW: SL_LOOP(true, true,
+        SL_EACH { r[k] = __fadd_rn(a[k], wrap1(__fmul_rn(x[k], y[k]))); accv[k] = r[k]; }) break;
+    case U_MACWN: SL_LOOP(true, true,
+        SL_EACH { r[k] = __fsub_rn(a[k], wrap1(__fmul_rn(x[k], y[k]))); accv[k] = r[k]; }) break;
+    case U_MACINTW: SL_LOOP(true, true,
+        SL_EACH { r[k] = wrap1(__fadd_rn(a[k], __fmul_rn(x[k], y[k]))); accv[k] = r[k]; }) break;
+    case U_ANDXOR: SL_LOOP(false, true,
+        SL_EACH { r[k] = __int2float_rn(logic_ops(a[k], x[k], y[k])); accv[k] = 0.0f; }) break;
+    case U_TSTNEG: SL_LOOP(true, true,
+        SL_EACH {
+            const int32_t q = cvt_x86(__fmul_rn(x[k], 2147483648.0f));
+            r[k] = (a[k] >= y[k]) ? x[k] : __fmul_rn(__int2float_rn(~q), 4.656612873077392578125e-10f); accv[k] = r[k];
+        }) break;
+    case U_LIMIT: SL_LOOP(true, true,
+        SL_EACH { r[k] = (a[k] >= y[k]) ? x[k] : y[k]; accv[k] = r[k]; }) break;
+    case U_LIMITN: SL_LOOP(true, true,
+        SL_EACH { r[k] = (a[k] < y[k]) ? x[k] : y[k]; accv[k] = r[k]; }) break;
+    case U_INTERP: {
+        const bool x_varies = lx || I.cx;         // a constant coefficient: 1.0 - X is formed once per batch
+        double omx[K];
+        SL_EACH { omx[k] = __dsub_rn(1.0, (double)X0[k]); }
+        SL_LOOP(true, true,
+            if (x_varies) { SL_EACH { omx[k] = __dsub_rn(1.0, (double)x[k]); } }
+            SL_EACH {
+                const double d = __dadd_rn(__dmul_rn(omx[k], (double)a[k]), (double)__fmul_rn(x[k], y[k]));
+                accv[k] = __double2float_rn(d); r[k] = sat1(accv[k]);
+            })
+        break; }
+    case U_LOG:
+    case U_EXP: {
+        const uint32_t tb_s = cx.tab_s + (I.aux >> 24) * (uint32_t)TAB_SMEM_BYTES;
+        SL_LOOP(true, false,
+            if (dyn_sel && lx && m + 1 < n_m) { I.qx += I.sx; if (m & 1) X0 = lds<K>(I.qx); else X1 = lds<K>(I.qx); }
+            int idx[K];
+            double xd[K];
+            bool wild = false;
+            SL_EACH { wild |= !(fabsf(a[k]) <= 1.0f); xd[k] = (double)a[k]; }
+            if (!wild) { SL_EACH { idx[k] = table_index_inrange(xd[k]); } }
+            else { SL_EACH { idx[k] = table_index_wild(a[k]); if (!(fabsf(a[k]) <= 1.0f)) cx.flags |= FX8010_RT_TABLE_RANGE; } }   // rule U6
+            if (w0 & F_TAB_SMEM) {
+                SL_EACH { double y1; double slope; lds_f64x2(tb_s + (uint32_t)idx[k] * (TAB_REPL * 16u), y1, slope); r[k] = table_finish(xd[k], idx[k], y1, slope); }
+            } else {
+                SL_EACH {
+                    int tsel;
+                    if (w0 & F_TAB_IMM) tsel = (int)(I.aux >> 24);
+                    else {
+                        int32_t sel = cvt_x86(x[k]);
+                        if (sel < 0 || sel > FX8010_TABLE_COUNT - 1) { cx.flags |= FX8010_RT_TABLE_RANGE; sel = sel < 0 ? 0 : FX8010_TABLE_COUNT - 1; }
+                        tsel = (uop == U_EXP ? FX8010_TABLE_COUNT : 0) + sel;
+                    }
+                    const double2 e = __ldg(reinterpret_cast<const double2*>(p.tabs + tsel * FX8010_TABLE_ENTRIES + idx[k]));
+                    r[k] = table_finish(xd[k], idx[k], e.x, e.y);
+                }
+            }
+            SL_EACH { accv[k] = r[k]; })
+        break; }
+    default: break;      // nothing else can appear in this kernel's encoded stream
+    }
+#undef SL_EACH
+#undef SL_WRITE
+#undef SL_HALF
+#undef SL_LOOP
+}
+
+// Runs the whole program for samples [m_lo, m_hi) of the current batch, instruction-major.
+template <int K, bool FINAL, bool CCRV>
 __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const int m_lo, const int m_hi) {
     uint4 nA = cx.prog[0], nB = cx.prog[1];
     const int n_exec = cx.n_exec;
-    const int n_m = m_hi - m_lo;
     for (int pc = 0; pc < n_exec; ++pc) {
         const uint4 wA = nA, wB = nB;
         nA = cx.prog[2 * pc + 2]; nB = cx.prog[2 * pc + 3];
         const uint32_t w0 = wA.x;
-        const uint32_t uop = w0 & 0xffu;
         // decode once per batch: address of sample m_lo and per-sample stride of every operand, store modes
 #define SL_STRIDE(w) ((((w) >> SL_STRIDE_SHIFT) & 0x7ffu) << 4)
 #define SL_ADDR(w) (cx.col_s + ((w) & SL_OFF_MASK) + (((w) & SL_BUF) ? cx.boff : 0u) + (uint32_t)m_lo * SL_STRIDE(w))
-        // a carried operand: the row of the previous sample (row M - 1 before sample 0), and the pointer stays there
+        // a carried operand: the row of the previous sample (row M - 1 before sample 0); later samples get it forwarded
 #define SL_ADDR_C(w) (cx.col_s + ((w) & SL_OFF_MASK) + (uint32_t)((m_lo == 0 ? p.M : m_lo) - 1) * SL_STRIDE(w))
-        const bool ca = (w0 >> SL_CARRY_SHIFT) & 1u, cxx = (w0 >> SL_CARRY_SHIFT) & 2u, cy = (w0 >> SL_CARRY_SHIFT) & 4u;
-        const uint32_t sr = SL_STRIDE(wA.y), sa = ca ? 0u : SL_STRIDE(wA.z), sx = cxx ? 0u : SL_STRIDE(wA.w), sy = cy ? 0u : SL_STRIDE(wB.x), sccr = SL_STRIDE(wB.z);
-        uint32_t qr = SL_ADDR(wA.y), qa = ca ? SL_ADDR_C(wA.z) : SL_ADDR(wA.z), qx = cxx ? SL_ADDR_C(wA.w) : SL_ADDR(wA.w),
-                 qy = cy ? SL_ADDR_C(wB.x) : SL_ADDR(wB.x), qccr = SL_ADDR(wB.z);
-        Vec<K> rp;                                // the previous sample's result (carried operands)
-        _Pragma("unroll") for (int k = 0; k < K; ++k) rp[k] = 0.0f;
-        const bool st_r = FINAL || !(w0 & F_ST_LAST);
-        const bool st_c = FINAL || (w0 & F_CCR);
-        const bool st_o = (w0 & F_OUT_DIRECT) && cx.valid;
-        float* qo = cx.out_b + (size_t)(w0 >> 24) * cx.out_cstride + (size_t)m_lo * cx.N;
-        const int N = cx.N;
-#define SL_EACH _Pragma("unroll") for (int k = 0; k < K; ++k)
-#define SL_FOR_M _Pragma("unroll 1") for (int m = 0; m < n_m; ++m, qr += sr, qa += sa, qx += sx, qy += sy, qccr += sccr, qo += N)
-        // R store (:1079-1082 etc.), setCCR (:211-232), output (:1229-1233, :1248) for the current sample
-#define SL_WRITE(SETS_ACC)                                                                                       \
-        {                                                                                                        \
-            if (st_r) sts<K>(qr, r);                                                                             \
-            rp = r;                                                                                              \
-            if (st_c) { Vec<K> c; SL_EACH { c[k] = ccr_of(r[k]); } sts<K>(qccr, c); }                             \
-            if (!FINAL) { if (st_o) vstore<K>(qo, r); }                                                          \
-            else {                                                                                               \
-                if (st_o) vstore<K>(p.latch + (size_t)(w0 >> 24) * cx.N + cx.inst0, r);                           \
-                if (SETS_ACC) cx.acc_last = accv;                                                                \
-            }                                                                                                    \
-        }
-#define SL_LOAD3 Vec<K> a = lds<K>(qa), x = lds<K>(qx), y = lds<K>(qy); Vec<K> r, accv;                            \
-        if (m > 0) { SL_EACH { a[k] = ca ? rp[k] : a[k]; x[k] = cxx ? rp[k] : x[k]; y[k] = cy ? rp[k] : y[k]; } }
-        switch (uop) {
-        case U_MACS: SL_FOR_M { SL_LOAD3
-            SL_EACH { accv[k] = __fadd_rn(a[k], __fmul_rn(x[k], y[k])); r[k] = sat1(accv[k]); } SL_WRITE(true) } break;
-        case U_MACSN: SL_FOR_M { SL_LOAD3
-            SL_EACH { accv[k] = __fsub_rn(a[k], __fmul_rn(x[k], y[k])); r[k] = sat1(accv[k]); } SL_WRITE(true) } break;
-        case U_ACC3: SL_FOR_M { SL_LOAD3
-            SL_EACH { accv[k] = __fadd_rn(__fadd_rn(a[k], x[k]), y[k]); r[k] = sat1(accv[k]); } SL_WRITE(true) } break;
-        case U_MACW: SL_FOR_M { SL_LOAD3
-            SL_EACH { r[k] = __fadd_rn(a[k], wrap1(__fmul_rn(x[k], y[k]))); accv[k] = r[k]; } SL_WRITE(true) } break;
-        case U_MACWN: SL_FOR_M { SL_LOAD3
-            SL_EACH { r[k] = __fsub_rn(a[k], wrap1(__fmul_rn(x[k], y[k]))); accv[k] = r[k]; } SL_WRITE(true) } break;
-        case U_MACINTW: SL_FOR_M { SL_LOAD3
-            SL_EACH { r[k] = wrap1(__fadd_rn(a[k], __fmul_rn(x[k], y[k]))); accv[k] = r[k]; } SL_WRITE(true) } break;
-        case U_ANDXOR: SL_FOR_M { SL_LOAD3
-            SL_EACH { r[k] = __int2float_rn(logic_ops(a[k], x[k], y[k])); accv[k] = 0.0f; } SL_WRITE(false) } break;
-        case U_TSTNEG: SL_FOR_M { SL_LOAD3
-            SL_EACH {
-                const int32_t q = cvt_x86(__fmul_rn(x[k], 2147483648.0f));
-                r[k] = (a[k] >= y[k]) ? x[k] : __fmul_rn(__int2float_rn(~q), 4.656612873077392578125e-10f); accv[k] = r[k];
-            } SL_WRITE(true) } break;
-        case U_LIMIT: SL_FOR_M { SL_LOAD3
-            SL_EACH { r[k] = (a[k] >= y[k]) ? x[k] : y[k]; accv[k] = r[k]; } SL_WRITE(true) } break;
-        case U_LIMITN: SL_FOR_M { SL_LOAD3
-            SL_EACH { r[k] = (a[k] < y[k]) ? x[k] : y[k]; accv[k] = r[k]; } SL_WRITE(true) } break;
-        case U_INTERP: SL_FOR_M { SL_LOAD3
-            SL_EACH {
-                const double d = __dadd_rn(__dmul_rn(__dsub_rn(1.0, (double)x[k]), (double)a[k]), (double)__fmul_rn(x[k], y[k]));
-                accv[k] = __double2float_rn(d); r[k] = sat1(accv[k]);
-            } SL_WRITE(true) } break;
-        case U_LOG:
-        case U_EXP: {
-            const uint32_t tb_s = cx.tab_s + (wB.y >> 24) * (uint32_t)TAB_SMEM_BYTES;
-            SL_FOR_M {
-                Vec<K> a = lds<K>(qa);
-                if (m > 0) { SL_EACH { a[k] = ca ? rp[k] : a[k]; } }
-                Vec<K> r, accv;
-                int idx[K];
-                double xd[K];
-                bool wild = false;
-                SL_EACH { wild |= !(fabsf(a[k]) <= 1.0f); xd[k] = (double)a[k]; }
-                if (!wild) { SL_EACH { idx[k] = table_index_inrange(xd[k]); } }
-                else { SL_EACH { idx[k] = table_index_wild(a[k]); if (!(fabsf(a[k]) <= 1.0f)) cx.flags |= FX8010_RT_TABLE_RANGE; } }   // rule U6
-                if (w0 & F_TAB_SMEM) {
-                    SL_EACH { double y1, slope; lds_f64x2(tb_s + (uint32_t)idx[k] * (TAB_REPL * 16u), y1, slope); r[k] = table_finish(xd[k], idx[k], y1, slope); }
-                } else {
-                    Vec<K> x;
-                    if (!(w0 & F_TAB_IMM)) x = lds<K>(qx);
-                    SL_EACH {
-                        int tsel;
-                        if (w0 & F_TAB_IMM) tsel = (int)(wB.y >> 24);
-                        else {
-                            int32_t sel = cvt_x86(x[k]);
-                            if (sel < 0 || sel > FX8010_TABLE_COUNT - 1) { cx.flags |= FX8010_RT_TABLE_RANGE; sel = sel < 0 ? 0 : FX8010_TABLE_COUNT - 1; }
-                            tsel = (uop == U_EXP ? FX8010_TABLE_COUNT : 0) + sel;
-                        }
-                        const double2 e = __ldg(reinterpret_cast<const double2*>(p.tabs + tsel * FX8010_TABLE_ENTRIES + idx[k]));
-                        r[k] = table_finish(xd[k], idx[k], e.x, e.y);
-                    }
-                }
-                SL_EACH { accv[k] = r[k]; }
-                SL_WRITE(true)
-            }
-            break; }
-        default: break;      // nothing else can appear in a stateless program's encoded stream
-        }
-#undef SL_EACH
-#undef SL_FOR_M
-#undef SL_WRITE
-#undef SL_LOAD3
+        SLInstr I;
+        I.w0 = w0; I.uop = w0 & 0xffu; I.aux = wB.y; I.n_m = m_hi - m_lo;
+        const uint32_t cbits = (w0 >> SL_CARRY_SHIFT) & 7u;
+        I.ca = cbits & 1u; I.cx = cbits & 2u; I.cy = cbits & 4u;
+        I.sr = SL_STRIDE(wA.y); I.sa = I.ca ? 0u : SL_STRIDE(wA.z); I.sx = I.cx ? 0u : SL_STRIDE(wA.w); I.sy = I.cy ? 0u : SL_STRIDE(wB.x); I.sccr = SL_STRIDE(wB.z);
+        I.qr = SL_ADDR(wA.y); I.qa = I.ca ? SL_ADDR_C(wA.z) : SL_ADDR(wA.z); I.qx = I.cx ? SL_ADDR_C(wA.w) : SL_ADDR(wA.w);
+        I.qy = I.cy ? SL_ADDR_C(wB.x) : SL_ADDR(wB.x); I.qccr = SL_ADDR(wB.z);
+        I.st_r = FINAL || !(w0 & F_ST_LAST);
+        I.st_c = FINAL || (CCRV && (w0 & F_CCR));
+        I.st_o = (w0 & F_OUT_DIRECT) && cx.valid;
+        I.qo = cx.out_b + (size_t)(w0 >> 24) * cx.out_cstride + (size_t)m_lo * cx.Nl;
+        if (FINAL || CCRV) sl_run<K, FINAL, CCRV, 2>(p, cx, I);          // cold paths: one general copy
+        else if (cbits == 0u) sl_run<K, false, false, 0>(p, cx, I);
+        else if (cbits == 1u) sl_run<K, false, false, 1>(p, cx, I);
+        else sl_run<K, false, false, 2>(p, cx, I);
 #undef SL_ADDR
 #undef SL_ADDR_C
     }
@@ -222,9 +282,9 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
             const int n = s_end - s0;                    // samples left (>= 1); the batch takes min(M, n)
             const float* g = p.in + (size_t)s0 * N + inst0;
             float* d = at(p.stage0 + boff);
-#pragma unroll
-            for (int m = 0; m < SL_MAX_M; ++m)
-                if (m < M && m < n) cp_async<4 * K>(reinterpret_cast<unsigned char*>(d) + (uint32_t)m * row_bytes, g + (size_t)m * N);
+            const int nm = min(M, n);
+#pragma unroll 4
+            for (int m = 0; m < nm; ++m) cp_async<4 * K>(reinterpret_cast<unsigned char*>(d) + (uint32_t)m * row_bytes, g + (size_t)m * N);
             for (int c = 1; c < C; ++c) {
                 g += p.in_cstride;
                 const uint32_t base = p.stage0 + (uint32_t)c * 2u * buf_bytes + boff;
@@ -259,7 +319,7 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
     cx.col_s = (uint32_t)__cvta_generic_to_shared(col);
     cx.tab_s = (uint32_t)__cvta_generic_to_shared(s_tab) + (uint32_t)(tid & (TAB_REPL - 1)) * 16u;
     cx.prog = c_prog[p.slot];
-    cx.N = N; cx.inst0 = inst0; cx.valid = valid; cx.boff = 0; cx.flags = 0;
+    cx.N = N; cx.Nl = pin64s((uint64_t)N); cx.inst0 = inst0; cx.valid = valid; cx.boff = 0; cx.flags = 0;
     cx.n_exec = p.n_exec; cx.out_cstride = p.out_cstride;
 #pragma unroll
     for (int k = 0; k < K; ++k) cx.acc_last[k] = 0.0f;
@@ -270,11 +330,11 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
         const int mb = min(M, s_end - s0);
         fetch_batch(s0 + M, cx.boff ^ buf_bytes);
         cp_async_wait<1>();
-        sl_exec<K, false>(p, cx, 0, mb);
+        if (p.ccr_live) sl_exec<K, false, true>(p, cx, 0, mb); else sl_exec<K, false, false>(p, cx, 0, mb);
         if (s0 + mb == p.n_samples && valid) {
             // This thread owns the call's last sample: leave the final state behind (cold path).
             if (p.pdl_late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // state writes follow
-            sl_exec<K, true>(p, cx, mb - 1, mb);
+            sl_exec<K, true, true>(p, cx, mb - 1, mb);
             for (int i = 0; i < p.n_wb; ++i) {
                 const uint2 e = p.wb_list[i];
                 const unsigned char* src = col + (e.x & SL_OFF_MASK) + ((e.x & SL_BUF) ? cx.boff : 0u) + (uint32_t)(mb - 1) * SL_STRIDE(e.x);
