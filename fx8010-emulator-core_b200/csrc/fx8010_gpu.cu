@@ -31,7 +31,7 @@ thread_local std::string g_create_error;
 
 struct Launch { int K, B, n_seg, seg_len, grid_x; size_t smem; int M; int chunk; };   // M > 0: stateless kernel, samples per batch
 struct PlanKey { int ns = -1; unsigned align = 0; };
-enum RowClass { ROW_NONE = 0, ROW_RO, ROW_WO, ROW_RW, ROW_IN };
+enum RowClass { ROW_NONE = 0, ROW_RO, ROW_WO, ROW_RW, ROW_IN, ROW_TR };
 
 }  // namespace
 
@@ -73,6 +73,11 @@ struct fx8010_gpu {
     // stateless fast path (fx8010_stateless.cuh)
     bool in_alias = false;                       // every INPUT-typed operand is preloaded by its own instruction
     bool sl_ok = false;                          // program qualifies
+    // TRAM read streams of the instruction-major kernel: the one IDELAY/XDELAY READ of a TRAM, prefetched like an input
+    struct TramStream { int isx, reg, yreg, w_yreg, w_first; } sl_tr[2];
+    int sl_n_tr = 0;
+    bool sl_tram = false;                        // the program has TRAM instructions (pointers are loaded and kept)
+    int use_tram_im = 1;
     bool sl_ccr_live = false;                    // the uploaded stateless encoding keeps per-sample CCR stores
     bool sl_serial = false;                      // ... with self-carried operands: one time segment, state loaded and kept
     bool acc_writer = false;                     // some instruction sets the accumulator
@@ -87,7 +92,7 @@ struct fx8010_gpu {
     int sl_M = 0;                                // batch length of the uploaded encoding (0 = generic encoding uploaded)
     std::vector<uint2> sl_load, sl_wb;
     uint2* d_sl_load = nullptr; uint2* d_sl_wb = nullptr;
-    bool sl_attr_set[3] = {};                 // MaxDynamicSharedMemorySize set for kernel <K, SKIP, EXT>
+    bool sl_attr_set[2][3] = {};                 // MaxDynamicSharedMemorySize set for kernel <K, SKIP, EXT>
     int n_exec = 0;                              // encoded instructions
     std::vector<uint32_t> latch_ch;              // channels served from the latch every sample period
     // device state
@@ -288,8 +293,47 @@ void analyse(fx8010_gpu* h) {
     // accumulators `macs a, a, x, y`), the register having no other writer.  Running instruction i over a batch of
     // samples before instruction i + 1 keeps every such dependence (loop distribution); a value carried from a LATER
     // instruction to an earlier one would not survive it, and sends the program to the sample-major kernels.
-    h->sl_ok = !h->has_skip && !h->has_ext && all_ch;
-    h->sl_serial = false;
+    // TRAM programs qualify when each TRAM has at most one READ and one WRITE instruction (then both pointers advance
+    // by one per sample and the distance between them is constant), their offsets come from registers the program never
+    // writes, and the READ's target register has no other writer and is never read before the READ: the reads are then
+    // prefetched a batch ahead, like an input channel, as long as the delay is longer than two batches (checked per
+    // thread at kernel start; shorter delays run the same code one sample at a time).
+    bool has_noise_or_macmv = false;
+    int n_rd[2] = {0, 0}, n_wr[2] = {0, 0};
+    h->sl_n_tr = 0; h->sl_tram = false;
+    bool tram_ok = h->use_tram_im != 0;
+    for (int i = 0; i < n; ++i) {
+        const fx8010_instr& in = h->instrs[i];
+        const Uop u = uop_of(h, in);
+        if (in.has_noise || u == U_MACMV) has_noise_or_macmv = true;
+        const bool rd = (u == U_IREAD || u == U_XREAD), wr = (u == U_IWRITE || u == U_XWRITE);
+        if (!rd && !wr) continue;
+        h->sl_tram = true;
+        const int t = (u == U_XREAD || u == U_XWRITE) ? 1 : 0;
+        if (h->written[in.y]) tram_ok = false;
+        if (rd) {
+            if (n_rd[t]++ || h->regs[in.a].type == FX_REG_INPUT || in.a == 0) tram_ok = false;
+            else {
+                fx8010_gpu::TramStream& q = h->sl_tr[h->sl_n_tr++];
+                q.isx = t; q.reg = in.a; q.yreg = in.y; q.w_yreg = -1; q.w_first = 0;
+            }
+        } else if (n_wr[t]++) tram_ok = false;
+    }
+    for (int i = 0; i < n && tram_ok; ++i) {               // the WRITE that shares a TRAM with each READ stream
+        const fx8010_instr& in = h->instrs[i];
+        const Uop u = uop_of(h, in);
+        if (u != U_IWRITE && u != U_XWRITE) continue;
+        for (int q = 0; q < h->sl_n_tr; ++q)
+            if (h->sl_tr[q].isx == (u == U_XWRITE ? 1 : 0)) {
+                h->sl_tr[q].w_yreg = in.y;
+                bool read_seen = false;
+                for (int j = 0; j < i; ++j) { const Uop uj = uop_of(h, h->instrs[j]); if (uj == (u == U_XWRITE ? U_XREAD : U_IREAD)) read_seen = true; }
+                h->sl_tr[q].w_first = read_seen ? 0 : 1;
+            }
+    }
+    if (!tram_ok) { h->sl_n_tr = 0; }
+    h->sl_ok = !h->has_skip && !has_noise_or_macmv && (!h->sl_tram || tram_ok) && all_ch;
+    h->sl_serial = h->sl_tram;
     h->sl_carry.assign(n, 0); h->sl_carried_reg.assign(nr, 0);
     std::vector<int> n_writers(nr, 0);
     for (int i = 0; i < n; ++i) {
@@ -302,6 +346,7 @@ void analyse(fx8010_gpu* h) {
         if (px && in.x != in.a) n_writers[in.x]++;
         if (py && in.y != in.a && in.y != in.x) n_writers[in.y]++;
         if (writes_r(u)) n_writers[in.r]++;
+        if (u == U_IREAD || u == U_XREAD) n_writers[in.a]++;
     }
     std::vector<uint8_t> sl_defined(nr, 0);
     std::vector<uint8_t> is_read(nr, 0);
@@ -316,14 +361,20 @@ void analyse(fx8010_gpu* h) {
         if (py) sl_defined[in.y] = 1;
         {
             const int opr[3] = {in.a, in.x, in.y};
+            const bool tram_rd = (u == U_IREAD || u == U_XREAD);
             for (int o = 0; o < 3; ++o) {
                 const int g = opr[o];
+                if (tram_rd && o == 0) continue;                        // A of a TRAM READ is its target
                 if (!h->written[g] || sl_defined[g]) continue;          // never written, or produced earlier in this period
                 if (h->use_carry && g != 0 && writes_r(u) && in.r == g && n_writers[g] == 1 && h->regs[g].type != FX_REG_INPUT) {
                     h->sl_carry[i] |= (uint8_t)(1u << o); h->sl_carried_reg[g] = 1; h->sl_serial = true;
                 } else h->sl_ok = false;
             }
             if (writes_r(u)) { sl_defined[in.r] = 1; sl_defined[0] = 1; }
+            if (tram_rd) {
+                if (n_writers[in.a] != 1) h->sl_ok = false;             // the stage rows stand in for the register: no other writer
+                sl_defined[in.a] = 1;
+            }
         }
         const int ch = h->regs[in.a].io_index;
         if ((pa && h->regs[in.a].io_index != ch) || (px && h->regs[in.x].io_index != ch) || (py && h->regs[in.y].io_index != ch)) h->sl_ok = false;
@@ -331,7 +382,8 @@ void analyse(fx8010_gpu* h) {
         const int ops[3] = {in.a, in.x, in.y};
         const bool pre[3] = {pa, px, py};
         for (int o = 0; o < 3; ++o) if (h->regs[ops[o]].type == FX_REG_INPUT && !pre[o]) h->sl_ok = false;
-        is_read[in.a] = is_read[in.x] = 1;
+        if (!(u == U_IREAD || u == U_XREAD)) is_read[in.a] = 1;
+        is_read[in.x] = 1;
         if (u != U_LOG && u != U_EXP) is_read[in.y] = 1;
     }
     h->sl_class.assign(nr, ROW_NONE); h->sl_index.assign(nr, 0);
@@ -340,6 +392,9 @@ void analyse(fx8010_gpu* h) {
         for (int r = 0; r < nr; ++r) {
             if (h->row_of[r] < 0) continue;
             if (h->regs[r].type == FX_REG_INPUT) { h->sl_class[r] = ROW_IN; continue; }
+            bool is_tr = false;
+            for (int q = 0; q < h->sl_n_tr; ++q) if (h->sl_tr[q].reg == r) { h->sl_class[r] = ROW_TR; h->sl_index[r] = q; is_tr = true; }
+            if (is_tr) continue;
             if (!h->written[r]) { h->sl_class[r] = ROW_RO; h->sl_index[r] = h->sl_n_ro++; }
             else if (!is_read[r]) { h->sl_class[r] = ROW_WO; h->sl_index[r] = h->sl_n_wo++; }
             else { h->sl_class[r] = ROW_RW; h->sl_index[r] = h->sl_n_rw++; }
@@ -348,7 +403,7 @@ void analyse(fx8010_gpu* h) {
 
 size_t sl_smem_bytes(const fx8010_gpu* h, int B, int K, int M) {
     return (size_t)h->n_smem_tabs * TAB_SMEM_BYTES +
-           (size_t)B * K * 4 * ((size_t)h->sl_n_ro + h->sl_n_wo + (size_t)h->sl_n_rw * M + 2 * (size_t)h->C * M);
+           (size_t)B * K * 4 * ((size_t)h->sl_n_ro + h->sl_n_wo + (size_t)h->sl_n_rw * M + 2 * (size_t)(h->C + h->sl_n_tr) * M);
 }
 
 // Operand word of register r for the stateless kernel (see fx8010_stateless.cuh).
@@ -361,6 +416,7 @@ uint32_t sl_word(const fx8010_gpu* h, int r, int B, int K, int M) {
     case ROW_WO: return wo0 + (uint32_t)h->sl_index[r] * row_bytes;
     case ROW_RW: return (rw0 + (uint32_t)h->sl_index[r] * M * row_bytes) | (stride16 << SL_STRIDE_SHIFT);
     case ROW_IN: return (st0 + (uint32_t)h->regs[r].io_index * 2u * M * row_bytes) | (stride16 << SL_STRIDE_SHIFT) | SL_BUF;
+    case ROW_TR: return (st0 + (uint32_t)(h->C + h->sl_index[r]) * 2u * M * row_bytes) | (stride16 << SL_STRIDE_SHIFT) | SL_BUF;   // TRAM read stream: stage rows after the input channels'
     default: return 0;   // never referenced
     }
 }
@@ -637,8 +693,9 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
 }
 
 typedef void (*SLKernelFn)(const SLParams);
-SLKernelFn pick_sl_kernel(int K) {
-    return K == 4 ? fx_stateless_kernel<4> : (K == 2 ? fx_stateless_kernel<2> : fx_stateless_kernel<1>);
+SLKernelFn pick_sl_kernel(int K, bool tram) {
+    if (tram) return K == 4 ? fx_stateless_kernel<4, true> : (K == 2 ? fx_stateless_kernel<2, true> : fx_stateless_kernel<1, true>);
+    return K == 4 ? fx_stateless_kernel<4, false> : (K == 2 ? fx_stateless_kernel<2, false> : fx_stateless_kernel<1, false>);
 }
 
 // Geometry for the stateless kernel: all the parallelism a launch needs comes from cutting the time
@@ -651,6 +708,8 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     };
     int K = 4;
     while (K > 1 && !aligned(K)) K >>= 1;
+    if (h->sl_serial)                        // one time segment: the warps come from the instances alone — keep about four per SM at least
+        while (K > 1 && (long)N / K / 32 < 4L * h->num_sms) K >>= 1;
     if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
     int B = h->tune_B ? h->tune_B : 128;
     while (B > 32 && (N / K + B - 1) / B * B >= 2 * (N / K) && N / K <= B / 2) B >>= 1;      // tiny N: do not launch mostly-idle blocks
@@ -668,7 +727,7 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     L.smem = sl_smem_bytes(h, B, K, M);
     L.grid_x = (N / K + B - 1) / B;
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_sl_kernel(K), B, L.smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_sl_kernel(K, h->sl_tram), B, L.smem);
     occ = std::max(occ, 1);
     // half a wave per launch: with programmatic dependent launch two consecutive launches share the SMs, and
     // fewer, longer segments spend fewer instructions on per-thread start-up
@@ -752,9 +811,21 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
             p.acc_writer = h->acc_writer ? 1 : 0;
             p.ccr_live = h->sl_ccr_live ? 1 : 0;
+            p.ptrs = h->d_ptrs; p.itram = h->d_itram; p.xtram = h->d_xtram; p.itram_size = h->itram_size; p.xtram_size = h->xtram_size;
+            p.has_tram = h->sl_tram ? 1 : 0; p.n_tr = h->sl_n_tr;
+            p.tr_on[0] = p.tr_on[1] = 0;
+            for (int q = 0; q < h->sl_n_tr; ++q) {
+                const fx8010_gpu::TramStream& t = h->sl_tr[q];
+                const int x = t.isx;                             // the kernel indexes streams by TRAM: 0 = iTRAM, 1 = xTRAM
+                p.tr_on[x] = 1;
+                p.tr_stage[x] = sl_word(h, t.reg, L.B, L.K, L.M) & SL_OFF_MASK;
+                p.tr_y[x] = sl_word(h, t.yreg, L.B, L.K, L.M) & SL_OFF_MASK;
+                p.tr_wy[x] = t.w_yreg >= 0 ? (sl_word(h, t.w_yreg, L.B, L.K, L.M) & SL_OFF_MASK) : 0xffffffffu;
+                p.tr_wfirst[x] = t.w_first;
+            }
             p.pdl_late_wait = late_wait;
-            SLKernelFn fn = pick_sl_kernel(L.K);
-            bool& attr = h->sl_attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)];
+            SLKernelFn fn = pick_sl_kernel(L.K, h->sl_tram);
+            bool& attr = h->sl_attr_set[h->sl_tram ? 1 : 0][L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)];
             if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
             FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
         } else {
@@ -848,6 +919,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     if (getenv("FX8010_NO_STATELESS")) h->use_sl = 0;
     if (getenv("FX8010_NO_SHORT")) h->use_short = 0;
     if (getenv("FX8010_NO_CARRY")) h->use_carry = 0;
+    if (getenv("FX8010_NO_TRAM_IM")) h->use_tram_im = 0;
     h->tune_M = env_int("FX8010_TUNE_M");
     h->tune_chunk = env_int("FX8010_TUNE_CHUNK");
     if (h->tune_chunk & (h->tune_chunk - 1) || h->tune_chunk > MAX_CHUNK) h->tune_chunk = 0;

@@ -53,6 +53,16 @@ struct SLParams {
     int smem_tab_id[MAX_SMEM_TABLES];
     int acc_writer;             // some instruction sets the accumulator (else it keeps its value)
     int ccr_live;               // somebody reads `ccr`: every setCCR is materialised per sample (else only the call's last one)
+    // TRAM (programs with IDELAY/XDELAY): pointers, rings, and the READ streams prefetched into stage rows
+    int32_t* ptrs;              // [4][N]  iw, ir, xw, xr
+    float* itram; float* xtram; // [size][N]
+    int itram_size, xtram_size;
+    int has_tram, n_tr;
+    int tr_on[2];               // TRAM t (0 = iTRAM, 1 = xTRAM) has a READ stream
+    uint32_t tr_stage[2];       // byte offset of the stream's stage rows [2 buffers][M]
+    uint32_t tr_y[2];           // byte offset of the row holding the READ's offset operand
+    uint32_t tr_wy[2];          // ... of the same TRAM's WRITE (0xffffffff: no WRITE instruction)
+    int tr_wfirst[2];           // the WRITE comes before the READ in program order
     int pdl_late_wait;
 };
 
@@ -71,6 +81,11 @@ template <int K> struct SLCtx {
     uint32_t boff;                  // byte offset of the current input-stage buffer
     unsigned int flags;
     Vec<K> acc_last;
+    // TRAM
+    int32_t tp[4][K];               // iw, ir, xw, xr of this thread's instances
+    bool tram_fast;                 // the READ streams are prefetched (else: synchronous reads, one sample at a time)
+    float* ring[2];                 // iTRAM / xTRAM at this thread's first instance
+    int rsize[2];
 };
 
 // Runs the whole program for samples [m_lo, m_hi) of the current batch, instruction-major.
@@ -97,7 +112,7 @@ struct SLInstr {
 // The sample loop is software-pipelined over TWO operand register sets (unrolled by two, no register moves): the
 // operands of sample m + 1 go in flight before the arithmetic of sample m, operands whose row does not change are
 // read once, and a carried operand is written straight into the next set — a recurrence's chain holds arithmetic only.
-template <int K, bool FINAL, bool CCRV, int CM>
+template <int K, bool FINAL, bool CCRV, int CM, bool TRAM>
 __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr& I) {
     const uint64_t Nl = cx.Nl;
     const uint32_t w0 = I.w0, uop = I.uop;
@@ -211,6 +226,58 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
             }
             SL_EACH { accv[k] = r[k]; })
         break; }
+        // TRAM READ (:1190-1193 / :1202-1205, readSmallDelay :934-956) and WRITE (:1195-1198 / :1207-1210,
+        // writeSmallDelay :909-917); T = 0 iTRAM, 1 xTRAM (a constant, so that the pointers stay in registers).
+        // The final-state pass re-runs arithmetic only: TRAM state is already final.
+#define SL_TRAM_READ(T)                                                                                          \
+        if (TRAM && !FINAL) {                                                                                    \
+            const int size = cx.rsize[T];                                                                        \
+            if (cx.tram_fast) {    /* the rows were prefetched with the batch: only the pointer moves */         \
+                SL_EACH { int32_t& rp = cx.tp[2 * T + 1][k]; rp += n_m; rp -= (rp >= size) ? size : 0; }         \
+            } else {                                                                                             \
+                const float* const ring = cx.ring[T];                                                            \
+                for (int m = 0; m < n_m; ++m, I.qa += I.sa) {                                                    \
+                    Vec<K> v;                                                                                    \
+                    SL_EACH {                                                                                    \
+                        int32_t& rp = cx.tp[2 * T + 1][k];                                                       \
+                        const int pos = min(max(cvt_x86(Y0[k]), 0), size - 1);                                   \
+                        int idx = rp - pos;                                                                      \
+                        idx += (idx < 0) ? size : 0;   /* rule U1: mathematical modulo */                        \
+                        rp = (rp + 1 == size) ? 0 : rp + 1;                                                      \
+                        v[k] = ring[(uint64_t)idx * Nl + k];                                                     \
+                    }                                                                                            \
+                    sts<K>(I.qa, v);                                                                             \
+                }                                                                                                \
+            }                                                                                                    \
+        }
+#define SL_TRAM_WRITE(T)                                                                                         \
+        if (TRAM && !FINAL) {                                                                                    \
+            const int size = cx.rsize[T];                                                                        \
+            float* const ring = cx.ring[T];                                                                      \
+            int pos[K];                                                                                          \
+            bool same = true;                                                                                    \
+            SL_EACH { pos[k] = min(max(cvt_x86(Y0[k]), 0), size - 1); same = same && (cx.tp[2 * T][k] + pos[k] == cx.tp[2 * T][0] + pos[0]); } \
+            Vec<K> a = A0;                                                                                       \
+            for (int m = 0; m < n_m; ++m) {                                                                      \
+                Vec<K> an = a;                                                                                   \
+                if (la && m + 1 < n_m) { I.qa += I.sa; an = lds<K>(I.qa); }                                      \
+                int widx[K];                                                                                     \
+                SL_EACH {                                                                                        \
+                    int32_t& wp = cx.tp[2 * T][k];                                                               \
+                    widx[k] = wp + pos[k];   /* not wrapped in the reference: slots at or beyond the ring are never read back -> dropped */ \
+                    wp = (wp + 1 == size) ? 0 : wp + 1;                                                          \
+                }                                                                                                \
+                if (K > 1 && same) { if (widx[0] < size && cx.valid) vstore<K>(ring + (uint64_t)widx[0] * Nl, a); } \
+                else { SL_EACH { if (widx[k] < size && cx.valid) ring[(uint64_t)widx[k] * Nl + k] = a[k]; } }    \
+                a = an;                                                                                          \
+            }                                                                                                    \
+        }
+    case U_IREAD: SL_TRAM_READ(0) break;
+    case U_XREAD: SL_TRAM_READ(1) break;
+    case U_IWRITE: SL_TRAM_WRITE(0) break;
+    case U_XWRITE: SL_TRAM_WRITE(1) break;
+#undef SL_TRAM_READ
+#undef SL_TRAM_WRITE
     default: break;      // nothing else can appear in this kernel's encoded stream
     }
 #undef SL_EACH
@@ -220,7 +287,7 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
 }
 
 // Runs the whole program for samples [m_lo, m_hi) of the current batch, instruction-major.
-template <int K, bool FINAL, bool CCRV>
+template <int K, bool FINAL, bool CCRV, bool TRAM>
 __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const int m_lo, const int m_hi) {
     uint4 nA = cx.prog[0], nB = cx.prog[1];
     const int n_exec = cx.n_exec;
@@ -244,16 +311,16 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
         I.st_c = FINAL || (CCRV && (w0 & F_CCR));
         I.st_o = (w0 & F_OUT_DIRECT) && cx.valid;
         I.qo = cx.out_b + (size_t)(w0 >> 24) * cx.out_cstride + (size_t)m_lo * cx.Nl;
-        if (FINAL || CCRV) sl_run<K, FINAL, CCRV, 2>(p, cx, I);          // cold paths: one general copy
-        else if (cbits == 0u) sl_run<K, false, false, 0>(p, cx, I);
-        else if (cbits == 1u) sl_run<K, false, false, 1>(p, cx, I);
-        else sl_run<K, false, false, 2>(p, cx, I);
+        if (FINAL || CCRV) sl_run<K, FINAL, CCRV, 2, TRAM>(p, cx, I);          // cold paths: one general copy
+        else if (cbits == 0u) sl_run<K, false, false, 0, TRAM>(p, cx, I);
+        else if (cbits == 1u) sl_run<K, false, false, 1, TRAM>(p, cx, I);
+        else sl_run<K, false, false, 2, TRAM>(p, cx, I);
 #undef SL_ADDR
 #undef SL_ADDR_C
     }
 }
 
-template <int K>
+template <int K, bool TRAM>
 __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int B = blockDim.x;
@@ -291,9 +358,8 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
                 for (int m = 0; m < M && m < n; ++m) cp_async<4 * K>(at(base + (uint32_t)m * row_bytes), g + (size_t)m * N);
             }
         }
-        cp_async_commit();
     };
-    fetch_batch(s_begin, 0);
+    fetch_batch(s_begin, 0);                            // (its group is committed after the TRAM streams joined it, below)
 
     for (int t = 0; t < p.n_smem_tabs; ++t) {
         const TableEntry* src = p.tabs + (size_t)p.smem_tab_id[t] * FX8010_TABLE_ENTRIES;
@@ -326,15 +392,91 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
     cx.out_b = p.out + (size_t)s_begin * N + inst0;
     const size_t out_step = (size_t)M * N;
 
+    // ---- TRAM: pointers, and the READ streams (source/FX8010.cpp:934-967) prefetched like input channels ----
+    // Every executed READ / WRITE moves its pointer by one, so with one READ and one WRITE per TRAM the slot a READ
+    // fetches was written a constant number of sample periods earlier (`dist`).  A batch's READs are fetched while the
+    // previous batch is still being computed: that is the same data as long as dist >= 2 M.
+    cx.tram_fast = true;
+    cx.ring[0] = p.itram + inst0; cx.ring[1] = p.xtram + inst0; cx.rsize[0] = p.itram_size; cx.rsize[1] = p.xtram_size;
+    int tr_next[2][K];                                  // ring slot of the stream's next sample to fetch
+    bool tr_same[2] = {true, true};
+    if (TRAM && p.has_tram) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            cx.tp[0][k] = p.ptrs[inst0 + k]; cx.tp[1][k] = p.ptrs[N + inst0 + k];
+            cx.tp[2][k] = p.ptrs[2 * N + inst0 + k]; cx.tp[3][k] = p.ptrs[3 * N + inst0 + k];
+        }
+        bool safe = true;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (!p.tr_on[t]) continue;
+            const int size = cx.rsize[t];
+            const Vec<K> yv = lds<K>(cx.col_s + p.tr_y[t]);
+            Vec<K> wv = yv;
+            const bool has_w = p.tr_wy[t] != 0xffffffffu;
+            if (has_w) wv = lds<K>(cx.col_s + p.tr_wy[t]);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int pos = min(max(cvt_x86(yv[k]), 0), size - 1);
+                int nx = cx.tp[2 * t + 1][k] - pos;
+                nx += (nx < 0) ? size : 0;
+                tr_next[t][k] = nx;
+                tr_same[t] = tr_same[t] && (nx == tr_next[t][0]);
+                if (has_w) {
+                    const int wpos = min(max(cvt_x86(wv[k]), 0), size - 1);
+                    int d = (cx.tp[2 * t][k] + wpos - nx) % size;      // write slot minus read slot of the same sample
+                    d += (d < 0) ? size : 0;
+                    const int dist = (d == 0 && !p.tr_wfirst[t]) ? size : d;
+                    safe = safe && (dist > 2 * M);
+                }
+            }
+        }
+        cx.tram_fast = __all_sync(0xffffffffu, safe);
+    }
+    auto fetch_tram = [&](int s0, uint32_t boff) {
+        if (TRAM && p.n_tr > 0 && cx.tram_fast && s0 < s_end) {
+            const int nm = min(M, s_end - s0);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                if (!p.tr_on[t]) continue;
+                const int size = cx.rsize[t];
+                const float* const ring = cx.ring[t];
+                unsigned char* d = reinterpret_cast<unsigned char*>(at(p.tr_stage[t] + boff));
+                for (int m = 0; m < nm; ++m, d += row_bytes) {
+                    if (K > 1 && tr_same[t]) {
+                        int idx = tr_next[t][0] + m; idx -= (idx >= size) ? size : 0;
+                        cp_async<4 * K>(d, ring + (size_t)idx * N);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            int idx = tr_next[t][k] + m; idx -= (idx >= size) ? size : 0;
+                            cp_async<4>(d + 4 * k, ring + (size_t)idx * N + k);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) { tr_next[t][k] += nm; tr_next[t][k] -= (tr_next[t][k] >= size) ? size : 0; }
+            }
+        }
+    };
+    fetch_tram(s_begin, 0);
+    cp_async_commit();
+
     for (int s0 = s_begin; s0 < s_end; s0 += M, cx.out_b += out_step) {
         const int mb = min(M, s_end - s0);
         fetch_batch(s0 + M, cx.boff ^ buf_bytes);
+        fetch_tram(s0 + M, cx.boff ^ buf_bytes);
+        cp_async_commit();
         cp_async_wait<1>();
-        if (p.ccr_live) sl_exec<K, false, true>(p, cx, 0, mb); else sl_exec<K, false, false>(p, cx, 0, mb);
+        const int step = (!TRAM || cx.tram_fast) ? mb : 1;         // a delay shorter than two batches: the same code, one sample at a time
+        for (int m0 = 0; m0 < mb; m0 += step) {
+            if (p.ccr_live) sl_exec<K, false, true, TRAM>(p, cx, m0, m0 + step);
+            else sl_exec<K, false, false, TRAM>(p, cx, m0, m0 + step);
+        }
         if (s0 + mb == p.n_samples && valid) {
             // This thread owns the call's last sample: leave the final state behind (cold path).
             if (p.pdl_late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // state writes follow
-            sl_exec<K, true, true>(p, cx, mb - 1, mb);
+            sl_exec<K, true, true, TRAM>(p, cx, mb - 1, mb);
             for (int i = 0; i < p.n_wb; ++i) {
                 const uint2 e = p.wb_list[i];
                 const unsigned char* src = col + (e.x & SL_OFF_MASK) + ((e.x & SL_BUF) ? cx.boff : 0u) + (uint32_t)(mb - 1) * SL_STRIDE(e.x);
@@ -343,6 +485,10 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 if (p.acc_writer) p.acc[inst0 + k] = (double)cx.acc_last[k];
+                if (TRAM && p.has_tram) {
+                    p.ptrs[inst0 + k] = cx.tp[0][k]; p.ptrs[N + inst0 + k] = cx.tp[1][k];
+                    p.ptrs[2 * N + inst0 + k] = cx.tp[2][k]; p.ptrs[3 * N + inst0 + k] = cx.tp[3][k];
+                }
                 p.counts[inst0 + k] += (unsigned long long)p.n_samples * (unsigned long long)p.n_instrs;
             }
         }

@@ -343,6 +343,52 @@ def test_carried_recurrences(fx, po, name, mode, monkeypatch):
         assert not (info.kernel_variant & (8 | 32))
 
 
+# TRAM programs in the instruction-major kernel: READ streams prefetched a batch ahead when the delay is longer than
+# two batches, otherwise the same code one sample at a time.
+def _tram_prog(size, order="rw", roff="0", woff="0", x=False, two=None):
+    d, sz = ("xdelay", "xtramsize") if x else ("idelay", "itramsize")
+    if order == "rw":     # feedback delay line (cfg3): read, mix, write back
+        body = f"{d} read, rd, at, {roff}\nmacs a, in_l, rd, 0.5\n{d} write, a, at, {woff}\n"
+    else:                 # tap: write the input, read it back delayed (negative ring indices follow rule U1)
+        body = f"{d} write, in_l, at, {woff}\n{d} read, rd, at, {roff}\nmacs a, rd, 0.5, 0.5\n"
+    decl2, body2 = "", ""
+    if two:               # the other TRAM as well: (write offset, read offset)
+        decl2 = "xtramsize 300 \n"
+        body2 = f"xdelay write, in_l, at, {two[0]}\nxdelay read, rx, at, {two[1]}\nmacs a2, rx, 0.5, 0.5\n"
+    return ("static a\nstatic a2\nstatic rd\nstatic rx\ncontrol dly = 5\ninput in_l 0\noutput out_l 0\n"
+            f"{sz} {size} \n{decl2}{body}{body2}macs out_l, in_l, rd, 0.5\nend")
+
+
+TRAM_CASES = {
+    "s3": dict(size=3), "s40": dict(size=40), "s64": dict(size=64), "s65": dict(size=65), "s66": dict(size=66), "s100": dict(size=100),
+    "s1000": dict(size=1000), "wr_off": dict(size=500, order="wr", roff="200", woff="3"),
+    "wr_short": dict(size=500, order="wr", roff="17", woff="0"), "wr_zero": dict(size=90, order="wr"),
+    "wr_wrap": dict(size=300, order="wr", roff="5", woff="290"),
+    "ctl_off": dict(size=400, order="wr", roff="dly"), "xdelay": dict(size=2000, x=True),
+    "two_slow": dict(size=700, two=(7, 2)), "two_fast": dict(size=700, two=(0, 150)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(TRAM_CASES))
+@pytest.mark.parametrize("mode", ["auto", "K4", "K2M8", "no_im"])
+def test_tram_instruction_major(fx, po, name, mode, monkeypatch):
+    if mode == "K4":
+        monkeypatch.setenv("FX8010_TUNE_K", "4")
+    elif mode == "K2M8":
+        monkeypatch.setenv("FX8010_TUNE_K", "2")
+        monkeypatch.setenv("FX8010_TUNE_M", "8")
+    elif mode == "no_im":
+        monkeypatch.setenv("FX8010_NO_TRAM_IM", "1")
+    rng = np.random.default_rng(31)
+    n = 136
+    text = _tram_prog(**TRAM_CASES[name])
+    ctl = {"dly": rng.integers(70, 390, n).astype(np.float32)} if name == "ctl_off" else None
+    x = progs.impulse_noise(n, 700, rng)
+    info = run_case(fx, po, text, n, [1, 150, 33, 64, 2, 450], rng, controls=ctl,
+                    stimulus=lambda a, k: x[a:a + k].reshape(1, k, n), what=f"tram {name} {mode}")
+    assert bool(info.kernel_variant & 8) == (mode != "no_im"), "wrong kernel took the program"
+
+
 def test_input_channel_quirk_takes_generic_kernel(fx, po):
     """X/Y INPUT operands read A's channel (reference :1057-1060): such a program is stateless but must not
     use the stage-aliasing kernel."""
