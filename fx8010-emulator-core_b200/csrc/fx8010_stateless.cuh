@@ -468,10 +468,15 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
         fetch_tram(s0 + M, cx.boff ^ buf_bytes);
         cp_async_commit();
         cp_async_wait<1>();
-        const int step = (!TRAM || cx.tram_fast) ? mb : 1;         // a delay shorter than two batches: the same code, one sample at a time
-        for (int m0 = 0; m0 < mb; m0 += step) {
-            if (p.ccr_live) sl_exec<K, false, true, TRAM>(p, cx, m0, m0 + step);
-            else sl_exec<K, false, false, TRAM>(p, cx, m0, m0 + step);
+        if (!TRAM) {
+            if (p.ccr_live) sl_exec<K, false, true, TRAM>(p, cx, 0, mb);
+            else sl_exec<K, false, false, TRAM>(p, cx, 0, mb);
+        } else {                                        // a TRAM delay shorter than two batches: the same code, one sample at a time
+            const int step = cx.tram_fast ? mb : 1;     // (one call site: the bulk code is instantiated once)
+            for (int m0 = 0; m0 < mb; m0 += step) {
+                if (p.ccr_live) sl_exec<K, false, true, TRAM>(p, cx, m0, m0 + step);
+                else sl_exec<K, false, false, TRAM>(p, cx, m0, m0 + step);
+            }
         }
         if (s0 + mb == p.n_samples && valid) {
             // This thread owns the call's last sample: leave the final state behind (cold path).
