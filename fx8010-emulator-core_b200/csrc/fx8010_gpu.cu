@@ -15,11 +15,22 @@
 #include <string>
 #include <vector>
 
-#include "fx8010_kernel.cuh"
-#include "fx8010_stateless.cuh"
-#include "fx8010_short.cuh"
+#include "fx8010_families.h"
 
 using namespace fxk;
+
+namespace fxk {
+SLKernelFn sl_kernel(int K, bool tram) { return K == 4 ? sl_kernel_4(tram) : (K == 2 ? sl_kernel_2(tram) : sl_kernel_1(tram)); }
+cudaError_t upload_program(Family f, const uint4* src, size_t bytes, int slot, cudaStream_t st) {
+    switch (f) {
+    case FAM_GENERIC: return upload_generic(src, bytes, slot, st);
+    case FAM_SHORT: return upload_short(src, bytes, slot, st);
+    case FAM_SL1: return upload_sl1(src, bytes, slot, st);
+    case FAM_SL2: return upload_sl2(src, bytes, slot, st);
+    default: return upload_sl4(src, bytes, slot, st);
+    }
+}
+}  // namespace fxk
 
 namespace {
 
@@ -62,6 +73,7 @@ struct fx8010_gpu {
     std::vector<int> tab_of;                     // per instruction: literal table id or -1
     uint4* h_prog = nullptr;                     // pinned, SLOT_WORDS words
     int enc_K = 0, enc_B = 0, enc_chunk = 0;     // geometry the uploaded encoding was made for
+    int enc_family = -1;                         // kernel family whose constant memory holds it
     PlanKey plan_key; Launch plan = {};          // last launch plan (reused while nothing relevant changes)
     bool attr_set[3][2][2][2] = {};
     // previous launch on last_stream: the buffers it writes / reads (for the PDL overlap decision)
@@ -85,7 +97,7 @@ struct fx8010_gpu {
     std::vector<uint8_t> sl_carried_reg;         // per register: some instruction carries it from sample to sample
     int use_carry = 1;
     bool short_ok = false;                       // SKIP-free, nobody reads ccr, no noise/MACMV, every channel written: fx_short_kernel when short enough
-    bool short_attr_set[3][2][SH_MAX_NI] = {};
+    bool short_attr_set[3][2][SH_MAX_NI_HOST] = {};
     int use_sl = 1, tune_M = 0, use_short = 1, tune_chunk = 0;
     std::vector<int> sl_class, sl_index;         // per register: RowClass and index inside its class
     int sl_n_ro = 0, sl_n_wo = 0, sl_n_rw = 0;
@@ -596,17 +608,7 @@ void free_state(fx8010_gpu* h) {
     h->d_itram = nullptr; h->d_xtram = nullptr; h->d_counts = nullptr; h->d_wb = nullptr; h->d_latch_ch = nullptr; h->d_reg_map = nullptr; h->d_load_rows = nullptr; h->d_sl_load = nullptr; h->d_sl_wb = nullptr;
 }
 
-typedef void (*KernelFn)(const Params);
-template <int K, int NI> KernelFn pick_kernel(bool skip, bool ext) {
-    if (skip) return ext ? fx_interp_kernel<K, true, true, NI> : fx_interp_kernel<K, true, false, NI>;
-    return ext ? fx_interp_kernel<K, false, true, NI> : fx_interp_kernel<K, false, false, NI>;
-}
-template <int K> KernelFn pick_kernel(bool skip, bool ext, bool shortp) {
-    return shortp ? pick_kernel<K, SHORT_NI>(skip, ext) : pick_kernel<K, 0>(skip, ext);
-}
-KernelFn pick_kernel(int K, bool skip, bool ext, bool shortp) {
-    return K == 4 ? pick_kernel<4>(skip, ext, shortp) : (K == 2 ? pick_kernel<2>(skip, ext, shortp) : pick_kernel<1>(skip, ext, shortp));
-}
+KernelFn pick_kernel(int K, bool skip, bool ext, bool shortp) { return generic_kernel(K, skip, ext, shortp); }
 // Encoded length of the program for the generic kernel (END/NOP are dropped when there is no SKIP).
 int encoded_length(const fx8010_gpu* h) {
     int e = 0;
@@ -621,20 +623,9 @@ bool is_short(const fx8010_gpu* h) { return h->use_short && encoded_length(h) <=
 // fx_short_kernel<K, EXT, NI>: NI = the exact number of executed instructions
 bool use_short_kernel(const fx8010_gpu* h) {
     const int e = encoded_length(h);
-    return h->use_short && h->short_ok && !h->trace_mode && e >= 1 && e <= SH_MAX_NI;
+    return h->use_short && h->short_ok && !h->trace_mode && e >= 1 && e <= SH_MAX_NI_HOST;
 }
-template <int K, bool EXT> KernelFn pick_short_kernel(int ni) {
-    switch (ni) {
-    case 1: return fx_short_kernel<K, EXT, 1>;
-    case 2: return fx_short_kernel<K, EXT, 2>;
-    case 3: return fx_short_kernel<K, EXT, 3>;
-    default: return fx_short_kernel<K, EXT, 4>;
-    }
-}
-template <int K> KernelFn pick_short_kernel(bool ext, int ni) { return ext ? pick_short_kernel<K, true>(ni) : pick_short_kernel<K, false>(ni); }
-KernelFn pick_short_kernel(int K, bool ext, int ni) {
-    return K == 4 ? pick_short_kernel<4>(ext, ni) : (K == 2 ? pick_short_kernel<2>(ext, ni) : pick_short_kernel<1>(ext, ni));
-}
+KernelFn pick_short_kernel(int K, bool ext, int ni) { return short_kernel(K, ext, ni); }
 
 // Geometry of one launch: contexts per thread, block size, time split.
 int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_cs, size_t out_cs, int n_samples, Launch& L) {
@@ -692,11 +683,7 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     return FX8010_OK;
 }
 
-typedef void (*SLKernelFn)(const SLParams);
-SLKernelFn pick_sl_kernel(int K, bool tram) {
-    if (tram) return K == 4 ? fx_stateless_kernel<4, true> : (K == 2 ? fx_stateless_kernel<2, true> : fx_stateless_kernel<1, true>);
-    return K == 4 ? fx_stateless_kernel<4, false> : (K == 2 ? fx_stateless_kernel<2, false> : fx_stateless_kernel<1, false>);
-}
+SLKernelFn pick_sl_kernel(int K, bool tram) { return sl_kernel(K, tram); }
 
 // Geometry for the stateless kernel: all the parallelism a launch needs comes from cutting the time
 // axis, so K is as wide as alignment allows and the segment count fills exactly one wave.
@@ -762,13 +749,15 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             if (rc) return rc;
             h->plan = L; h->plan_key.ns = ns; h->plan_key.align = align;
         }
-        if (h->encode_dirty || h->enc_K != L.K || h->enc_B != L.B || h->sl_M != L.M || (L.M == 0 && h->enc_chunk != L.chunk)) {
+        // the kernel family that will run this launch (each keeps its own constant-memory copy of the program)
+        const Family fam = L.M > 0 ? sl_family(L.K) : ((use_short_kernel(h)) ? FAM_SHORT : FAM_GENERIC);
+        if (h->encode_dirty || h->enc_K != L.K || h->enc_B != L.B || h->sl_M != L.M || (L.M == 0 && h->enc_chunk != L.chunk) || h->enc_family != (int)fam) {
             // the previous upload must have left the pinned buffer before it is rewritten
             FX_CUDA(h, cudaStreamSynchronize(st));
             if (h->last_stream && h->last_stream != st) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));
             if (L.M > 0) encode_stateless(h, L.K, L.B, L.M); else encode(h, L.K, L.B, L.chunk);
-            FX_CUDA(h, cudaMemcpyToSymbolAsync(c_prog, h->h_prog, sizeof(uint4) * 2 * (h->n_exec + 1),
-                                               sizeof(uint4) * (size_t)SLOT_WORDS * h->slot, cudaMemcpyHostToDevice, st));
+            FX_CUDA(h, upload_program(fam, h->h_prog, sizeof(uint4) * 2 * (h->n_exec + 1), h->slot, st));
+            h->enc_family = (int)fam;
             if (L.M > 0) {
                 FX_CUDA(h, cudaMemcpyAsync(h->d_sl_load, h->sl_load.data(), sizeof(uint2) * h->sl_load.size(), cudaMemcpyHostToDevice, st));
                 FX_CUDA(h, cudaMemcpyAsync(h->d_sl_wb, h->sl_wb.data(), sizeof(uint2) * h->sl_wb.size(), cudaMemcpyHostToDevice, st));

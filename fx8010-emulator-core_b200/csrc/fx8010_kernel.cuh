@@ -53,7 +53,7 @@ constexpr uint32_t F_PRE_ANY = F_PRE_A | F_PRE_X | F_PRE_Y;
 constexpr int MAX_INSTR = FX8010_MAX_INSTRUCTIONS;
 constexpr int PROG_SLOTS = 2;            // live programs per device (one slot per handle)
 constexpr int SLOT_WORDS = 2 * (MAX_INSTR + 1);
-__constant__ uint4 c_prog[PROG_SLOTS][SLOT_WORDS];
+static __constant__ uint4 c_prog[PROG_SLOTS][SLOT_WORDS];   // one copy per kernel translation unit (see fx8010_families.h)
 
 constexpr int MAX_CHUNK = 64;             // input stage: two buffers of `chunk` samples per channel; while one is consumed the
                                          // other is in flight (a recurrence needs ~30 sample rows in flight per thread to
@@ -189,7 +189,7 @@ __device__ __forceinline__ int table_index_inrange(double xd) {
     return __double2int_rz(__dmul_rn(__dadd_rn(xd, 1.0), 31.5));
 }
 // Outside [-1, 1] (rule U6) the reference's index is clamped; cvttsd2si overflow / NaN -> INT_MIN -> 0.
-__device__ __noinline__ int table_index_wild(float a) {
+static __device__ __noinline__ int table_index_wild(float a) {
     const double q = __dmul_rn(__dadd_rn((double)a, 1.0), 31.5);
     int i = __double2int_rz(q);
     i = min(max(i, 0), FX8010_TABLE_ENTRIES - 1);
@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                     float* const pa = at(wA.z);
                     float* const px = at(wA.w);
                     float* const py = at(wB.x);
+                    if (w0 & (F_PRE_ANY | F_NOISE)) {                 // the less common pre-work behind one test
                     if (w0 & F_PRE_ANY) {                             // :1053-1061
                         Vec<K> v;
                         if (has_in) v = vload<K>(at(wB.z + stage_s));
@@ -422,27 +423,28 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                                 g2[k] += g1[k];
                             }
                     }
+                    }
+                    // All three operands are fetched up front (every operand offset names a valid row): the loads are
+                    // in flight while the opcode is dispatched.
+                    const Vec<K> a = vload<K>(pa), x = vload<K>(px), y = vload<K>(py);
                     Vec<K> r;
                     bool writes_r = true;
-#define FX_LOAD_A const Vec<K> a = vload<K>(pa)
-#define FX_LOAD_X const Vec<K> x = vload<K>(px)
-#define FX_LOAD_Y const Vec<K> y = vload<K>(py)
 #define FX_EACH _Pragma("unroll") for (int k = 0; k < K; ++k)
 #define FX_ACC(val) { if (act[k]) { acc_f[k] = (val); acc_is_f[k] = true; } }
                     switch (uop) {
-                    case U_MACS: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;   // :1077-1085 (MACINTS :1095-1103 is identical)
+                    case U_MACS: {   // :1077-1085 (MACINTS :1095-1103 is identical)
                         FX_EACH { const float t = __fadd_rn(a[k], __fmul_rn(x[k], y[k])); FX_ACC(t); r[k] = sat1(t); } break; }
-                    case U_MACSN: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;  // :1086-1094
+                    case U_MACSN: {  // :1086-1094
                         FX_EACH { const float t = __fsub_rn(a[k], __fmul_rn(x[k], y[k])); FX_ACC(t); r[k] = sat1(t); } break; }
-                    case U_ACC3: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;   // :1104-1112
+                    case U_ACC3: {   // :1104-1112
                         FX_EACH { const float t = __fadd_rn(__fadd_rn(a[k], x[k]), y[k]); FX_ACC(t); r[k] = sat1(t); } break; }
-                    case U_MACW: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;   // :1126-1131
+                    case U_MACW: {   // :1126-1131
                         FX_EACH { r[k] = __fadd_rn(a[k], wrap1(__fmul_rn(x[k], y[k]))); FX_ACC(r[k]); } break; }
-                    case U_MACWN: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;  // :1132-1137
+                    case U_MACWN: {  // :1132-1137
                         FX_EACH { r[k] = __fsub_rn(a[k], wrap1(__fmul_rn(x[k], y[k]))); FX_ACC(r[k]); } break; }
-                    case U_MACINTW: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y; // :1138-1143
+                    case U_MACINTW: { // :1138-1143
                         FX_EACH { r[k] = wrap1(__fadd_rn(a[k], __fmul_rn(x[k], y[k]))); FX_ACC(r[k]); } break; }
-                    case U_MACMV: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;  // :1144-1149
+                    case U_MACMV: {  // :1144-1149
                         FX_EACH {
                             if (EXT && act[k]) {
                                 const double base = acc_is_f[k] ? (double)acc_f[k] : acc_d[k];
@@ -451,20 +453,20 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                             }
                             r[k] = a[k];
                         } break; }
-                    case U_ANDXOR: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y; // :1150-1154 (accumulator untouched)
+                    case U_ANDXOR: { // :1150-1154 (accumulator untouched)
                         FX_EACH { r[k] = __int2float_rn(logic_ops(a[k], x[k], y[k])); } break; }
-                    case U_TSTNEG: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y; // :1155-1162
+                    case U_TSTNEG: { // :1155-1162
                         FX_EACH {
                             const int32_t q = cvt_x86(__fmul_rn(x[k], 2147483648.0f));
                             r[k] = (a[k] >= y[k]) ? x[k] : __fmul_rn(__int2float_rn(~q), 4.656612873077392578125e-10f);
                             FX_ACC(r[k]);
                         } break; }
-                    case U_LIMIT: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y;  // :1163-1168
+                    case U_LIMIT: {  // :1163-1168
                         FX_EACH { r[k] = (a[k] >= y[k]) ? x[k] : y[k]; FX_ACC(r[k]); } break; }
-                    case U_LIMITN: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y; // :1169-1174
+                    case U_LIMITN: { // :1169-1174
                         FX_EACH { r[k] = (a[k] < y[k]) ? x[k] : y[k]; FX_ACC(r[k]); } break; }
                     case U_LOG:                                       // :1113-1119
-                    case U_EXP: { FX_LOAD_A;                          // :1120-1125, linearInterpolate :283-296
+                    case U_EXP: {                          // :1120-1125, linearInterpolate :283-296
                         int idx[K];
                         bool wild = false;
                         FX_EACH { wild |= !(fabsf(a[k]) <= 1.0f); }
@@ -482,8 +484,6 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                                 r[k] = table_finish((double)a[k], idx[k], e.y1, e.slope); FX_ACC(r[k]);
                             }
                         } else {
-                            Vec<K> x;
-                            if (!(w0 & F_TAB_IMM)) x = vload<K>(px);
                             FX_EACH {
                                 int tsel;
                                 if (w0 & F_TAB_IMM) tsel = (int)(wB.y >> 24);
@@ -500,17 +500,17 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                             }
                         }
                         break; }
-                    case U_INTERP: { FX_LOAD_A; FX_LOAD_X; FX_LOAD_Y; // :1180-1187
+                    case U_INTERP: { // :1180-1187
                         FX_EACH {
                             const double d = __dadd_rn(__dmul_rn(__dsub_rn(1.0, (double)x[k]), (double)a[k]), (double)__fmul_rn(x[k], y[k]));
                             const float t = __double2float_rn(d); FX_ACC(t); r[k] = sat1(t);
                         } break; }
                     case U_SKIP:                                      // :1175-1179
-                        if (SKIP) { FX_LOAD_X; FX_LOAD_Y; const Vec<K> c = vload<K>(at(0));
+                        if (SKIP) { const Vec<K> c = vload<K>(at(0));
                             FX_EACH { if (act[k] && __int2float_rn(cvt_x86(x[k])) == c[k]) skip[k] = cvt_x86(y[k]); } }
                         writes_r = false; break;
                     case U_IREAD: case U_XREAD:                       // :1190-1193 / :1202-1205, readSmallDelay :934-956
-                        if (EXT) { FX_LOAD_Y;
+                        if (EXT) { 
                             const bool isx = (uop == U_XREAD);
                             const float* const ring = isx ? p.xtram : p.itram;
                             const int size = isx ? p.xtram_size : p.itram_size;
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                         }
                         writes_r = false; break;
                     case U_IWRITE: case U_XWRITE:                     // :1195-1198 / :1207-1210, writeSmallDelay :909-917
-                        if (EXT) { FX_LOAD_A; FX_LOAD_Y;
+                        if (EXT) { 
                             const bool isx = (uop == U_XWRITE);
                             float* const ring = isx ? p.xtram : p.itram;
                             const int size = isx ? p.xtram_size : p.itram_size;
@@ -552,9 +552,6 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                         writes_r = false; break;
                     default: writes_r = false; break;                 // U_NOP: IDELAY/XDELAY whose R is neither read nor write
                     }
-#undef FX_LOAD_A
-#undef FX_LOAD_X
-#undef FX_LOAD_Y
 #undef FX_ACC
                     if (writes_r) {
                         if (!SKIP) vstore<K>(pr, r);
@@ -642,7 +639,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
 }
 
 // Fills register `reg` of every instance with one value (broadcast setRegisterValue).
-__global__ void fx_fill_kernel(float* dst, float v, int n) {
+static __global__ void fx_fill_kernel(float* dst, float v, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = v;
 }
