@@ -639,7 +639,8 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     const long max_seg = h->stateless ? std::max(1, n_samples / min_seg) : 1;
     const long want_threads = (long)h->num_sms * 512;
     int K = 4;
-    while (K > 1 && (!aligned(K) || ((long)(N / K) * max_seg < want_threads && N / K < h->num_sms * 128))) K >>= 1;
+    // (measured on the 512-instruction cfg5 at 32 768 instances: K = 2 130 ms, K = 1 141 ms, K = 4 177 ms)
+    while (K > 1 && (!aligned(K) || ((long)(N / K) * max_seg < want_threads && N / K < h->num_sms * 64))) K >>= 1;
     if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
     if (h->trace_mode) K = 1;
     // block size: spread small jobs over the SMs, keep several blocks per SM resident
@@ -657,7 +658,7 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     if (h->tune_chunk) chunk = h->tune_chunk;
     auto smem = [&](int b, int k, int ch) { return smem_bytes(nr, C, b, k, h->n_smem_tabs, ch); };
     auto fits = [&](int b, int k) { return smem(b, k, chunk) <= h->smem_optin; };
-    while (B > 32 && ((long)((N / K + B - 1) / B) * max_seg < 2L * h->num_sms || smem(B, K, chunk) > 56 * 1024)) B >>= 1;
+    while (B > 32 && ((long)((N / K + B - 1) / B) * max_seg < 2L * h->num_sms || smem(B, K, chunk) > 80 * 1024)) B >>= 1;
     if (h->tune_B) B = h->tune_B;
     while (!fits(B, K) && chunk > 4) chunk >>= 1;
     while (!fits(B, K) && K > 1) K >>= 1;
@@ -695,8 +696,8 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     };
     int K = 4;
     while (K > 1 && !aligned(K)) K >>= 1;
-    if (h->sl_serial)                        // one time segment: the warps come from the instances alone — keep about four per SM at least
-        while (K > 1 && (long)N / K / 32 < 4L * h->num_sms) K >>= 1;
+    if (h->sl_serial)                        // one time segment: the warps come from the instances alone — keep two per SM at least
+        while (K > 1 && (long)N / K / 32 < 2L * h->num_sms) K >>= 1;   // (cfg4, 65 536 instances: K = 4 147 us, K = 2 158 us, K = 1 155 us)
     if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
     int B = h->tune_B ? h->tune_B : 128;
     while (B > 32 && (N / K + B - 1) / B * B >= 2 * (N / K) && N / K <= B / 2) B >>= 1;      // tiny N: do not launch mostly-idle blocks

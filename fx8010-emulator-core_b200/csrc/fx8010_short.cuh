@@ -31,9 +31,6 @@ constexpr int SH_MAX_NI = 4;
 constexpr uint32_t SH_TAB_SMEM = U_END + 1;   // literal selector, table staged in shared memory
 constexpr uint32_t SH_TAB_IMM = U_END + 2;    // literal selector, table in global memory
 
-// An opaque move: the result cannot be rematerialised from the constant bank inside the sample loop.
-__device__ __forceinline__ uint32_t pin32(uint32_t v) { uint32_t o; asm volatile("mov.b32 %0, %1;" : "=r"(o) : "r"(v)); return o; }
-__device__ __forceinline__ uint64_t pin64(uint64_t v) { uint64_t o; asm volatile("mov.b64 %0, %1;" : "=l"(o) : "l"(v)); return o; }
 
 // Predicated global store of K floats (a branch here would sit on the per-sample chain).
 template <int K> __device__ __forceinline__ void stg_if(uint32_t pred, float* p, const Vec<K>& r) {
