@@ -54,6 +54,10 @@ class CDims(C.Structure):
                                          "xtram_size", "itram_alloc", "xtram_alloc")]
 
 
+class CControlEvent(C.Structure):
+    _fields_ = [("sample", C.c_int32), ("reg_index", C.c_int32), ("broadcast", C.c_int32), ("reserved", C.c_int32), ("values", C.c_void_p)]
+
+
 class CLaunchInfo(C.Structure):
     _fields_ = [("kernel_launches", C.c_ulonglong), ("last_grid", C.c_int32), ("last_block", C.c_int32),
                 ("last_time_split", C.c_int32), ("last_smem_bytes", C.c_int32), ("kernel_variant", C.c_int32)]
@@ -97,6 +101,8 @@ GPU_SYMBOLS = {
     "fx8010_gpu_set_tram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fx8010_gpu_get_runtime_flags": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), C.c_int]),
     "fx8010_gpu_last_error": (C.c_char_p, [C.c_void_p]),
+    "fx8010_gpu_process_batch_events": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "fx8010_gpu_process_batch_planar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fx8010_gpu_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fx8010_gpu_get_launch_info": (C.c_int, [C.c_void_p, C.POINTER(CLaunchInfo)]),
 }
@@ -381,6 +387,19 @@ class Gpu:
 
     def process_device(self, d_in, d_out, n_samples: int, stream=None):
         self._check(self.L.fx8010_gpu_process_batch(self.h, _ptr(d_in), _ptr(d_out), n_samples, stream))
+
+    def process_device_events(self, d_in, d_out, n_samples: int, events, stream=None):
+        """events: iterable of (sample, reg_index, value) with value a float (broadcast) or an array of N floats."""
+        arr = (CControlEvent * max(1, len(events)))()
+        keep = []
+        for i, (sample, reg, val) in enumerate(events):
+            v = np.ascontiguousarray(np.atleast_1d(val), dtype=np.float32)
+            keep.append(v)
+            arr[i].sample, arr[i].reg_index, arr[i].broadcast, arr[i].values = sample, reg, int(v.size == 1), v.ctypes.data
+        self._check(self.L.fx8010_gpu_process_batch_events(self.h, _ptr(d_in), _ptr(d_out), n_samples, C.addressof(arr), len(events), stream))
+
+    def process_device_planar(self, d_in, d_out, n_samples: int, stream=None):
+        self._check(self.L.fx8010_gpu_process_batch_planar(self.h, _ptr(d_in), _ptr(d_out), n_samples, stream))
 
     def process_host(self, x, n_samples=None, out=None) -> np.ndarray:
         if x is not None and not isinstance(x, int):

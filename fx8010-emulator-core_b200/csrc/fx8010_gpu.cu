@@ -73,6 +73,10 @@ struct fx8010_gpu {
     std::vector<int> tab_of;                     // per instruction: literal table id or -1
     uint4* h_prog = nullptr;                     // pinned, SLOT_WORDS words
     int enc_K = 0, enc_B = 0, enc_chunk = 0;     // geometry the uploaded encoding was made for
+    std::vector<uint8_t> enc_sensitive;          // per register: its value / uniformity is folded into the encoding (LOG/EXP selector, SKIP count)
+    cudaEvent_t ev_events = nullptr;
+    float* d_events = nullptr; size_t events_floats = 0;      // device copies of per-instance control-event values
+    float* d_planar_in = nullptr; float* d_planar_out = nullptr; size_t planar_floats = 0;   // [C][S][N] scratch of process_batch_planar
     int enc_family = -1;                         // kernel family whose constant memory holds it
     PlanKey plan_key; Launch plan = {};          // last launch plan (reused while nothing relevant changes)
     bool attr_set[3][2][2][2] = {};
@@ -214,6 +218,12 @@ void analyse(fx8010_gpu* h) {
         if (u == U_SKIP) h->has_skip = true;
     }
     if (any_ccr_writer) h->written[0] = 1;
+    h->enc_sensitive.assign(nr, 0);
+    for (int i = 0; i < n; ++i) {
+        const Uop u = uop_of(h, h->instrs[i]);
+        if (u == U_LOG || u == U_EXP) h->enc_sensitive[h->instrs[i].x] = 1;     // literal table selectors are resolved at encode time
+        if (u == U_SKIP) h->enc_sensitive[h->instrs[i].y] = 1;                  // so is a constant skip count (CCR liveness)
+    }
     // Only registers some instruction refers to (plus ccr) get a shared-memory row; the others
     // (unused declarations, the read/write/at pseudo registers) stay in the state arrays untouched.
     std::vector<uint8_t> used(nr, 0);
@@ -895,6 +905,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
         ok = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_events, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost(&h->h_prog, sizeof(uint4) * SLOT_WORDS) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_flags, sizeof(unsigned int)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_tabs, sizeof(TableEntry) * 2 * FX8010_TABLE_COUNT * FX8010_TABLE_ENTRIES) == cudaSuccess;
@@ -925,7 +936,8 @@ void fx8010_gpu_destroy(fx8010_gpu* h) {
     cudaSetDevice(h->device);
     sync_all(h);
     free_state(h);
-    cudaFree(h->d_flags); cudaFree(h->d_tabs);
+    cudaFree(h->d_flags); cudaFree(h->d_tabs); cudaFree(h->d_events); cudaFree(h->d_planar_in); cudaFree(h->d_planar_out);
+    if (h->ev_events) cudaEventDestroy(h->ev_events);
     for (int i = 0; i < HOST_PIPE_BUFS; ++i) {
         cudaFree(h->d_stage_in[i]); cudaFree(h->d_stage_out[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -1075,7 +1087,7 @@ int fx8010_gpu_set_controls(fx8010_gpu* h, int reg, const float* values, int bro
         FX_CUDA(h, cudaMemcpy(dst, values, sizeof(float) * h->N, cudaMemcpyHostToDevice));
         h->reg_uniform[reg] = 0;
     }
-    h->encode_dirty = true;
+    if (h->enc_sensitive[reg]) h->encode_dirty = true;
     return FX8010_OK;
 }
 
@@ -1085,7 +1097,7 @@ int fx8010_gpu_set_controls_device(fx8010_gpu* h, int reg, const float* d_values
     cudaStream_t st = (cudaStream_t)stream;
     FX_CUDA(h, cudaMemcpyAsync(h->d_gpr + (size_t)reg * h->N, d_values, sizeof(float) * h->N, cudaMemcpyDeviceToDevice, st));
     h->reg_uniform[reg] = 0;
-    h->encode_dirty = true;
+    if (h->enc_sensitive[reg]) h->encode_dirty = true;
     h->last_stream = st;
     return FX8010_OK;
 }
@@ -1106,6 +1118,116 @@ int fx8010_gpu_process_batch(fx8010_gpu* h, const float* d_in, float* d_out, int
     // queued host-buffer batches (process_batch_host_async) run on an internal stream: they come first
     if (h->last_stream == h->s_comp && (cudaStream_t)stream != h->s_comp) FX_CUDA(h, cudaStreamSynchronize(h->s_comp));
     return launch_block(h, d_in, d_out, cs, cs, n_samples, (cudaStream_t)stream);
+}
+
+int fx8010_gpu_process_batch_events(fx8010_gpu* h, const float* d_in, float* d_out, int n_samples,
+                                    const fx8010_control_event* events, int n_events, void* stream) {
+    FX_NEED_PROGRAM(h);
+    if (!d_out || n_samples < 0 || n_events < 0 || (n_events > 0 && !events)) return fail(h, FX8010_ERR_ARG, "bad buffer, count or event list");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = (size_t)h->N, cs = (size_t)n_samples * N;
+    size_t per_instance = 0;
+    for (int e = 0; e < n_events; ++e) {
+        const fx8010_control_event& ev = events[e];
+        if (!ev.values || ev.reg_index < 0 || ev.reg_index >= (int)h->regs.size() || ev.sample < 0 || ev.sample >= std::max(1, n_samples) ||
+            (e > 0 && ev.sample < events[e - 1].sample))
+            return fail(h, FX8010_ERR_ARG, "control event: bad register, sample out of range or list not sorted by sample");
+        if (!ev.broadcast) ++per_instance;
+    }
+    if (h->last_stream == h->s_comp && st != h->s_comp) FX_CUDA(h, cudaStreamSynchronize(h->s_comp));
+    // per-instance value arrays go to the device up front (the caller may reuse them when this call returns)
+    if (per_instance * N > h->events_floats) {
+        const int rc = sync_all(h);
+        if (rc) return rc;
+        cudaFree(h->d_events); h->d_events = nullptr; h->events_floats = 0;
+        FX_CUDA(h, cudaMalloc(&h->d_events, sizeof(float) * per_instance * N));
+        h->events_floats = per_instance * N;
+    } else if (per_instance) {                           // an earlier call's copies out of d_events must have been consumed
+        if (h->last_stream) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));
+        FX_CUDA(h, cudaStreamSynchronize(st));
+    }
+    size_t slot = 0;
+    if (per_instance) {                                  // on the copy stream: `st` may be busy with earlier batches
+        for (int e = 0; e < n_events; ++e)
+            if (!events[e].broadcast)
+                FX_CUDA(h, cudaMemcpyAsync(h->d_events + (slot++) * N, events[e].values, sizeof(float) * N, cudaMemcpyHostToDevice, h->s_h2d));
+        FX_CUDA(h, cudaEventRecord(h->ev_events, h->s_h2d));
+        FX_CUDA(h, cudaStreamWaitEvent(st, h->ev_events, 0));
+        FX_CUDA(h, cudaEventSynchronize(h->ev_events)); // the caller's arrays are free again when this call returns
+    }
+    int e = 0, s0 = 0;
+    slot = 0;
+    while (true) {
+        // changes that take effect before sample s0 (source/main.cpp:109-113: setRegisterValue, then process)
+        for (; e < n_events && events[e].sample <= s0; ++e) {
+            const fx8010_control_event& ev = events[e];
+            float* dst = h->d_gpr + (size_t)ev.reg_index * N;
+            if (ev.broadcast) {
+                fx_fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(dst, ev.values[0], (int)N);
+                h->info.kernel_launches++;
+                FX_CUDA(h, cudaGetLastError());
+                h->reg_uniform[ev.reg_index] = 1; h->reg_value[ev.reg_index] = ev.values[0];
+            } else {
+                FX_CUDA(h, cudaMemcpyAsync(dst, h->d_events + (slot++) * N, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+                h->reg_uniform[ev.reg_index] = 0;
+            }
+            if (h->enc_sensitive[ev.reg_index]) h->encode_dirty = true;
+            h->last_stream = st;
+        }
+        if (s0 >= n_samples) break;
+        const int s1 = (e < n_events) ? std::min(n_samples, (int)events[e].sample) : n_samples;
+        const int rc = launch_block(h, d_in ? d_in + (size_t)s0 * N : nullptr, d_out + (size_t)s0 * N, cs, cs, s1 - s0, st);
+        if (rc) return rc;
+        s0 = s1;
+        if (e >= n_events && s0 >= n_samples) break;
+    }
+    return FX8010_OK;
+}
+
+// [C][rows][cols] -> [C][cols][rows], 32 x 32 tiles through shared memory (coalesced on both sides)
+static __global__ void fx_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const size_t plane = (size_t)rows * cols * blockIdx.z;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = src[plane + (size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[plane + (size_t)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+int fx8010_gpu_process_batch_planar(fx8010_gpu* h, const float* d_in, float* d_out, int n_samples, void* stream) {
+    FX_NEED_PROGRAM(h);
+    if (!d_out || n_samples < 0) return fail(h, FX8010_ERR_ARG, "d_out is NULL or n_samples negative");
+    if (n_samples == 0) return FX8010_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = (size_t)h->N, C = (size_t)h->C, S = (size_t)n_samples, need = C * S * N;
+    if (need > h->planar_floats) {
+        const int rc = sync_all(h);
+        if (rc) return rc;
+        FX_CUDA(h, cudaStreamSynchronize(st));
+        cudaFree(h->d_planar_in); cudaFree(h->d_planar_out); h->d_planar_in = h->d_planar_out = nullptr; h->planar_floats = 0;
+        FX_CUDA(h, cudaMalloc(&h->d_planar_in, sizeof(float) * need));
+        FX_CUDA(h, cudaMalloc(&h->d_planar_out, sizeof(float) * need));
+        h->planar_floats = need;
+    }
+    if (h->last_stream == h->s_comp && st != h->s_comp) FX_CUDA(h, cudaStreamSynchronize(h->s_comp));
+    const dim3 blk(32, 8);
+    if (d_in) {     // [C][N][S] -> [C][S][N]
+        fx_transpose_kernel<<<dim3((unsigned)((S + 31) / 32), (unsigned)((N + 31) / 32), (unsigned)C), blk, 0, st>>>(d_in, h->d_planar_in, (int)N, (int)S);
+        h->info.kernel_launches++;
+        FX_CUDA(h, cudaGetLastError());
+    }
+    const int rc = launch_block(h, d_in ? h->d_planar_in : nullptr, h->d_planar_out, S * N, S * N, n_samples, st);
+    if (rc) return rc;
+    fx_transpose_kernel<<<dim3((unsigned)((N + 31) / 32), (unsigned)((S + 31) / 32), (unsigned)C), blk, 0, st>>>(h->d_planar_out, d_out, (int)S, (int)N);
+    h->info.kernel_launches++;
+    FX_CUDA(h, cudaGetLastError());
+    return FX8010_OK;
 }
 
 static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_samples, bool wait) {

@@ -149,6 +149,34 @@ FX8010_API int fx8010_gpu_process_batch_host(fx8010_gpu* h, const float* in, flo
  * buffers; with pageable memory the driver makes the copies synchronous anyway). */
 FX8010_API int fx8010_gpu_process_batch_host_async(fx8010_gpu* h, const float* in, float* out, int n_samples);
 
+/* ---- the caller's block loop -------------------------------------------
+ * The reference's driver changes sliders BETWEEN process() calls, every 8 sample periods
+ * (source/main.cpp:107-114: setRegisterValue, then process).  A batched caller would have to cut its
+ * batches at every change; these entry points take the schedule instead. */
+
+/* One control change inside a batch: register `reg_index` takes `values` right before sample period
+ * `sample` of the batch (0 <= sample < n_samples).  values: HOST pointer; broadcast != 0 -> values[0]
+ * goes to every instance, else values[N]. */
+typedef struct fx8010_control_event {
+    int32_t sample;
+    int32_t reg_index;
+    int32_t broadcast;
+    int32_t reserved;
+    const float* values;
+} fx8010_control_event;
+
+/* fx8010_gpu_process_batch with `n_events` control changes (sorted by `sample`, several may share one):
+ * equivalent to set_controls + process_batch on every stretch between changes, queued on `stream` without a
+ * host round trip in between (the value arrays are copied to the device before the first launch; they may be
+ * reused when the call returns). */
+FX8010_API int fx8010_gpu_process_batch_events(fx8010_gpu* h, const float* d_in, float* d_out, int n_samples,
+                                               const fx8010_control_event* events, int n_events, void* stream);
+
+/* fx8010_gpu_process_batch for PLANAR audio buffers, as an audio host keeps them: DEVICE pointers,
+ * [n_channels][n_instances][n_samples] float32 (one contiguous block of samples per instance and channel).
+ * The [sample][instance] layout the interpreter streams is produced and undone by tiled transposes on `stream`. */
+FX8010_API int fx8010_gpu_process_batch_planar(fx8010_gpu* h, const float* d_in, float* d_out, int n_samples, void* stream);
+
 /* Page-locked host memory for process_batch_host buffers: with these the host<->device copies run
  * asynchronously at full PCIe rate (pageable buffers work too, through the driver's staging). */
 FX8010_API void* fx8010_gpu_host_alloc(size_t bytes);

@@ -581,3 +581,75 @@ def test_trace_matches_execution(fx, po):
             assert_bits_equal(gpu.process_host(x2), orc.process(x2), "after trace")
         finally:
             gpu.close()
+
+
+# ---- the caller's block loop: control changes inside a batch, planar audio buffers --------------
+
+@pytest.mark.parametrize("name", ["testcode", "cfg2", "onepole", "delay", "dynsel"])
+def test_control_events_inside_a_batch(fx, po, name):
+    """The reference driver's pattern (source/main.cpp:107-114): a slider changes every 8 sample periods, between
+    process() calls.  One process_batch_events call with the schedule == the oracle stepped stretch by stretch."""
+    import torch
+    rng = np.random.default_rng(41)
+    n = 300
+    text, ctl = {
+        "testcode": (progs.CFG1A_TESTCODE, "volume"),
+        "cfg2": (progs.CFG2_LOG_GAIN, "volume"),
+        "onepole": (progs.CFG4_ONEPOLE, "filter_cutoff"),
+        "delay": ("static a\nstatic rd\ncontrol fb = 0.5\ninput in_l 0\noutput out_l 0\nitramsize 150 \nidelay read, rd, at, 0\n"
+                  "macs a, in_l, rd, fb\nidelay write, a, at, 0\nmacs out_l, in_l, rd, fb\nend", "fb"),
+        # the control is a LOG table selector: the literal-selector encoding has to follow it
+        "dynsel": ("static a\ninput in_l 0\ncontrol sel = 3\noutput out_l 0\nlog a, in_l, sel, 0\nmacs out_l, 0, a, 0.5\nend", "sel"),
+    }[name]
+    prog, img, orc, gpu = make_pair(fx, po, text, n)
+    try:
+        reg = prog.reg_index(ctl)
+        s_total = 100
+        x = (1.8 * rng.random((1, s_total, n)) - 0.9).astype(np.float32)
+        events = []
+        for s0 in range(0, s_total, 8):
+            if name == "dynsel":
+                v = float(rng.integers(0, 32)) if (s0 // 8) % 2 else rng.integers(0, 32, n).astype(np.float32)
+            else:
+                v = float(rng.random()) if (s0 // 8) % 3 == 0 else rng.random(n).astype(np.float32)
+            events.append((s0, reg, v))
+        events.insert(3, (16, reg, 0.125))             # two changes at the same sample: the later one wins
+        events.sort(key=lambda e: e[0])
+        # oracle: stretch by stretch
+        yo = np.zeros_like(x)
+        bounds = sorted({e[0] for e in events} | {s_total})
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            for (s, r, v) in events:
+                if s == a:
+                    orc.set_register(r, np.full(n, v, np.float32) if np.isscalar(v) else v)
+            yo[:, a:b] = orc.process(np.ascontiguousarray(x[:, a:b]))
+        d_in = torch.from_numpy(x).cuda()
+        d_out = torch.empty_like(d_in)
+        st = torch.cuda.Stream()
+        gpu.process_device_events(d_in, d_out, s_total, events, st.cuda_stream)
+        gpu.synchronize(st.cuda_stream)
+        assert_bits_equal(d_out.cpu().numpy(), yo, f"{name} outputs with control events")
+        compare_state(gpu, orc, img, f"{name} events", (0, n - 1))
+    finally:
+        gpu.close()
+
+
+@pytest.mark.parametrize("n,s", [(300, 77), (64, 1024), (1, 5), (33, 1)])
+def test_planar_buffers(fx, po, n, s):
+    """[channel][instance][sample] device buffers in and out (what an audio host holds)."""
+    import torch
+    rng = np.random.default_rng(42)
+    text = "static a\ninput in_l 0\ninput in_r 1\noutput out_l 0\noutput out_r 1\nmacs a, in_l, in_l, 0.5\nmacs out_l, a, 0.25, 0.5\nmacs out_r, in_r, a, 0.5\nend"
+    prog, img, orc, gpu = make_pair(fx, po, text, n, channels=2)
+    try:
+        for _ in range(2):
+            x = (1.8 * rng.random((2, s, n)) - 0.9).astype(np.float32)
+            yo = orc.process(x)
+            d_in = torch.from_numpy(np.ascontiguousarray(x.transpose(0, 2, 1))).cuda()      # [C][N][S]
+            d_out = torch.empty_like(d_in)
+            gpu.process_device_planar(d_in, d_out, s, None)
+            gpu.synchronize(None)
+            assert_bits_equal(d_out.cpu().numpy().transpose(0, 2, 1), yo, "planar outputs")
+        compare_state(gpu, orc, img, "planar", (0, n - 1))
+    finally:
+        gpu.close()
