@@ -709,14 +709,16 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     if (h->sl_serial)                        // one time segment: the warps come from the instances alone — keep two per SM at least
         while (K > 1 && (long)N / K / 32 < 2L * h->num_sms) K >>= 1;   // (cfg4, 65 536 instances: K = 4 147 us, K = 2 158 us, K = 1 155 us)
     if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
-    int B = h->tune_B ? h->tune_B : 128;
+    // time-split launches: 64-thread blocks with batches of 8 samples (decode amortised over twice the samples at the
+    // same shared-memory footprint as 128 x 4; cfg2: 8.7 vs 9.2 us)
+    int B = h->tune_B ? h->tune_B : (h->sl_serial ? 128 : 64);
     while (B > 32 && (N / K + B - 1) / B * B >= 2 * (N / K) && N / K <= B / 2) B >>= 1;      // tiny N: do not launch mostly-idle blocks
     if (h->sl_serial && !h->tune_B)          // one time segment: only N / K threads — spread them over the SMs
         while (B > 32 && (N / K + B - 1) / B < 2 * h->num_sms) B >>= 1;
     // A serial launch has few warps, and the batch is also how far the input stage runs ahead: make it deep.
-    int M = h->tune_M ? h->tune_M : (h->sl_serial ? SL_MAX_M : 4);
+    int M = h->tune_M ? h->tune_M : (h->sl_serial ? SL_MAX_M : 8);
     // serial: all blocks are resident at once; give each its share of the SM's shared memory
-    const size_t budget = h->sl_serial ? std::min<size_t>(h->smem_optin, (size_t)200 * 1024 / std::max(1, ((N / K + B - 1) / B + h->num_sms - 1) / h->num_sms)) : 48 * 1024;
+    const size_t budget = h->sl_serial ? std::min<size_t>(h->smem_optin, (size_t)200 * 1024 / std::max(1, ((N / K + B - 1) / B + h->num_sms - 1) / h->num_sms)) : 36 * 1024;
     while (!h->tune_M && M > 1 && sl_smem_bytes(h, B, K, M) > budget) M >>= 1;
     if (h->sl_serial && M < 2) M = 2;        // a carried operand reads row (m - 1) mod M while row m is written
     while (sl_smem_bytes(h, B, K, M) > h->smem_optin && B > 32) B >>= 1;

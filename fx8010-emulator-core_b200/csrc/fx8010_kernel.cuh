@@ -185,8 +185,14 @@ __device__ __forceinline__ int32_t logic_ops(float fa, float fx, float fy) {
 // (x + 1.0) * 31.5 in double gives the same integer as (x + 1.0) / (2.0/63) for every binary32 x in
 // [-1, 1] (exhaustively checked in C, sampled in tests/test_oracle.py::test_table_index_formula, swept
 // on the GPU by test_table_sweep_all_selectors); there the result is already inside 0..63.
-__device__ __forceinline__ int table_index_inrange(double xd) {
-    return __double2int_rz(__dmul_rn(__dadd_rn(xd, 1.0), 31.5));
+// The conversion unit (F2I.F64 / I2F.F64, about 11 issue cycles per warp instruction on this chip) is kept out of it:
+// for 0 <= q < 2^31, q + 2^52 rounded toward -infinity is exactly 2^52 + floor(q), whose low mantissa word is the
+// index and from which (double)index = t - 2^52 follows exactly — two FP64-pipe adds instead of two conversions.
+__device__ __forceinline__ int table_index_inrange(double xd, double& di) {
+    const double q = __dmul_rn(__dadd_rn(xd, 1.0), 31.5);
+    const double t = __dadd_rd(q, 4503599627370496.0);
+    di = __dsub_rn(t, 4503599627370496.0);
+    return __double2loint(t);
 }
 // Outside [-1, 1] (rule U6) the reference's index is clamped; cvttsd2si overflow / NaN -> INT_MIN -> 0.
 static __device__ __noinline__ int table_index_wild(float a) {
@@ -196,9 +202,9 @@ static __device__ __noinline__ int table_index_wild(float a) {
     return (q < 2147483648.0) ? i : 0;
 }
 // y = (y2 - y1) / (x2 - x1) * (x - x1) + y1 with the quotient precomputed on the host (:287-293)
-__device__ __forceinline__ float table_finish(double xd, int i, double y1, double slope) {
+__device__ __forceinline__ float table_finish(double xd, double di, double y1, double slope) {   // di = (double)index
     const double step = 2.0 / 63.0;
-    const double x1 = __dadd_rn(-1.0, __dmul_rn((double)i, step));
+    const double x1 = __dadd_rn(-1.0, __dmul_rn(di, step));
     return __double2float_rn(__dadd_rn(__dmul_rn(slope, __dsub_rn(xd, x1)), y1));
 }
 
@@ -472,12 +478,13 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                     case U_LOG:                                       // :1113-1119
                     case U_EXP: {                          // :1120-1125, linearInterpolate :283-296
                         int idx[K];
+                        double di[K];
                         bool wild = false;
                         FX_EACH { wild |= !(fabsf(a[k]) <= 1.0f); }
-                        if (!wild) { FX_EACH { idx[k] = table_index_inrange((double)a[k]); } }
+                        if (!wild) { FX_EACH { idx[k] = table_index_inrange((double)a[k], di[k]); } }
                         else {                                        // rule U6: clamp and flag (rare, may diverge)
                             FX_EACH {
-                                idx[k] = table_index_wild(a[k]);
+                                idx[k] = table_index_wild(a[k]); di[k] = (double)idx[k];
                                 if (!(fabsf(a[k]) <= 1.0f) && act[k]) flags |= FX8010_RT_TABLE_RANGE;
                             }
                         }
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                             const TableEntry* const tb = s_tab + (size_t)(wB.y >> 24) * (FX8010_TABLE_ENTRIES * TAB_REPL) + lane_rep;
                             FX_EACH {
                                 const TableEntry e = tb[idx[k] * TAB_REPL];
-                                r[k] = table_finish((double)a[k], idx[k], e.y1, e.slope); FX_ACC(r[k]);
+                                r[k] = table_finish((double)a[k], di[k], e.y1, e.slope); FX_ACC(r[k]);
                             }
                         } else {
                             FX_EACH {
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                                     tsel = (uop == U_EXP ? FX8010_TABLE_COUNT : 0) + sel;
                                 }
                                 const double2 e = __ldg(reinterpret_cast<const double2*>(p.tabs + tsel * FX8010_TABLE_ENTRIES + idx[k]));
-                                r[k] = table_finish((double)a[k], idx[k], e.x, e.y); FX_ACC(r[k]);
+                                r[k] = table_finish((double)a[k], di[k], e.x, e.y); FX_ACC(r[k]);
                             }
                         }
                         break; }

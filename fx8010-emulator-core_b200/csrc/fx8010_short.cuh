@@ -210,17 +210,18 @@ __global__ void __launch_bounds__(128) fx_short_kernel(const Params p) {
                 } SH_WRITE(true) } break;
             case U_LOG: case U_EXP: case SH_TAB_SMEM: case SH_TAB_IMM: {   // :1113-1125, linearInterpolate :283-296
                 int idx[K];
+                double di[K];
                 bool wild = false;
                 SH_EACH { wild |= !(fabsf(a[k]) <= 1.0f); }
-                if (!wild) { SH_EACH { idx[k] = table_index_inrange((double)a[k]); } }
+                if (!wild) { SH_EACH { idx[k] = table_index_inrange((double)a[k], di[k]); } }
                 else {                                        // rule U6: clamp and flag (rare)
-                    SH_EACH { idx[k] = table_index_wild(a[k]); if (!(fabsf(a[k]) <= 1.0f)) flags |= FX8010_RT_TABLE_RANGE; }
+                    SH_EACH { idx[k] = table_index_wild(a[k]); di[k] = (double)idx[k]; if (!(fabsf(a[k]) <= 1.0f)) flags |= FX8010_RT_TABLE_RANGE; }
                 }
                 if (s_uop[i] == SH_TAB_SMEM) {
                     SH_EACH {
                         double y1, sl;
                         lds_f64x2(s_aux[i] + (uint32_t)idx[k] * (uint32_t)(TAB_REPL * 16), y1, sl);
-                        r[k] = table_finish((double)a[k], idx[k], y1, sl); accv[k] = r[k];
+                        r[k] = table_finish((double)a[k], di[k], y1, sl); accv[k] = r[k];
                     }
                 } else {
                     SH_EACH {
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(128) fx_short_kernel(const Params p) {
                             tsel = (uint32_t)((s_uop[i] == U_EXP ? FX8010_TABLE_COUNT : 0) + sel) * (uint32_t)FX8010_TABLE_ENTRIES;
                         }
                         const double2 e = __ldg(reinterpret_cast<const double2*>(gtabs + tsel + idx[k]));
-                        r[k] = table_finish((double)a[k], idx[k], e.x, e.y); accv[k] = r[k];
+                        r[k] = table_finish((double)a[k], di[k], e.x, e.y); accv[k] = r[k];
                     }
                 }
                 SH_WRITE(true) } break;

@@ -204,13 +204,13 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
         SL_LOOP(true, false,
             if (dyn_sel && lx && m + 1 < n_m) { I.qx += I.sx; if (m & 1) X0 = lds<K>(I.qx); else X1 = lds<K>(I.qx); }
             int idx[K];
-            double xd[K];
+            double xd[K], di[K];
             bool wild = false;
             SL_EACH { wild |= !(fabsf(a[k]) <= 1.0f); xd[k] = (double)a[k]; }
-            if (!wild) { SL_EACH { idx[k] = table_index_inrange(xd[k]); } }
-            else { SL_EACH { idx[k] = table_index_wild(a[k]); if (!(fabsf(a[k]) <= 1.0f)) cx.flags |= FX8010_RT_TABLE_RANGE; } }   // rule U6
+            if (!wild) { SL_EACH { idx[k] = table_index_inrange(xd[k], di[k]); } }
+            else { SL_EACH { idx[k] = table_index_wild(a[k]); di[k] = (double)idx[k]; if (!(fabsf(a[k]) <= 1.0f)) cx.flags |= FX8010_RT_TABLE_RANGE; } }   // rule U6
             if (w0 & F_TAB_SMEM) {
-                SL_EACH { double y1; double slope; lds_f64x2(tb_s + (uint32_t)idx[k] * (TAB_REPL * 16u), y1, slope); r[k] = table_finish(xd[k], idx[k], y1, slope); }
+                SL_EACH { double y1; double slope; lds_f64x2(tb_s + (uint32_t)idx[k] * (TAB_REPL * 16u), y1, slope); r[k] = table_finish(xd[k], di[k], y1, slope); }
             } else {
                 SL_EACH {
                     int tsel;
@@ -221,7 +221,7 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
                         tsel = (uop == U_EXP ? FX8010_TABLE_COUNT : 0) + sel;
                     }
                     const double2 e = __ldg(reinterpret_cast<const double2*>(p.tabs + tsel * FX8010_TABLE_ENTRIES + idx[k]));
-                    r[k] = table_finish(xd[k], idx[k], e.x, e.y);
+                    r[k] = table_finish(xd[k], di[k], e.x, e.y);
                 }
             }
             SL_EACH { accv[k] = r[k]; })
