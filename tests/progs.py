@@ -362,3 +362,93 @@ def fuzz_source(rng: np.random.Generator) -> str:
     if not text.strip("\n"):
         return fuzz_source(rng)
     return text
+
+
+def random_flow_program(rng: np.random.Generator, n_instr: int, *, channels: int = 1, tram: str = "", size: int = 200,
+                        cross: bool = False) -> str:
+    """A random SKIP-free program whose only loop-carried values are SELF recurrences (the data-flow class the
+    instruction-major kernel takes): every operand is an input, a control / literal, a register defined earlier in the
+    same sample period, or the instruction's own result register.  tram = "i" / "x" / "ix" adds one READ and one WRITE
+    per TRAM at random places with literal offsets.  cross=True plants one value carried from a later instruction to an
+    earlier one (such a program must NOT take that kernel).  All values stay inside the reference's defined behaviour."""
+    lines, statics = [], [f"s{i}" for i in range(n_instr + 4)]
+    for r in statics:
+        lines.append(f"static {r} = {rng.random():.5f}" if rng.random() < 0.6 else f"static {r}")
+    ins = [f"in{c}" for c in range(channels)]
+    outs = [f"out{c}" for c in range(channels)]
+    lines += [f"input {r} {c}" for c, r in enumerate(ins)] + [f"output {r} {c}" for c, r in enumerate(outs)]
+    ctl = ["c0", "c1"]
+    lines += [f"control {r} = {rng.random():.4f}" for r in ctl]
+    rd = {}
+    for t in tram:
+        lines.append(f"{t}tramsize {size} ")
+        lines.append(f"static rd{t}")
+        rd[t] = f"rd{t}"
+    free = list(statics)
+    rng.shuffle(free)
+    defined_narrow, defined_wide = [], []          # produced earlier in this period: in [-1, 1] / possibly wider
+    body = []
+
+    def lit():
+        return f"{rng.choice([0.0, 0.125, 0.25, 0.5, 0.75, 1.0, -0.5, -0.25]):g}"
+
+    def src(narrow_only, own=None):
+        pool = list(ins) * 2 + ctl + [lit(), lit()] + defined_narrow * 2
+        if not narrow_only:
+            pool += defined_wide * 2
+        if own is not None:
+            pool += [own] * 3
+        return str(rng.choice(pool))
+
+    tram_ops = []
+    for t in tram:
+        d = "idelay" if t == "i" else "xdelay"
+        roff, woff = int(rng.integers(0, size // 2)), int(rng.integers(0, 4))
+        tram_ops += [("rd", t, f"{d} read, {rd[t]}, at, {roff}"), ("wr", t, d, woff)]
+    slots = sorted(rng.choice(n_instr + 1, size=len(tram_ops), replace=True).tolist()) if tram_ops else []
+    order = list(rng.permutation(len(tram_ops))) if tram_ops else []
+    planted = None
+    for i in range(n_instr + 1):
+        for k, sl in enumerate(slots):
+            if sl == i:
+                op = tram_ops[order[k]]
+                if op[0] == "rd":
+                    body.append(op[2]); defined_narrow.append(rd[op[1]])
+                else:
+                    body.append(f"{op[2]} write, {src(True)}, at, {op[3]}")
+        if i == n_instr:
+            break
+        last = (i >= n_instr - channels)
+        r = outs[i - (n_instr - channels)] if last else free.pop()
+        own = r if rng.random() < 0.45 else None       # self recurrence on this instruction's result register
+        kind = rng.choice(["sat", "sat", "sat", "interp", "wrap", "limit", "tstneg", "table", "andxor"])
+        if kind == "sat":
+            body.append(f"{rng.choice(['macs', 'macsn', 'acc3', 'macints'])} {r}, {src(False, own)}, {src(True, own)}, {src(True, own)}")
+            defined_narrow.append(r)
+        elif kind == "interp":
+            body.append(f"interp {r}, {src(True, own)}, {rng.choice(ctl + [lit()])}, {src(True)}")
+            defined_narrow.append(r)
+        elif kind == "wrap":
+            body.append(f"{rng.choice(['macw', 'macwn', 'macintw'])} {r}, {src(True, own)}, {src(True)}, {src(True)}")
+            defined_wide.append(r)
+        elif kind == "limit":
+            body.append(f"{rng.choice(['limit', 'limitn'])} {r}, {src(False, own)}, {src(True, own)}, {src(True)}")
+            defined_narrow.append(r)
+        elif kind == "tstneg":
+            body.append(f"tstneg {r}, {src(False)}, {src(True, own)}, {src(True)}")
+            defined_narrow.append(r)
+        elif kind == "table":
+            body.append(f"{rng.choice(['log', 'exp'])} {r}, {src(True, own)}, {int(rng.integers(0, 32))}, 0")
+            defined_narrow.append(r)
+        else:
+            body.append(f"andxor {r}, {src(False)}, {src(True)}, {src(True)}")
+            defined_wide.append(r)
+        if cross and planted is None and i >= 1 and not last:
+            planted = r
+    if cross and planted is not None:
+        # the first instruction now reads what a later one leaves behind: carried across instructions
+        first = body[0].split(",")
+        if not body[0].startswith(("idelay", "xdelay")):
+            first[-1] = " " + planted
+            body[0] = ",".join(first)
+    return "\n".join(lines + body + ["end"])

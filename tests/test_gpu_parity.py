@@ -583,6 +583,31 @@ def test_trace_matches_execution(fx, po):
             gpu.close()
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_instruction_major(fx, po, seed):
+    """Random programs of the instruction-major kernel's data-flow class (self recurrences, same-period flow, one
+    READ + one WRITE per TRAM), against the oracle: outputs and the whole state, several ragged calls."""
+    rng = np.random.default_rng(1000 + seed)
+    tram = ["", "", "i", "x", "ix"][seed % 5]
+    ch = 2 if seed % 7 == 3 else 1
+    text = progs.random_flow_program(rng, int(rng.integers(2, 14)), channels=ch, tram=tram, size=int(rng.choice([5, 70, 200, 900])))
+    n = int(rng.choice([96, 130, 257]))
+    info = run_case(fx, po, text, n, [1, 40, 7, 64, 33], rng, channels=ch, what=f"flow fuzz {seed}")
+    if ch == 1:     # (with two channels an X / Y input operand reads A's channel, reference :1057-1060: those programs take the generic kernel)
+        assert info.kernel_variant & 8, "the generator is meant to stay inside the instruction-major class:\n" + text
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_cross_instruction_carry_leaves_the_instruction_major_kernel(fx, po, seed):
+    rng = np.random.default_rng(2000 + seed)
+    text = progs.random_flow_program(rng, int(rng.integers(3, 9)), cross=True)
+    info = run_case(fx, po, text, 100, [1, 30, 9], rng, what=f"cross fuzz {seed}")
+    first = text.split("\n")
+    body0 = [l for l in first if l.split(" ")[0] in ("macs", "macsn", "acc3", "macints", "interp", "macw", "macwn", "macintw", "limit", "limitn", "tstneg", "log", "exp", "andxor")][0]
+    if not body0.startswith(("log", "exp")):       # LOG/EXP never read Y: nothing is carried there
+        assert not (info.kernel_variant & 8), text
+
+
 # ---- the caller's block loop (SURVEY.md §8f-2): control changes inside a batch, planar audio buffers --------------
 
 @pytest.mark.parametrize("name", ["testcode", "cfg2", "onepole", "delay", "dynsel"])
