@@ -187,6 +187,10 @@ class Oracle:
         rc = olib().fx_oracle_get_tram(self.h, which, instance, out.ctypes.data)
         return out if rc == 0 else np.zeros(0, dtype=np.float32)
 
+    def set_tram(self, which: int, instance: int, values) -> int:
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        return int(olib().fx_oracle_set_tram(self.h, which, instance, v.ctypes.data))
+
 
 # ------------------------------------------------------------------------------------------------
 _rlib = None

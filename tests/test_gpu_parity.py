@@ -583,6 +583,37 @@ def test_trace_matches_execution(fx, po):
             gpu.close()
 
 
+@pytest.mark.parametrize("order", ["rw", "wr"])
+def test_tram_pointers_differ_per_instance(fx, po, order):
+    """TRAM pointers are per-instance state (set through the checkpoint API here): neighbouring instances then sit
+    at different ring positions (no vector access), and some have a delay shorter than two batches, so their warps
+    take the one-sample-at-a-time path while others prefetch."""
+    rng = np.random.default_rng(51)
+    n, size = 192, 400
+    text = _tram_prog(size, order=order, roff="30" if order == "wr" else "0", woff="2")
+    prog, img, orc, gpu = make_pair(fx, po, text, n)
+    try:
+        ptrs = np.zeros((4, n), np.int32)
+        ptrs[0] = rng.integers(0, size, n)                       # iw
+        ptrs[1] = (ptrs[0] + rng.integers(0, size, n)) % size    # ir: any distance, including very short ones
+        ptrs[1, 32:64] = (ptrs[0, 32:64] + 200) % size           # one warp (K = 1) / part of one (K = 4) comfortably far
+        ptrs[1, 64:68] = (ptrs[0, 64:68] + 1) % size
+        acc, lfsr, latch, _ = gpu.scalars()
+        gpu.set_scalars(acc, lfsr, latch, ptrs)
+        orc.tram_ptrs[...] = ptrs
+        ring = (rng.random((n, size)) - 0.5).astype(np.float32)
+        for i in range(n):
+            gpu.set_tram(0, i, ring[i])
+            orc.set_tram(0, i, ring[i])
+        for s in (1, 70, 64, 33):
+            x = (1.8 * rng.random((1, s, n)) - 0.9).astype(np.float32)
+            assert_bits_equal(gpu.process_host(x), orc.process(x), f"outputs, per-instance pointers, {order}")
+        compare_state(gpu, orc, img, "per-instance pointers", (0, 40, 65, n - 1))
+        assert gpu.launch_info().kernel_variant & 8
+    finally:
+        gpu.close()
+
+
 @pytest.mark.parametrize("seed", range(24))
 def test_fuzz_instruction_major(fx, po, seed):
     """Random programs of the instruction-major kernel's data-flow class (self recurrences, same-period flow, one
