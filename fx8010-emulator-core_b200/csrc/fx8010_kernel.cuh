@@ -195,7 +195,7 @@ __device__ __forceinline__ int table_index_inrange(double xd, double& di) {
     return __double2loint(t);
 }
 // Outside [-1, 1] (rule U6) the reference's index is clamped; cvttsd2si overflow / NaN -> INT_MIN -> 0.
-static __device__ __noinline__ int table_index_wild(float a) {
+__device__ __forceinline__ int table_index_wild(float a) {   // (inlined: a real call makes ptxas spill the callers' long-lived state around it)
     const double q = __dmul_rn(__dadd_rn((double)a, 1.0), 31.5);
     int i = __double2int_rz(q);
     i = min(max(i, 0), FX8010_TABLE_ENTRIES - 1);

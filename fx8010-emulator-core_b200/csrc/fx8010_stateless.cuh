@@ -17,6 +17,8 @@
 // Arithmetic is the same code as the generic kernel (fx8010_kernel.cuh): bit-exact with the reference.
 #pragma once
 
+#include <type_traits>
+
 #include "fx8010_kernel.cuh"
 
 namespace fxk {
@@ -255,20 +257,25 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
             const int size = cx.rsize[T];                                                                        \
             float* const ring = cx.ring[T];                                                                      \
             int pos[K];                                                                                          \
-            bool same = true;                                                                                    \
-            SL_EACH { pos[k] = min(max(cvt_x86(Y0[k]), 0), size - 1); same = same && (cx.tp[2 * T][k] + pos[k] == cx.tp[2 * T][0] + pos[0]); } \
+            float* wq[K];            /* running address of slot wp + pos (not wrapped in the reference: slots at or */ \
+            bool same = true;        /* beyond the ring are never read back -> dropped) */                       \
+            SL_EACH {                                                                                            \
+                pos[k] = min(max(cvt_x86(Y0[k]), 0), size - 1);                                                  \
+                wq[k] = ring + (uint64_t)(cx.tp[2 * T][k] + pos[k]) * Nl + k;                                    \
+                same = same && (cx.tp[2 * T][k] + pos[k] == cx.tp[2 * T][0] + pos[0]);                           \
+            }                                                                                                    \
             Vec<K> a = A0;                                                                                       \
             for (int m = 0; m < n_m; ++m) {                                                                      \
                 Vec<K> an = a;                                                                                   \
                 if (la && m + 1 < n_m) { I.qa += I.sa; an = lds<K>(I.qa); }                                      \
-                int widx[K];                                                                                     \
+                if (K > 1 && same) { if (cx.tp[2 * T][0] + pos[0] < size && cx.valid) vstore<K>(wq[0], a); }     \
+                else { SL_EACH { if (cx.tp[2 * T][k] + pos[k] < size && cx.valid) *wq[k] = a[k]; } }             \
                 SL_EACH {                                                                                        \
                     int32_t& wp = cx.tp[2 * T][k];                                                               \
-                    widx[k] = wp + pos[k];   /* not wrapped in the reference: slots at or beyond the ring are never read back -> dropped */ \
-                    wp = (wp + 1 == size) ? 0 : wp + 1;                                                          \
+                    const bool wrap = (++wp == size);                                                            \
+                    wp = wrap ? 0 : wp;                                                                          \
+                    wq[k] = wrap ? ring + (uint64_t)pos[k] * Nl + k : wq[k] + Nl;                                \
                 }                                                                                                \
-                if (K > 1 && same) { if (widx[0] < size && cx.valid) vstore<K>(ring + (uint64_t)widx[0] * Nl, a); } \
-                else { SL_EACH { if (widx[k] < size && cx.valid) ring[(uint64_t)widx[k] * Nl + k] = a[k]; } }    \
                 a = an;                                                                                          \
             }                                                                                                    \
         }
@@ -433,30 +440,37 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
         }
         cx.tram_fast = __all_sync(0xffffffffu, safe);
     }
+    // running global addresses of the streams' next sample (one add per sample, a reset where the ring wraps)
+    const float* tr_ptr[2][K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        tr_ptr[0][k] = cx.ring[0] + (size_t)(TRAM && p.tr_on[0] ? tr_next[0][k] : 0) * N + k;
+        tr_ptr[1][k] = cx.ring[1] + (size_t)(TRAM && p.tr_on[1] ? tr_next[1][k] : 0) * N + k;
+    }
+    auto fetch_stream = [&](auto tc, const int nm, const uint32_t boff) {
+        constexpr int t = decltype(tc)::value;
+        const int size = cx.rsize[t];
+        const float* const ring = cx.ring[t];
+        unsigned char* d = reinterpret_cast<unsigned char*>(at(p.tr_stage[t] + boff));
+        for (int m = 0; m < nm; ++m, d += row_bytes) {
+            if (K > 1 && tr_same[t]) cp_async<4 * K>(d, tr_ptr[t][0]);
+            else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) cp_async<4>(d + 4 * k, tr_ptr[t][k]);
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const bool wrap = (++tr_next[t][k] == size);
+                tr_next[t][k] = wrap ? 0 : tr_next[t][k];
+                tr_ptr[t][k] = wrap ? ring + k : tr_ptr[t][k] + N;
+            }
+        }
+    };
     auto fetch_tram = [&](int s0, uint32_t boff) {
         if (TRAM && p.n_tr > 0 && cx.tram_fast && s0 < s_end) {
             const int nm = min(M, s_end - s0);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                if (!p.tr_on[t]) continue;
-                const int size = cx.rsize[t];
-                const float* const ring = cx.ring[t];
-                unsigned char* d = reinterpret_cast<unsigned char*>(at(p.tr_stage[t] + boff));
-                for (int m = 0; m < nm; ++m, d += row_bytes) {
-                    if (K > 1 && tr_same[t]) {
-                        int idx = tr_next[t][0] + m; idx -= (idx >= size) ? size : 0;
-                        cp_async<4 * K>(d, ring + (size_t)idx * N);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            int idx = tr_next[t][k] + m; idx -= (idx >= size) ? size : 0;
-                            cp_async<4>(d + 4 * k, ring + (size_t)idx * N + k);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < K; ++k) { tr_next[t][k] += nm; tr_next[t][k] -= (tr_next[t][k] >= size) ? size : 0; }
-            }
+            if (p.tr_on[0]) fetch_stream(std::integral_constant<int, 0>{}, nm, boff);
+            if (p.tr_on[1]) fetch_stream(std::integral_constant<int, 1>{}, nm, boff);
         }
     };
     fetch_tram(s_begin, 0);
