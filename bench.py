@@ -117,6 +117,33 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# IEEE operations one executed DSP instruction needs: (FP32/INT-pipe ops, FP64-pipe ops).
+# Dispatch, operand fetch and CCR are excluded — this is the arithmetic the semantics require.
+OP_COST = {"macs": (4, 0), "macsn": (4, 0), "macints": (4, 0), "acc3": (4, 0), "macw": (5, 0), "macwn": (5, 0), "macintw": (5, 0),
+           "macmv": (2, 1), "andxor": (10, 0), "tstneg": (7, 0), "limit": (2, 0), "limitn": (2, 0), "log": (2, 5), "exp": (2, 5),
+           "interp": (6, 3), "skip": (4, 0), "idelay": (0, 0), "xdelay": (0, 0), "end": (0, 0)}
+
+
+def compute_roofline(text: str, executed_per_step: float, n_inst: int, step_s: float, sm_mhz: float, bytes_per: int, hbm_gbs: float):
+    """SURVEY.md §8d for compute-bound programs: t_roofline = max(bytes / BW_HBM, sum FP32 ops / P32, sum FP64 ops / P64)
+    with the sums from the program's opcode histogram scaled by the executed fraction (skipped instructions do no
+    arithmetic), P32 = 128 and P64 = 64 lane-ops per clock and SM at the SM clock seen during the run (nominal pipe
+    widths, not microbenchmarked)."""
+    ops = [ln.split()[0] for ln in text.lower().splitlines() if ln.split() and ln.split()[0] in OP_COST]
+    f32 = sum(OP_COST[o][0] for o in ops)
+    f64 = sum(OP_COST[o][1] for o in ops)
+    frac = executed_per_step / (len(ops) * float(n_inst) * BLOCK)          # executed / issued
+    clk = (sm_mhz or 1965.0) * 1e6
+    t32 = f32 * frac * n_inst * BLOCK / (148 * 128 * clk)
+    t64 = f64 * frac * n_inst * BLOCK / (148 * 64 * clk)
+    thbm = bytes_per * n_inst * BLOCK / (hbm_gbs * 1e9)
+    t_roof = max(t32, t64, thbm)
+    return {"bound": "fp32-pipe" if t_roof == t32 else ("fp64-pipe" if t_roof == t64 else "hbm"),
+            "t_roofline_us": 1e6 * t_roof, "t_measured_us": 1e6 * step_s, "frac": t_roof / step_s,
+            "fp32_ops_per_sample": f32 * frac, "fp64_ops_per_sample": f64 * frac, "executed_fraction": frac,
+            "peaks": "nominal: 148 SMs x 128 FP32 / 64 FP64 lane-ops per clock at the SM clock sampled during the run"}
+
+
 def ncu_traffic(cfg: str):
     """dram bytes per launch of the interpreter kernel from the committed ncu capture, if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -356,6 +383,9 @@ def main():
                              "traffic": ncu_traffic(args.config), "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": 1e3 * launch_ms},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
+        if args.config == "cfg5":        # compute-bound program: the arithmetic roofline of SURVEY.md §8d beside the HBM one
+            line["compute_roofline"] = compute_roofline(text, instr_per_step, n_inst, 1e-3 * ms / args.steps,
+                                                        (clocks or {}).get("sm_mhz"), bytes_per, peak)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_rate(text, args.config, 10.0, os.cpu_count() or 1)
         print(json.dumps(line))

@@ -367,6 +367,12 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
         }
     };
     fetch_batch(s_begin, 0);                            // (its group is committed after the TRAM streams joined it, below)
+    if (!has_in) {                                      // no input block: INPUT operands read silence (their rows are the stage rows)
+        Vec<K> z;
+#pragma unroll
+        for (int k = 0; k < K; ++k) z[k] = 0.0f;
+        for (int j = 0; j < 2 * C * M; ++j) vstore<K>(at(p.stage0 + (uint32_t)j * row_bytes), z);
+    }
 
     for (int t = 0; t < p.n_smem_tabs; ++t) {
         const TableEntry* src = p.tabs + (size_t)p.smem_tab_id[t] * FX8010_TABLE_ENTRIES;

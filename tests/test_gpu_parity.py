@@ -709,3 +709,21 @@ def test_planar_buffers(fx, po, n, s):
         compare_state(gpu, orc, img, "planar", (0, n - 1))
     finally:
         gpu.close()
+
+
+@pytest.mark.parametrize("text", [progs.CFG2_LOG_GAIN, progs.CFG4_ONEPOLE, progs.cfg3_delay(100)])
+def test_null_input_block_is_silence(fx, po, text):
+    """process_batch with d_in == NULL: INPUT operands read 0.0 (every kernel family)."""
+    import torch
+    n, s = 96, 70
+    prog, img, orc, gpu = make_pair(fx, po, text, n)
+    try:
+        x = (np.random.default_rng(61).random((1, s, n)) - 0.5).astype(np.float32)
+        assert_bits_equal(gpu.process_host(x), orc.process(x), "warm-up block")
+        d_out = torch.empty((1, s, n), dtype=torch.float32, device="cuda")
+        gpu.process_device(None, d_out, s, None)
+        gpu.synchronize(None)
+        assert_bits_equal(d_out.cpu().numpy(), orc.process(np.zeros((1, s, n), np.float32)), "NULL input")
+        compare_state(gpu, orc, img, "NULL input", (0, n - 1))
+    finally:
+        gpu.close()
