@@ -727,3 +727,29 @@ def test_null_input_block_is_silence(fx, po, text):
         compare_state(gpu, orc, img, "NULL input", (0, n - 1))
     finally:
         gpu.close()
+
+
+@pytest.mark.parametrize("text", [
+    # a TRAM that is only written, one that is only read (its ring comes from the checkpoint API), both in one program
+    "static a\ninput in_l 0\noutput out_l 0\nitramsize 50 \nmacs a, in_l, 0.5, 0.5\nidelay write, a, at, 3\nmacs out_l, a, in_l, 0.25\nend",
+    "static rd\ninput in_l 0\noutput out_l 0\nxtramsize 333 \nxdelay read, rd, at, 40\nmacs out_l, rd, in_l, 0.25\nend",
+    "static a\nstatic rd\ninput in_l 0\noutput out_l 0\nitramsize 50 \nxtramsize 333 \nxdelay read, rd, at, 40\nmacs a, in_l, rd, 0.5\n"
+    "idelay write, a, at, 3\nmacs out_l, a, in_l, 0.25\nend",
+])
+def test_tram_written_only_or_read_only(fx, po, text):
+    rng = np.random.default_rng(71)
+    n = 100
+    prog, img, orc, gpu = make_pair(fx, po, text, n)
+    try:
+        d = gpu.dims()
+        if d.xtram_size:
+            for i in range(n):
+                ring = (rng.random(d.xtram_size) - 0.5).astype(np.float32)
+                gpu.set_tram(1, i, ring); orc.set_tram(1, i, ring)
+        for s in (1, 90, 64, 500):
+            x = (1.8 * rng.random((1, s, n)) - 0.9).astype(np.float32)
+            assert_bits_equal(gpu.process_host(x), orc.process(x), "outputs")
+        compare_state(gpu, orc, img, "one-sided TRAM", (0, 50, n - 1))
+        assert gpu.launch_info().kernel_variant & 8
+    finally:
+        gpu.close()
