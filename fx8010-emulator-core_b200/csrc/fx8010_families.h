@@ -16,8 +16,8 @@ typedef void (*SLKernelFn)(const SLParams);
 
 enum Family { FAM_GENERIC = 0, FAM_SHORT, FAM_SL1, FAM_SL2, FAM_SL4, FAM_COUNT };
 
-// fx_interp_kernel<K, SKIP, EXT, NI>  (k_generic.cu)
-KernelFn generic_kernel(int K, bool skip, bool ext, bool shortp);
+// fx_interp_kernel<K, SKIP, EXT>  (k_generic.cu)
+KernelFn generic_kernel(int K, bool skip, bool ext);
 // fx_short_kernel<K, EXT, NI>  (k_short.cu); ni = exact number of encoded instructions, 1..SH_MAX_NI
 KernelFn short_kernel(int K, bool ext, int ni);
 // fx_stateless_kernel<K, TRAM>  (k_sl1.cu, k_sl2.cu, k_sl4.cu)

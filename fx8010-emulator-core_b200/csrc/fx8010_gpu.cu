@@ -79,7 +79,7 @@ struct fx8010_gpu {
     float* d_planar_in = nullptr; float* d_planar_out = nullptr; size_t planar_floats = 0;   // [C][S][N] scratch of process_batch_planar
     int enc_family = -1;                         // kernel family whose constant memory holds it
     PlanKey plan_key; Launch plan = {};          // last launch plan (reused while nothing relevant changes)
-    bool attr_set[3][2][2][2] = {};
+    bool attr_set[3][2][2] = {};
     // previous launch on last_stream: the buffers it writes / reads (for the PDL overlap decision)
     struct Span { const char* out_lo = nullptr; const char* out_hi = nullptr; const char* in_lo = nullptr; const char* in_hi = nullptr;
                   cudaStream_t stream = nullptr; bool valid = false; } prev[2];   // [0] = latest
@@ -618,7 +618,7 @@ void free_state(fx8010_gpu* h) {
     h->d_itram = nullptr; h->d_xtram = nullptr; h->d_counts = nullptr; h->d_wb = nullptr; h->d_latch_ch = nullptr; h->d_reg_map = nullptr; h->d_load_rows = nullptr; h->d_sl_load = nullptr; h->d_sl_wb = nullptr;
 }
 
-KernelFn pick_kernel(int K, bool skip, bool ext, bool shortp) { return generic_kernel(K, skip, ext, shortp); }
+KernelFn pick_kernel(int K, bool skip, bool ext) { return generic_kernel(K, skip, ext); }
 // Encoded length of the program for the generic kernel (END/NOP are dropped when there is no SKIP).
 int encoded_length(const fx8010_gpu* h) {
     int e = 0;
@@ -629,7 +629,6 @@ int encoded_length(const fx8010_gpu* h) {
     }
     return e;
 }
-bool is_short(const fx8010_gpu* h) { return h->use_short && encoded_length(h) <= SHORT_NI; }
 // fx_short_kernel<K, EXT, NI>: NI = the exact number of executed instructions
 bool use_short_kernel(const fx8010_gpu* h) {
     const int e = encoded_length(h);
@@ -679,7 +678,7 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     L.grid_x = (N / K + B - 1) / B;
     L.n_seg = 1; L.seg_len = n_samples;
     if (h->stateless && n_samples > min_seg && !h->trace_mode) {
-        KernelFn fn = use_short_kernel(h) ? pick_short_kernel(K, h->has_ext, encoded_length(h)) : pick_kernel(K, h->has_skip, h->has_ext, is_short(h));
+        KernelFn fn = use_short_kernel(h) ? pick_short_kernel(K, h->has_ext, encoded_length(h)) : pick_kernel(K, h->has_skip, h->has_ext);
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, B, L.smem);
         occ = std::max(occ, 1);
@@ -718,7 +717,8 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     // A serial launch has few warps, and the batch is also how far the input stage runs ahead: make it deep.
     int M = h->tune_M ? h->tune_M : (h->sl_serial ? SL_MAX_M : 8);
     // serial: all blocks are resident at once; give each its share of the SM's shared memory
-    const size_t budget = h->sl_serial ? std::min<size_t>(h->smem_optin, (size_t)200 * 1024 / std::max(1, ((N / K + B - 1) / B + h->num_sms - 1) / h->num_sms)) : 36 * 1024;
+    // (with more blocks than fit at once the launch runs in waves: 56 KiB keeps four 128-thread blocks per SM)
+    const size_t budget = h->sl_serial ? std::min<size_t>(h->smem_optin, std::max<size_t>(56 * 1024, (size_t)200 * 1024 / std::max(1, ((N / K + B - 1) / B + h->num_sms - 1) / h->num_sms))) : 36 * 1024;
     while (!h->tune_M && M > 1 && sl_smem_bytes(h, B, K, M) > budget) M >>= 1;
     if (h->sl_serial && M < 2) M = 2;        // a carried operand reads row (m - 1) mod M while row m is written
     while (sl_smem_bytes(h, B, K, M) > h->smem_optin && B > 32) B >>= 1;
@@ -846,13 +846,12 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             for (int t = 0; t < MAX_SMEM_TABLES; ++t) p.smem_tab_id[t] = h->smem_tab_id[t];
             p.chunk = L.chunk;
             p.pdl_late_wait = late_wait;
-            const bool shortp = is_short(h) && !h->trace_mode;
             const bool kskip = h->has_skip || h->trace_mode, kext = h->has_ext || h->trace_mode;
             p.trace = h->trace_mode ? h->d_trace : nullptr; p.trace_inst = h->trace_inst;
             const bool lean = use_short_kernel(h);
-            KernelFn fn = lean ? pick_short_kernel(L.K, kext, h->n_exec) : pick_kernel(L.K, kskip, kext, shortp);
+            KernelFn fn = lean ? pick_short_kernel(L.K, kext, h->n_exec) : pick_kernel(L.K, kskip, kext);
             bool& attr = lean ? h->short_attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][kext ? 1 : 0][h->n_exec - 1]
-                              : h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][kskip ? 1 : 0][kext ? 1 : 0][shortp ? 1 : 0];
+                              : h->attr_set[L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)][kskip ? 1 : 0][kext ? 1 : 0];
             if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
             FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
         }
@@ -862,7 +861,7 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
         h->info.kernel_launches++;
         h->info.last_grid = L.grid_x * L.n_seg; h->info.last_block = L.B; h->info.last_time_split = L.n_seg;
         h->info.last_smem_bytes = (int)L.smem;
-        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | ((L.M == 0 && is_short(h)) ? 16 : 0) | ((L.M == 0 && use_short_kernel(h)) ? 32 : 0) | (L.K << 8) | (L.M << 16);
+        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | ((L.M == 0 && use_short_kernel(h)) ? 32 : 0) | (L.K << 8) | (L.M << 16);
     }
     h->last_stream = st;
     return FX8010_OK;

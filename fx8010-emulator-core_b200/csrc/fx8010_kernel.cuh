@@ -227,7 +227,7 @@ __device__ __forceinline__ uint64_t pin64(uint64_t v) { uint64_t o; asm volatile
 // one-instruction recurrence's time).  They are therefore bounced through shared memory once and read
 // back with VOLATILE loads before the loop: a volatile access cannot be repeated, so the value has to
 // stay in a register.
-constexpr int INV_WORDS = 8 + 8 * 4;     // scalars + up to 4 hoisted instructions of 8 words
+constexpr int INV_WORDS = 8;             // the scalars below
 __device__ __forceinline__ uint32_t inv_read(const uint32_t* s_inv, int i) { return *reinterpret_cast<const volatile uint32_t*>(s_inv + i); }
 
 // Shared-memory layout of one block (host and device agree through these formulas):
@@ -246,13 +246,7 @@ __host__ __device__ inline uint32_t stage_offset(int n_regs, int C, int c, int R
 //   SKIP: the program contains SKIP (per-context predicate, extra passes when END is skipped)
 //   EXT : the program uses TRAM, the noise LFSR or MACMV (their state stays out of the registers
 //         of simpler programs)
-//   NI  : 0 = fetch every instruction from __constant__ memory inside the sample loop (any length);
-//         NI > 0 = short program (n_exec <= NI): its decoded words are read ONCE into registers and the
-//         instruction loop is unrolled, so fetch, decode and operand address arithmetic leave the
-//         per-sample dependency chain (recurrences such as a one-pole filter or a feedback delay are
-//         bound by exactly that chain).
-constexpr int SHORT_NI = 4;
-template <int K, bool SKIP, bool EXT, int NI>
+template <int K, bool SKIP, bool EXT>
 __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int B = blockDim.x;
@@ -349,24 +343,12 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
         s_inv[3] = (uint32_t)(p.out_cstride & 0xffffffffu); s_inv[4] = (uint32_t)(p.out_cstride >> 32);
         s_inv[5] = (uint32_t)p.N;
     }
-    if (NI > 0 && tid < 2 * NI) {
-        const uint4 w = prog[tid];
-        s_inv[8 + 4 * tid] = w.x; s_inv[9 + 4 * tid] = w.y; s_inv[10 + 4 * tid] = w.z; s_inv[11 + 4 * tid] = w.w;
-    }
     __syncthreads();                  // s_tab / s_inv visible (the only block-wide dependency)
     const int n_exec = (int)inv_read(s_inv, 0), n_latch_ch = (int)inv_read(s_inv, 1), last_s = (int)inv_read(s_inv, 2);
     const size_t out_cstride = (size_t)inv_read(s_inv, 3) | ((size_t)inv_read(s_inv, 4) << 32);
     const int Nv = (int)inv_read(s_inv, 5);        // N for use inside the sample loop
 
-    uint4 WA[NI > 0 ? NI : 1], WB[NI > 0 ? NI : 1];
-    if (NI > 0) {
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {             // slots past n_exec hold padding
-            WA[i] = make_uint4(inv_read(s_inv, 8 + 8 * i), inv_read(s_inv, 9 + 8 * i), inv_read(s_inv, 10 + 8 * i), inv_read(s_inv, 11 + 8 * i));
-            WB[i] = make_uint4(inv_read(s_inv, 12 + 8 * i), inv_read(s_inv, 13 + 8 * i), inv_read(s_inv, 14 + 8 * i), inv_read(s_inv, 15 + 8 * i));
-        }
-    }
-    const bool tracing = (K == 1 && SKIP && EXT && NI == 0) && p.trace != nullptr && valid && inst0 == p.trace_inst;
+    const bool tracing = (K == 1 && SKIP && EXT) && p.trace != nullptr && valid && inst0 == p.trace_inst;
     const int lane_rep = tid & (TAB_REPL - 1);
     float* out_s = p.out + (size_t)s_begin * N + inst0;   // this thread's slot in the current output row
     uint32_t boff = 0;                                     // byte offset of the stage buffer being consumed
@@ -582,7 +564,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                         } else if (!SKIP) vstore<K>(at(wB.w), vload<K>(pr));
                         else { float* const pl = at(wB.w); FX_EACH { if (act[k]) pl[k] = pr[k]; } }
                     }
-                    if (K == 1 && SKIP && EXT && NI == 0) {          // debug trace (fx8010_gpu_trace), compiled into one variant only
+                    if (K == 1 && SKIP && EXT) {          // debug trace (fx8010_gpu_trace), compiled into one variant only
                         if (tracing) {
                             fx8010_trace_entry e;
                             e.index = trace_pc; e.executed = act[0] ? 1 : 0;
@@ -594,11 +576,7 @@ __global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
                         ++trace_pc;
                     }
                 };
-                if (NI > 0) {
-#pragma unroll
-                    for (int i = 0; i < NI; ++i)
-                        if (i < n_exec) exec_instr(WA[i], WB[i]);
-                } else {
+                {
                     uint4 nA = prog[0], nB = prog[1];
                     for (int pc = 0; pc < n_exec; ++pc) {
                         const uint4 wA = nA, wB = nB;

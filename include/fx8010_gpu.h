@@ -246,7 +246,7 @@ typedef struct fx8010_launch_info {
     int32_t last_grid, last_block;        /* geometry of the last interpreter launch       */
     int32_t last_time_split;              /* sample segments per instance (1 = serial)     */
     int32_t last_smem_bytes;
-    int32_t kernel_variant;               /* bit0 SKIP, bit1 TRAM/noise/MACMV, bit2 stateless, bit3 sample-batched stateless kernel, bits 8..15 instances per thread, bits 16.. samples per batch */
+    int32_t kernel_variant;               /* bit0 SKIP, bit1 TRAM/noise/MACMV, bit2 stateless, bit3 instruction-major kernel, bit5 short-program kernel, bits 8..15 instances per thread, bits 16.. samples per batch */
 } fx8010_launch_info;
 FX8010_API int fx8010_gpu_get_launch_info(fx8010_gpu* h, fx8010_launch_info* out);
 
