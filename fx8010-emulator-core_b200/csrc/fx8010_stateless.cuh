@@ -1,18 +1,32 @@
-// fx8010_stateless.cuh — the sample-parallel kernel for STATELESS programs (sm_100a).
+// fx8010_stateless.cuh — the INSTRUCTION-MAJOR kernel (sm_100a): stateless programs, self recurrences, delay lines.
 //
-// A program is stateless when no sample period reads anything an earlier period wrote (no SKIP, TRAM,
-// noise or MACMV; every register it reads is either never written or written earlier in the same
-// period — decided at load time, fx8010_gpu.cu::analyse).  Its sample periods are independent, so the
-// interpreter may run them in any order.  This kernel runs them INSTRUCTION-MAJOR over mini-batches of
-// M samples: each DSP instruction is fetched from __constant__ memory and decoded once, then executed
-// for the M samples of the batch (and K adjacent instances each), which amortises the interpretive
-// overhead M-fold and gives the warp M x K independent dependency chains.  Registers the program
-// writes and reads back get one shared-memory row PER SAMPLE of the batch; registers it only reads
-// keep a single row; registers it only writes (outputs, an unobserved CCR) are stored once, on the
-// batch-final sample, for the state write-back.  INPUT registers are not copied at all: the cp.async
-// input stage rows ARE their rows (every read of an INPUT register is preceded by its preload in the
-// same instruction, reference source/FX8010.cpp:1053-1061).  The time axis is also cut into segments
-// across blockIdx.y; only the thread that owns the last sample writes state back.
+// The interpreter runs a batch of M sample periods instruction by instruction: each DSP instruction is fetched from
+// __constant__ memory and decoded once, then executed for the M samples of the batch (and K adjacent instances each),
+// which amortises the interpretive overhead M-fold.  That is loop distribution of the sample loop over the program, and
+// it keeps the reference's results (source/FX8010.cpp:1023-1249 runs sample by sample) exactly when no value flows from
+// a LATER instruction of one sample period to an EARLIER instruction of the next.  fx8010_gpu.cu::analyse decides that
+// at load time and sorts every operand read into
+//   * same period  — the producer comes earlier in program order: registers the program writes and reads back get one
+//                    shared-memory row PER SAMPLE of the batch; registers it only reads keep one row; registers it only
+//                    writes (outputs, an unobserved CCR) are stored on the batch-final sample only; INPUT registers are
+//                    not copied at all: the cp.async input stage rows ARE their rows (every read of an INPUT register
+//                    is preceded by its preload in the same instruction, :1053-1061);
+//   * self-carried — the operand is the instruction's OWN result of the previous sample period (`interp out, out, c,
+//                    in`, `macs a, a, x, y`; the register has no other writer): forwarded in a hardware register from
+//                    sample to sample, so a recurrence's dependency chain holds arithmetic only; row M - 1 carries the
+//                    value between batches and calls;
+//   * TRAM         — (TRAM = true) one READ and one WRITE per ring, offsets from registers the program never writes:
+//                    both pointers advance by one per sample period (:909-967), so the slot a READ fetches was written a
+//                    constant number of periods earlier.  The READs of batch b + 1 are prefetched with cp.async while
+//                    batch b is computed (their stage rows stand in for the target register) as long as that distance
+//                    exceeds two batches — checked per thread at kernel start, voted per warp; a warp with a shorter
+//                    delay runs the same code one sample at a time with synchronous reads, which is the sequential order.
+// Programs with anything else carried across instructions, SKIP, noise or MACMV take the sample-major kernels.
+//
+// Stateless programs (nothing carried, no TRAM) are additionally cut along time into segments across blockIdx.y; only
+// the thread that owns the call's last sample writes state back, after re-running that one sample in a cold FINAL copy
+// of the code that stores everything the write-back needs.  Recurrences and delay lines run one segment with batches of
+// up to 32 samples (the batch is also how far the input stage runs ahead of the arithmetic).
 //
 // Arithmetic is the same code as the generic kernel (fx8010_kernel.cuh): bit-exact with the reference.
 #pragma once
