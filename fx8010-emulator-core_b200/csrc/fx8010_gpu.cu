@@ -732,6 +732,9 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     // half a wave per launch: with programmatic dependent launch two consecutive launches share the SMs, and
     // fewer, longer segments spend fewer instructions on per-thread start-up
     long n_seg = std::max(1L, (long)h->num_sms * occ / (2 * L.grid_x));
+    // ... a launch much longer than its own ramp-up gains nothing from sharing the SMs with its neighbours: fill
+    // them, twice over so that the tail balances
+    if ((double)N * n_samples > 8.0 * 4096 * 1024) n_seg = std::max(1L, 2L * h->num_sms * occ / L.grid_x);
     if (h->tune_seg) n_seg = h->tune_seg;
     n_seg = std::min<long>(n_seg, std::max(1, n_samples / M));
     if (h->sl_serial) n_seg = 1;             // a recurrence cannot be cut along time
