@@ -70,6 +70,26 @@ void FX8010::processBlockDevice(const float* d_in, float* d_out, int n_samples, 
     check(fx8010_gpu_process_batch(gpu_, d_in, d_out, n_samples, stream), "process_batch");
 }
 
+void FX8010::processBlockDeviceWithControls(const float* d_in, float* d_out, int n_samples,
+                                            const std::vector<ControlChange>& changes, void* stream) {
+    ensureUploaded();
+    std::vector<fx8010_control_event> ev;
+    std::vector<float> vals(changes.size());
+    for (size_t i = 0; i < changes.size(); ++i) {
+        const int reg = front_.findRegister(changes[i].key);
+        if (reg < 0) throw std::runtime_error("FX8010: unknown register '" + changes[i].key + "'");
+        vals[i] = changes[i].value;
+        ev.push_back(fx8010_control_event{changes[i].sample, reg, 1, 0, &vals[i]});
+        front_.registers()[reg].value = changes[i].value;    // initial value of a later upload, as setRegisterValue keeps it
+    }
+    check(fx8010_gpu_process_batch_events(gpu_, d_in, d_out, n_samples, ev.data(), (int)ev.size(), stream), "process_batch_events");
+}
+
+void FX8010::processBlockDevicePlanar(const float* d_in, float* d_out, int n_samples, void* stream) {
+    ensureUploaded();
+    check(fx8010_gpu_process_batch_planar(gpu_, d_in, d_out, n_samples, stream), "process_batch_planar");
+}
+
 int FX8010::getInstructionCounter() {
     if (!gpu_ || uploaded_instrs_ == (size_t)-1) return 0;
     std::vector<unsigned long long> c((size_t)instances_);

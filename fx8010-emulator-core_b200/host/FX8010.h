@@ -58,6 +58,13 @@ public:
     void processBlock(const float* in, float* out, int n_samples);
     // same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t)
     void processBlockDevice(const float* d_in, float* d_out, int n_samples, void* stream);
+    // the driver's slider pattern (source/main.cpp:107-114) inside one block: `key` takes `value` for every instance
+    // right before sample period `sample`; DEVICE buffers, asynchronous on `stream`
+    struct ControlChange { int sample; std::string key; float value; };
+    void processBlockDeviceWithControls(const float* d_in, float* d_out, int n_samples,
+                                        const std::vector<ControlChange>& changes, void* stream);
+    // DEVICE buffers laid out [channel][instance][sample] (planar audio), asynchronous on `stream`
+    void processBlockDevicePlanar(const float* d_in, float* d_out, int n_samples, void* stream);
     unsigned long long getInstructionCounterTotal();           // summed over instances
     fx8010_gpu* gpuHandle();                                   // creates the handle / uploads the program if needed
     fx8010::Frontend& frontend() { return front_; }
