@@ -727,6 +727,10 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     L.smem = sl_smem_bytes(h, B, K, M);
     L.grid_x = (N / K + B - 1) / B;
     int occ = 1;
+    {   // (the occupancy query honours the opt-in shared-memory limit only once it is set on the function)
+        bool& attr = h->sl_attr_set[h->sl_tram ? 1 : 0][K == 4 ? 2 : (K == 2 ? 1 : 0)];
+        if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(pick_sl_kernel(K, h->sl_tram), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
+    }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_sl_kernel(K, h->sl_tram), B, L.smem);
     occ = std::max(occ, 1);
     // half a wave per launch: with programmatic dependent launch two consecutive launches share the SMs, and

@@ -469,8 +469,8 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
     }
     auto fetch_stream = [&](auto tc, const int nm, const uint32_t boff) {
         constexpr int t = decltype(tc)::value;
-        const int size = cx.rsize[t];
         const float* const ring = cx.ring[t];
+        const float* const ring_end = ring + (size_t)cx.rsize[t] * N;
         unsigned char* d = reinterpret_cast<unsigned char*>(at(p.tr_stage[t] + boff));
         for (int m = 0; m < nm; ++m, d += row_bytes) {
             if (K > 1 && tr_same[t]) cp_async<4 * K>(d, tr_ptr[t][0]);
@@ -479,10 +479,9 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
                 for (int k = 0; k < K; ++k) cp_async<4>(d + 4 * k, tr_ptr[t][k]);
             }
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const bool wrap = (++tr_next[t][k] == size);
-                tr_next[t][k] = wrap ? 0 : tr_next[t][k];
-                tr_ptr[t][k] = wrap ? ring + k : tr_ptr[t][k] + N;
+            for (int k = 0; k < K; ++k) {                  // (the address itself tells where the ring ends: no index to keep)
+                const float* const nx = tr_ptr[t][k] + N;
+                tr_ptr[t][k] = (nx == ring_end + k) ? ring + k : nx;
             }
         }
     };
