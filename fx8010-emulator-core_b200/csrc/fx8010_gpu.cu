@@ -40,7 +40,7 @@ std::mutex g_mutex;
 bool g_slot_used[MAX_DEVICES][PROG_SLOTS];
 thread_local std::string g_create_error;
 
-struct Launch { int K, B, n_seg, seg_len, grid_x; size_t smem; int M; int chunk; };   // M > 0: stateless kernel, samples per batch
+struct Launch { int K, B, n_seg, seg_len, grid_x; size_t smem; int M; int chunk; int P; };   // M > 0: instruction-major kernel, samples per batch; P: threads sharing one instance column (they split each batch's samples), blockDim = B * P
 struct PlanKey { int ns = -1; unsigned align = 0; };
 enum RowClass { ROW_NONE = 0, ROW_RO, ROW_WO, ROW_RW, ROW_IN, ROW_TR };
 
@@ -124,7 +124,7 @@ struct fx8010_gpu {
     size_t stage_floats = 0;
     unsigned long long pipe_seq = 0;             // sub-blocks pushed through the staging buffers so far
     // tuning overrides (0 = heuristic)
-    int tune_K = 0, tune_B = 0, tune_seg = 0, tune_sub = 0;
+    int tune_K = 0, tune_B = 0, tune_seg = 0, tune_sub = 0, tune_P = 0, use_split = 1;
     std::string err;
     fx8010_launch_info info = {};
 };
@@ -673,7 +673,7 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     while (!fits(B, K) && K > 1) K >>= 1;
     while (!fits(B, K) && B > 32) B >>= 1;
     if (!fits(B, K)) return fail(h, FX8010_ERR_CAPACITY, "register file does not fit in shared memory");
-    L.K = K; L.B = B; L.chunk = chunk;
+    L.K = K; L.B = B; L.chunk = chunk; L.P = 1;
     L.smem = smem(B, K, chunk);
     L.grid_x = (N / K + B - 1) / B;
     L.n_seg = 1; L.seg_len = n_samples;
@@ -705,8 +705,10 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     };
     int K = 4;
     while (K > 1 && !aligned(K)) K >>= 1;
+    bool splittable = h->sl_serial && h->sl_tram && h->use_split;     // (see the sample split below)
+    for (uint8_t c : h->sl_carry) splittable = splittable && !c;
     if (h->sl_serial)                        // one time segment: the warps come from the instances alone — keep two per SM at least
-        while (K > 1 && (long)N / K / 32 < 2L * h->num_sms) K >>= 1;   // (cfg4, 65 536 instances: K = 4 147 us, K = 2 158 us, K = 1 155 us)
+        while (K > 1 && (long)N / K / 32 * (splittable ? 4 : 1) < 2L * h->num_sms * (splittable ? 2 : 1)) K >>= 1;   // (cfg4, 65 536 instances: K = 4 147 us, K = 2 158 us, K = 1 155 us; cfg3 with the split: K = 2 156 us, K = 1 180 us)
     if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
     // time-split launches: 64-thread blocks with batches of 8 samples (decode amortised over twice the samples at the
     // same shared-memory footprint as 128 x 4; cfg2: 8.7 vs 9.2 us)
@@ -723,7 +725,17 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     if (h->sl_serial && M < 2) M = 2;        // a carried operand reads row (m - 1) mod M while row m is written
     while (sl_smem_bytes(h, B, K, M) > h->smem_optin && B > 32) B >>= 1;
     if (sl_smem_bytes(h, B, K, M) > h->smem_optin) return fail(h, FX8010_ERR_CAPACITY, "register file does not fit in shared memory");
-    L.K = K; L.B = B; L.M = M; L.chunk = 0;
+    // Sample split: a serial program whose only state across sample periods is TRAM (nothing carried in registers) has
+    // independent samples inside a batch, so P threads can share one instance column and take M / P samples each — P
+    // times the warps for the same instances (cfg3: 16 384 instances are 512 warps otherwise, less than one per scheduler).
+    int P = 1;
+    bool any_carry = false;
+    for (uint8_t c : h->sl_carry) any_carry = any_carry || c;
+    if (h->sl_serial && h->sl_tram && !any_carry && h->use_split) {
+        while (P < 8 && (long)((N / K + 31) / 32) * P < 8L * h->num_sms && B * P * 2 <= 128 && M / (P * 2) >= 4) P <<= 1;
+        if (h->tune_P && (h->tune_P & (h->tune_P - 1)) == 0 && B * h->tune_P <= 128 && M / h->tune_P >= 1) P = h->tune_P;
+    }
+    L.K = K; L.B = B; L.M = M; L.chunk = 0; L.P = P;
     L.smem = sl_smem_bytes(h, B, K, M);
     L.grid_x = (N / K + B - 1) / B;
     int occ = 1;
@@ -801,7 +813,7 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
                        !overlap(in_lo, in_hi, q.out_lo, q.out_hi) && !overlap(out_lo, out_hi, q.in_lo, q.in_hi);
         const int late_wait = (h->use_pdl && h->stateless && disjoint) ? 1 : 0;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(L.grid_x, L.n_seg); cfg.blockDim = dim3(L.B); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+        cfg.gridDim = dim3(L.grid_x, L.n_seg); cfg.blockDim = dim3(L.B * L.P); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
         cudaLaunchAttribute attrs[1];
         attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attrs[0].val.programmaticStreamSerializationAllowed = 1;
@@ -821,7 +833,13 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             p.acc_writer = h->acc_writer ? 1 : 0;
             p.ccr_live = h->sl_ccr_live ? 1 : 0;
             p.ptrs = h->d_ptrs; p.itram = h->d_itram; p.xtram = h->d_xtram; p.itram_size = h->itram_size; p.xtram_size = h->xtram_size;
-            p.has_tram = h->sl_tram ? 1 : 0; p.n_tr = h->sl_n_tr;
+            p.has_tram = h->sl_tram ? 1 : 0; p.n_tr = h->sl_n_tr; p.P = L.P;
+            for (int j = 0; j < 4; ++j) p.tr_ops[j] = 0;
+            for (const fx8010_instr& in : h->instrs) {           // pointer j (iw, ir, xw, xr) moves once per sample period per executed op
+                const Uop u = uop_of(h, in);
+                if (u == U_IWRITE) p.tr_ops[0]++; else if (u == U_IREAD) p.tr_ops[1]++;
+                else if (u == U_XWRITE) p.tr_ops[2]++; else if (u == U_XREAD) p.tr_ops[3]++;
+            }
             p.tr_on[0] = p.tr_on[1] = 0;
             for (int q = 0; q < h->sl_n_tr; ++q) {
                 const fx8010_gpu::TramStream& t = h->sl_tr[q];
@@ -866,7 +884,7 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
         h->prev[0].out_lo = out_lo; h->prev[0].out_hi = out_hi; h->prev[0].in_lo = in_lo; h->prev[0].in_hi = in_hi;
         h->prev[0].stream = st; h->prev[0].valid = true;
         h->info.kernel_launches++;
-        h->info.last_grid = L.grid_x * L.n_seg; h->info.last_block = L.B; h->info.last_time_split = L.n_seg;
+        h->info.last_grid = L.grid_x * L.n_seg; h->info.last_block = L.B * L.P; h->info.last_time_split = L.n_seg;
         h->info.last_smem_bytes = (int)L.smem;
         h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | ((L.M == 0 && use_short_kernel(h)) ? 32 : 0) | (L.K << 8) | (L.M << 16);
     }
@@ -929,6 +947,8 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     if (getenv("FX8010_NO_SHORT")) h->use_short = 0;
     if (getenv("FX8010_NO_CARRY")) h->use_carry = 0;
     if (getenv("FX8010_NO_TRAM_IM")) h->use_tram_im = 0;
+    if (getenv("FX8010_NO_SPLIT")) h->use_split = 0;
+    h->tune_P = env_int("FX8010_TUNE_P");
     h->tune_M = env_int("FX8010_TUNE_M");
     h->tune_chunk = env_int("FX8010_TUNE_CHUNK");
     if (h->tune_chunk & (h->tune_chunk - 1) || h->tune_chunk > MAX_CHUNK) h->tune_chunk = 0;

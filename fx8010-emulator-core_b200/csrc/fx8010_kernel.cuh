@@ -247,7 +247,7 @@ __host__ __device__ inline uint32_t stage_offset(int n_regs, int C, int c, int R
 //   EXT : the program uses TRAM, the noise LFSR or MACMV (their state stays out of the registers
 //         of simpler programs)
 template <int K, bool SKIP, bool EXT>
-__global__ void __launch_bounds__(128) fx_interp_kernel(const Params p) {
+__global__ void __launch_bounds__(128, 3) fx_interp_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int B = blockDim.x;
     const int tid = threadIdx.x;

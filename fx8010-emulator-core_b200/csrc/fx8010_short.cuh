@@ -41,7 +41,7 @@ template <int K> __device__ __forceinline__ void stg_if(uint32_t pred, float* p,
 
 // grid = (ceil(N / (K * B)), n_seg), block = B threads; same shared-memory layout and encoding as fx_interp_kernel.
 template <int K, bool EXT, int NI>
-__global__ void __launch_bounds__(128) fx_short_kernel(const Params p) {
+__global__ void __launch_bounds__(128, 3) fx_short_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int B = blockDim.x;
     const int tid = threadIdx.x;

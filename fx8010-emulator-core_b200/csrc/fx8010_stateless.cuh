@@ -74,6 +74,8 @@ struct SLParams {
     float* itram; float* xtram; // [size][N]
     int itram_size, xtram_size;
     int has_tram, n_tr;
+    int P;                      // threads per instance column: each takes M / P samples of every batch (1 unless the program's only state is TRAM)
+    int tr_ops[4];              // executed TRAM ops per sample period that move pointer iw, ir, xw, xr (0 or 1 each)
     int tr_on[2];               // TRAM t (0 = iTRAM, 1 = xTRAM) has a READ stream
     uint32_t tr_stage[2];       // byte offset of the stream's stage rows [2 buffers][M]
     uint32_t tr_y[2];           // byte offset of the row holding the READ's offset operand
@@ -248,9 +250,7 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
 #define SL_TRAM_READ(T)                                                                                          \
         if (TRAM && !FINAL) {                                                                                    \
             const int size = cx.rsize[T];                                                                        \
-            if (cx.tram_fast) {    /* the rows were prefetched with the batch: only the pointer moves */         \
-                SL_EACH { int32_t& rp = cx.tp[2 * T + 1][k]; rp += n_m; rp -= (rp >= size) ? size : 0; }         \
-            } else {                                                                                             \
+            if (!cx.tram_fast) {   /* (else the rows were prefetched with the batch; the kernel moves the pointers) */ \
                 const float* const ring = cx.ring[T];                                                            \
                 for (int m = 0; m < n_m; ++m, I.qa += I.sa) {                                                    \
                     Vec<K> v;                                                                                    \
@@ -342,10 +342,12 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
 }
 
 template <int K, bool TRAM>
-__global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
+__global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int B = blockDim.x;
-    const int tid = threadIdx.x;
+    const int P = TRAM ? p.P : 1;                      // threads per instance column; they split each batch's samples
+    const int B = blockDim.x / P;                      // instance threads (columns) per block
+    const int part = TRAM ? (int)threadIdx.x / B : 0;  // this thread's share of every batch: samples [part, part + 1) * M / P
+    const int tid = TRAM ? (int)threadIdx.x - part * B : (int)threadIdx.x;
     const int N = p.N, C = p.C, M = p.M;
     const int tslot_raw = blockIdx.x * B + tid;
     const bool valid = tslot_raw * K < N;
@@ -355,6 +357,7 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
     const int s_end = min(p.n_samples, s_begin + p.seg_len);
     const uint32_t row_bytes = (uint32_t)B * K * 4u;
     const uint32_t buf_bytes = (uint32_t)M * row_bytes;
+    const int sub = M / P;                             // samples of a batch per thread (P divides M)
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!p.pdl_late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -363,25 +366,29 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
     unsigned char* const col = smem_raw + (size_t)p.n_smem_tabs * TAB_SMEM_BYTES + (size_t)tid * K * 4;
     auto at = [&](uint32_t byte_off) { return reinterpret_cast<float*>(col + byte_off); };
 
+    // this thread's samples [lo, hi) of a batch of nm samples
+    auto my_lo = [&](int nm) { return min(nm, part * sub); };
+    auto my_hi = [&](int nm) { return min(nm, part * sub + sub); };
+
     // input stage: batch starting at sample s0 -> buffer at byte offset boff (channel 0 unrolled)
     const bool has_in = (p.in != nullptr);
     auto fetch_batch = [&](int s0, uint32_t boff) {
         if (has_in && s0 < s_end) {
-            const int n = s_end - s0;                    // samples left (>= 1); the batch takes min(M, n)
-            const float* g = p.in + (size_t)s0 * N + inst0;
-            float* d = at(p.stage0 + boff);
-            const int nm = min(M, n);
+            const int nm = min(M, s_end - s0);
+            const int lo = my_lo(nm), hi = my_hi(nm);
+            const float* g = p.in + (size_t)(s0 + lo) * N + inst0;
+            unsigned char* d = reinterpret_cast<unsigned char*>(at(p.stage0 + boff)) + (uint32_t)lo * row_bytes;
 #pragma unroll 4
-            for (int m = 0; m < nm; ++m) cp_async<4 * K>(reinterpret_cast<unsigned char*>(d) + (uint32_t)m * row_bytes, g + (size_t)m * N);
+            for (int m = lo; m < hi; ++m, d += row_bytes, g += N) cp_async<4 * K>(d, g);
             for (int c = 1; c < C; ++c) {
-                g += p.in_cstride;
+                const float* gc = p.in + (size_t)c * p.in_cstride + (size_t)(s0 + lo) * N + inst0;
                 const uint32_t base = p.stage0 + (uint32_t)c * 2u * buf_bytes + boff;
-                for (int m = 0; m < M && m < n; ++m) cp_async<4 * K>(at(base + (uint32_t)m * row_bytes), g + (size_t)m * N);
+                for (int m = lo; m < hi; ++m, gc += N) cp_async<4 * K>(at(base + (uint32_t)m * row_bytes), gc);
             }
         }
     };
     fetch_batch(s_begin, 0);                            // (its group is committed after the TRAM streams joined it, below)
-    if (!has_in) {                                      // no input block: INPUT operands read silence (their rows are the stage rows)
+    if (!has_in && part == 0) {                         // no input block: INPUT operands read silence (their rows are the stage rows)
         Vec<K> z;
 #pragma unroll
         for (int k = 0; k < K; ++k) z[k] = 0.0f;
@@ -391,10 +398,10 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
     for (int t = 0; t < p.n_smem_tabs; ++t) {
         const TableEntry* src = p.tabs + (size_t)p.smem_tab_id[t] * FX8010_TABLE_ENTRIES;
 #pragma unroll 4
-        for (int i = tid; i < FX8010_TABLE_ENTRIES * TAB_REPL; i += B)
+        for (int i = (int)threadIdx.x; i < FX8010_TABLE_ENTRIES * TAB_REPL; i += (int)blockDim.x)
             s_tab[t * FX8010_TABLE_ENTRIES * TAB_REPL + i] = src[i / TAB_REPL];
     }
-    {   // read-only rows (controls, literals): the only state a stateless program can see
+    if (part == 0) {   // read-only rows (controls, literals) and carried-in rows: the only state such a program can see
         int j = 0;
         for (; j + 4 <= p.n_load; j += 4) {
             Vec<K> t[4];
@@ -422,16 +429,17 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
     // ---- TRAM: pointers, and the READ streams (source/FX8010.cpp:934-967) prefetched like input channels ----
     // Every executed READ / WRITE moves its pointer by one, so with one READ and one WRITE per TRAM the slot a READ
     // fetches was written a constant number of sample periods earlier (`dist`).  A batch's READs are fetched while the
-    // previous batch is still being computed: that is the same data as long as dist >= 2 M.
+    // previous batch is still being computed: that is the same data as long as dist > 2 M.
     cx.tram_fast = true;
     cx.ring[0] = p.itram + inst0; cx.ring[1] = p.xtram + inst0; cx.rsize[0] = p.itram_size; cx.rsize[1] = p.xtram_size;
-    int tr_next[2][K];                                  // ring slot of the stream's next sample to fetch
+    int32_t tp0[4][K];                                  // iw, ir, xw, xr at the start of the current batch
+    int tr_next[2][K];                                  // ring slot of the streams' first sample of the NEXT batch to fetch
     bool tr_same[2] = {true, true};
     if (TRAM && p.has_tram) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            cx.tp[0][k] = p.ptrs[inst0 + k]; cx.tp[1][k] = p.ptrs[N + inst0 + k];
-            cx.tp[2][k] = p.ptrs[2 * N + inst0 + k]; cx.tp[3][k] = p.ptrs[3 * N + inst0 + k];
+            tp0[0][k] = p.ptrs[inst0 + k]; tp0[1][k] = p.ptrs[N + inst0 + k];
+            tp0[2][k] = p.ptrs[2 * N + inst0 + k]; tp0[3][k] = p.ptrs[3 * N + inst0 + k];
         }
         bool safe = true;
 #pragma unroll
@@ -445,43 +453,53 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int pos = min(max(cvt_x86(yv[k]), 0), size - 1);
-                int nx = cx.tp[2 * t + 1][k] - pos;
+                int nx = tp0[2 * t + 1][k] - pos;
                 nx += (nx < 0) ? size : 0;
                 tr_next[t][k] = nx;
                 tr_same[t] = tr_same[t] && (nx == tr_next[t][0]);
                 if (has_w) {
                     const int wpos = min(max(cvt_x86(wv[k]), 0), size - 1);
-                    int d = (cx.tp[2 * t][k] + wpos - nx) % size;      // write slot minus read slot of the same sample
+                    int d = (tp0[2 * t][k] + wpos - nx) % size;      // write slot minus read slot of the same sample
                     d += (d < 0) ? size : 0;
                     const int dist = (d == 0 && !p.tr_wfirst[t]) ? size : d;
                     safe = safe && (dist > 2 * M);
                 }
             }
         }
-        cx.tram_fast = __all_sync(0xffffffffu, safe);
+        if (P > 1) {                                    // threads sharing a column must agree: different warps, the same instances
+            __shared__ int s_unsafe;
+            if (threadIdx.x == 0) s_unsafe = 0;
+            __syncthreads();
+            if (!safe) s_unsafe = 1;
+            __syncthreads();
+            cx.tram_fast = (s_unsafe == 0);
+        } else cx.tram_fast = __all_sync(0xffffffffu, safe);
     }
-    // running global addresses of the streams' next sample (one add per sample, a reset where the ring wraps)
-    const float* tr_ptr[2][K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        tr_ptr[0][k] = cx.ring[0] + (size_t)(TRAM && p.tr_on[0] ? tr_next[0][k] : 0) * N + k;
-        tr_ptr[1][k] = cx.ring[1] + (size_t)(TRAM && p.tr_on[1] ? tr_next[1][k] : 0) * N + k;
-    }
+    // fetches this thread's rows [lo, hi) of a batch of nm samples of stream t, then moves the stream on by the batch
     auto fetch_stream = [&](auto tc, const int nm, const uint32_t boff) {
         constexpr int t = decltype(tc)::value;
+        const int size = cx.rsize[t];
         const float* const ring = cx.ring[t];
-        const float* const ring_end = ring + (size_t)cx.rsize[t] * N;
-        unsigned char* d = reinterpret_cast<unsigned char*>(at(p.tr_stage[t] + boff));
-        for (int m = 0; m < nm; ++m, d += row_bytes) {
-            if (K > 1 && tr_same[t]) cp_async<4 * K>(d, tr_ptr[t][0]);
+        const float* const ring_end = ring + (size_t)size * N;
+        const int lo = my_lo(nm), hi = my_hi(nm);
+        const float* ptr[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            int idx = tr_next[t][k] + lo; idx -= (idx >= size) ? size : 0;      // (prefetching implies size > 2 M)
+            ptr[k] = ring + (size_t)idx * N + k;
+            tr_next[t][k] += nm; tr_next[t][k] -= (tr_next[t][k] >= size) ? size : 0;
+        }
+        unsigned char* d = reinterpret_cast<unsigned char*>(at(p.tr_stage[t] + boff)) + (uint32_t)lo * row_bytes;
+        for (int m = lo; m < hi; ++m, d += row_bytes) {
+            if (K > 1 && tr_same[t]) cp_async<4 * K>(d, ptr[0]);
             else {
 #pragma unroll
-                for (int k = 0; k < K; ++k) cp_async<4>(d + 4 * k, tr_ptr[t][k]);
+                for (int k = 0; k < K; ++k) cp_async<4>(d + 4 * k, ptr[k]);
             }
 #pragma unroll
-            for (int k = 0; k < K; ++k) {                  // (the address itself tells where the ring ends: no index to keep)
-                const float* const nx = tr_ptr[t][k] + N;
-                tr_ptr[t][k] = (nx == ring_end + k) ? ring + k : nx;
+            for (int k = 0; k < K; ++k) {                  // (the address itself tells where the ring ends)
+                const float* const nx = ptr[k] + N;
+                ptr[k] = (nx == ring_end + k) ? ring + k : nx;
             }
         }
     };
@@ -497,21 +515,45 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
 
     for (int s0 = s_begin; s0 < s_end; s0 += M, cx.out_b += out_step) {
         const int mb = min(M, s_end - s0);
+        // threads sharing a column work on different samples of the same batch: nobody starts fetching batch b + 1's
+        // TRAM reads before everybody's writes of batch b - 1 are out
+        if (TRAM && P > 1) __syncthreads();
         fetch_batch(s0 + M, cx.boff ^ buf_bytes);
         fetch_tram(s0 + M, cx.boff ^ buf_bytes);
         cp_async_commit();
         cp_async_wait<1>();
+        bool owner = true;                              // this thread computes the batch's last sample (final state, if it is the call's last)
         if (!TRAM) {
             if (p.ccr_live) sl_exec<K, false, true, TRAM>(p, cx, 0, mb);
             else sl_exec<K, false, false, TRAM>(p, cx, 0, mb);
-        } else {                                        // a TRAM delay shorter than two batches: the same code, one sample at a time
-            const int step = cx.tram_fast ? mb : 1;     // (one call site: the bulk code is instantiated once)
-            for (int m0 = 0; m0 < mb; m0 += step) {
+        } else {
+            // prefetched TRAM reads: this thread's share of the batch in one go; a delay shorter than two batches: the
+            // same code one sample at a time, by the column's first thread alone (one call site: the bulk code is
+            // instantiated once)
+            const int lo = cx.tram_fast ? my_lo(mb) : (part == 0 ? 0 : mb);
+            const int hi = cx.tram_fast ? my_hi(mb) : (part == 0 ? mb : mb);
+            const int step = cx.tram_fast ? max(1, hi - lo) : 1;
+            owner = (lo < hi) && (hi == mb);
+            for (int m0 = lo; m0 < hi; m0 += step) {
+                if (p.has_tram) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {       // TRAM pointers at sample m0 (every pointer moves tr_ops per sample period)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) cx.tp[j][k] = (tp0[j][k] + m0 * p.tr_ops[j]) % max(1, cx.rsize[j >> 1]);
+                    }
+                }
                 if (p.ccr_live) sl_exec<K, false, true, TRAM>(p, cx, m0, m0 + step);
                 else sl_exec<K, false, false, TRAM>(p, cx, m0, m0 + step);
             }
+            if (p.has_tram) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tp0[j][k] = (tp0[j][k] + mb * p.tr_ops[j]) % max(1, cx.rsize[j >> 1]);
+                }
+            }
         }
-        if (s0 + mb == p.n_samples && valid) {
+        if (s0 + mb == p.n_samples && valid && owner) {
             // This thread owns the call's last sample: leave the final state behind (cold path).
             if (p.pdl_late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // state writes follow
             sl_exec<K, true, true, TRAM>(p, cx, mb - 1, mb);
@@ -524,8 +566,8 @@ __global__ void __launch_bounds__(128) fx_stateless_kernel(const SLParams p) {
             for (int k = 0; k < K; ++k) {
                 if (p.acc_writer) p.acc[inst0 + k] = (double)cx.acc_last[k];
                 if (TRAM && p.has_tram) {
-                    p.ptrs[inst0 + k] = cx.tp[0][k]; p.ptrs[N + inst0 + k] = cx.tp[1][k];
-                    p.ptrs[2 * N + inst0 + k] = cx.tp[2][k]; p.ptrs[3 * N + inst0 + k] = cx.tp[3][k];
+                    p.ptrs[inst0 + k] = tp0[0][k]; p.ptrs[N + inst0 + k] = tp0[1][k];
+                    p.ptrs[2 * N + inst0 + k] = tp0[2][k]; p.ptrs[3 * N + inst0 + k] = tp0[3][k];
                 }
                 p.counts[inst0 + k] += (unsigned long long)p.n_samples * (unsigned long long)p.n_instrs;
             }
