@@ -370,7 +370,7 @@ TRAM_CASES = {
 
 
 @pytest.mark.parametrize("name", sorted(TRAM_CASES))
-@pytest.mark.parametrize("mode", ["auto", "K4", "K2M8", "no_im"])
+@pytest.mark.parametrize("mode", ["auto", "K4", "K2M8", "no_im", "P1", "P2", "K1P4M16"])
 def test_tram_instruction_major(fx, po, name, mode, monkeypatch):
     if mode == "K4":
         monkeypatch.setenv("FX8010_TUNE_K", "4")
@@ -379,6 +379,12 @@ def test_tram_instruction_major(fx, po, name, mode, monkeypatch):
         monkeypatch.setenv("FX8010_TUNE_M", "8")
     elif mode == "no_im":
         monkeypatch.setenv("FX8010_NO_TRAM_IM", "1")
+    elif mode[0] == "P":        # threads per instance column (they split each batch's samples)
+        monkeypatch.setenv("FX8010_TUNE_P", mode[1:])
+    elif mode == "K1P4M16":
+        monkeypatch.setenv("FX8010_TUNE_K", "1")
+        monkeypatch.setenv("FX8010_TUNE_P", "4")
+        monkeypatch.setenv("FX8010_TUNE_M", "16")
     rng = np.random.default_rng(31)
     n = 136
     text = _tram_prog(**TRAM_CASES[name])
