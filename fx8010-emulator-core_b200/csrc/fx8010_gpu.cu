@@ -41,7 +41,7 @@ bool g_slot_used[MAX_DEVICES][PROG_SLOTS];
 thread_local std::string g_create_error;
 
 struct Launch { int K, B, n_seg, seg_len, grid_x; size_t smem; int M; int chunk; int P; };   // M > 0: instruction-major kernel, samples per batch; P: threads sharing one instance column (they split each batch's samples), blockDim = B * P
-struct PlanKey { int ns = -1; unsigned align = 0; };
+struct PlanKey { int ns = -1; unsigned align = 0; int deep = -1; };   // deep: the TRAM delays are known to allow 64-sample batches
 enum RowClass { ROW_NONE = 0, ROW_RO, ROW_WO, ROW_RW, ROW_IN, ROW_TR };
 
 }  // namespace
@@ -94,6 +94,7 @@ struct fx8010_gpu {
     int sl_n_tr = 0;
     bool sl_tram = false;                        // the program has TRAM instructions (pointers are loaded and kept)
     int use_tram_im = 1;
+    bool tram_ptrs_pristine = true;              // TRAM pointers as load_program left them (read and write pointer of a ring move in lockstep)
     bool sl_ccr_live = false;                    // the uploaded stateless encoding keeps per-sample CCR stores
     bool sl_serial = false;                      // ... with self-carried operands: one time segment, state loaded and kept
     bool acc_writer = false;                     // some instruction sets the accumulator
@@ -695,6 +696,32 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
 
 SLKernelFn pick_sl_kernel(int K, bool tram) { return sl_kernel(K, tram); }
 
+// Shortest READ-after-WRITE distance of the TRAM streams, in sample periods, when the host can tell: pointers untouched
+// since load_program (both pointers of a ring then advance in lockstep from 0) and offsets held by registers that
+// carry one known value in every instance.  0 = unknown.  (The kernel checks the real distance per thread anyway; this
+// only decides how long a batch is worth planning for.)
+int known_tram_distance(const fx8010_gpu* h) {
+    if (!h->tram_ptrs_pristine) return 0;
+    int best = 1 << 30;
+    for (const fx8010_instr& in : h->instrs) {            // a written ring shorter than a batch would see two samples of one batch in one slot
+        const Uop u = uop_of(h, in);
+        if (u == U_IWRITE) best = std::min(best, h->itram_size);
+        if (u == U_XWRITE) best = std::min(best, h->xtram_size);
+    }
+    for (int q = 0; q < h->sl_n_tr; ++q) {
+        const fx8010_gpu::TramStream& t = h->sl_tr[q];
+        if (t.w_yreg < 0) continue;                        // nobody writes this ring: any batch length is safe
+        if (!h->reg_uniform[t.yreg] || !h->reg_uniform[t.w_yreg]) return 0;
+        const int size = t.isx ? h->xtram_size : h->itram_size;
+        if (size <= 0) return 0;
+        const int pos = std::min(std::max(cvt_x86_host(h->reg_value[t.yreg]), 0), size - 1);
+        const int wpos = std::min(std::max(cvt_x86_host(h->reg_value[t.w_yreg]), 0), size - 1);
+        const int d = (wpos + pos) % size;
+        best = std::min(best, (d == 0 && !t.w_first) ? size : d);
+    }
+    return best;
+}
+
 // Geometry for the stateless kernel: all the parallelism a launch needs comes from cutting the time
 // axis, so K is as wide as alignment allows and the segment count fills exactly one wave.
 int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_cs, size_t out_cs, int n_samples, Launch& L) {
@@ -717,7 +744,10 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     if (h->sl_serial && !h->tune_B)          // one time segment: only N / K threads — spread them over the SMs
         while (B > 32 && (N / K + B - 1) / B < 2 * h->num_sms) B >>= 1;
     // A serial launch has few warps, and the batch is also how far the input stage runs ahead: make it deep.
-    int M = h->tune_M ? h->tune_M : (h->sl_serial ? SL_MAX_M : 8);
+    // (a split program decodes every instruction once per thread and batch: with a delay known to exceed two 64-sample
+    //  batches the longer batch halves that cost — cfg3: 152 -> 98 us)
+    const bool deep = splittable && known_tram_distance(h) > 2 * SL_MAX_M;
+    int M = h->tune_M ? h->tune_M : (h->sl_serial ? (deep ? SL_MAX_M : 32) : 8);
     // serial: all blocks are resident at once; give each its share of the SM's shared memory
     // (with more blocks than fit at once the launch runs in waves: 56 KiB keeps four 128-thread blocks per SM)
     const size_t budget = h->sl_serial ? std::min<size_t>(h->smem_optin, std::max<size_t>(56 * 1024, (size_t)200 * 1024 / std::max(1, ((N / K + B - 1) / B + h->num_sms - 1) / h->num_sms))) : 36 * 1024;
@@ -732,7 +762,7 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     bool any_carry = false;
     for (uint8_t c : h->sl_carry) any_carry = any_carry || c;
     if (h->sl_serial && h->sl_tram && !any_carry && h->use_split) {
-        while (P < 8 && (long)((N / K + 31) / 32) * P < 8L * h->num_sms && B * P * 2 <= 128 && M / (P * 2) >= 4) P <<= 1;
+        while (P < 8 && (long)((N / K + 31) / 32) * P < 4L * h->num_sms && B * P * 2 <= 128 && M / (P * 2) >= 8) P <<= 1;   // (each thread decodes every instruction once per batch: keep its share of the batch long)
         if (h->tune_P && (h->tune_P & (h->tune_P - 1)) == 0 && B * h->tune_P <= 128 && M / h->tune_P >= 1) P = h->tune_P;
     }
     L.K = K; L.B = B; L.M = M; L.chunk = 0; L.P = P;
@@ -774,12 +804,13 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
         float* out = d_out + (size_t)s0 * h->N;
         // the plan depends on the batch length and on how far the buffers are aligned
         const unsigned align = (unsigned)(((uintptr_t)in | (uintptr_t)out | (uintptr_t)(in_cs * 4) | (uintptr_t)(out_cs * 4)) & 15u) | (in ? 16u : 0u);
-        if (h->plan_key.ns == ns && h->plan_key.align == align) L = h->plan;
+        const int deep = (h->sl_ok && h->sl_tram) ? (known_tram_distance(h) > 2 * SL_MAX_M ? 1 : 0) : 0;
+        if (h->plan_key.ns == ns && h->plan_key.align == align && h->plan_key.deep == deep) L = h->plan;
         else {
             L.M = 0;
             const int rc = (h->sl_ok && h->use_sl && !h->trace_mode) ? plan_stateless(h, in, out, in_cs, out_cs, ns, L) : plan_launch(h, in, out, in_cs, out_cs, ns, L);
             if (rc) return rc;
-            h->plan = L; h->plan_key.ns = ns; h->plan_key.align = align;
+            h->plan = L; h->plan_key.ns = ns; h->plan_key.align = align; h->plan_key.deep = deep;
         }
         // the kernel family that will run this launch (each keeps its own constant-memory copy of the program)
         const Family fam = L.M > 0 ? sl_family(L.K) : ((use_short_kernel(h)) ? FAM_SHORT : FAM_GENERIC);
@@ -952,7 +983,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     h->tune_M = env_int("FX8010_TUNE_M");
     h->tune_chunk = env_int("FX8010_TUNE_CHUNK");
     if (h->tune_chunk & (h->tune_chunk - 1) || h->tune_chunk > MAX_CHUNK) h->tune_chunk = 0;
-    if (h->tune_M != 1 && h->tune_M != 2 && h->tune_M != 4 && h->tune_M != 8 && h->tune_M != 16 && h->tune_M != 32) h->tune_M = 0;
+    if (h->tune_M != 1 && h->tune_M != 2 && h->tune_M != 4 && h->tune_M != 8 && h->tune_M != 16 && h->tune_M != 32 && h->tune_M != 64) h->tune_M = 0;
     if (h->tune_K != 1 && h->tune_K != 2 && h->tune_K != 4) h->tune_K = 0;
     if (h->tune_B != 32 && h->tune_B != 64 && h->tune_B != 128) h->tune_B = 0;
     *out = h;
@@ -1090,7 +1121,7 @@ int fx8010_gpu_load_program(fx8010_gpu* h, const fx8010_program_image* im) {
     if (!h->wb.empty()) FX_CUDA(h, cudaMemcpy(h->d_wb, h->wb.data(), sizeof(uint32_t) * h->wb.size(), cudaMemcpyHostToDevice));
     FX_CUDA(h, cudaDeviceSynchronize());
     h->encode_dirty = true;
-    h->loaded = true;
+    h->loaded = true; h->tram_ptrs_pristine = true; h->plan_key = PlanKey();
     return FX8010_OK;
 }
 
@@ -1409,7 +1440,7 @@ int fx8010_gpu_set_scalars(fx8010_gpu* h, const double* acc, const uint32_t* lfs
     if (acc) FX_CUDA(h, cudaMemcpy(h->d_acc, acc, sizeof(double) * N, cudaMemcpyHostToDevice));
     if (lfsr) FX_CUDA(h, cudaMemcpy(h->d_lfsr, lfsr, sizeof(uint32_t) * 2 * N, cudaMemcpyHostToDevice));
     if (out_latch) FX_CUDA(h, cudaMemcpy(h->d_latch, out_latch, sizeof(float) * h->C * N, cudaMemcpyHostToDevice));
-    if (tram_ptrs) FX_CUDA(h, cudaMemcpy(h->d_ptrs, tram_ptrs, sizeof(int32_t) * 4 * N, cudaMemcpyHostToDevice));
+    if (tram_ptrs) { FX_CUDA(h, cudaMemcpy(h->d_ptrs, tram_ptrs, sizeof(int32_t) * 4 * N, cudaMemcpyHostToDevice)); h->tram_ptrs_pristine = false; }
     return FX8010_OK;
 }
 

@@ -42,7 +42,7 @@ constexpr uint32_t SL_OFF_MASK = 0xfffffu;   // [0:20)  byte offset
 constexpr int SL_STRIDE_SHIFT = 20;          // [20:31) bytes between consecutive samples of the batch, in 16-byte units
 constexpr uint32_t SL_BUF = 1u << 31;        // input-stage row: add the offset of the current stage buffer
 constexpr uint32_t F_ST_LAST = 1u << 17;     // R is never read by the program: store it on the batch-final sample only
-constexpr int SL_MAX_M = 32;             // a serial (recurrent) launch has few warps: its batch is also how far the input stage runs ahead of the arithmetic
+constexpr int SL_MAX_M = 64;             // a serial (recurrent) launch has few warps: its batch is also how far the input stage runs ahead of the arithmetic
 constexpr int SL_CARRY_SHIFT = 18;           // w0 bits 18..20: operand A / X / Y is this instruction's OWN result of the previous sample
                                              // (a self recurrence): row (m - 1) mod M on the first sample of a batch, then forwarded
                                              // in a hardware register — the recurrence never waits for shared memory
@@ -102,6 +102,7 @@ template <int K> struct SLCtx {
     // TRAM
     int32_t tp[4][K];               // iw, ir, xw, xr of this thread's instances
     bool tram_fast;                 // the READ streams are prefetched (else: synchronous reads, one sample at a time)
+    bool split;                     // several threads share this column (P > 1): the kernel sets the pointers before every call
     float* ring[2];                 // iTRAM / xTRAM at this thread's first instance
     int rsize[2];
 };
@@ -250,7 +251,9 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
 #define SL_TRAM_READ(T)                                                                                          \
         if (TRAM && !FINAL) {                                                                                    \
             const int size = cx.rsize[T];                                                                        \
-            if (!cx.tram_fast) {   /* (else the rows were prefetched with the batch; the kernel moves the pointers) */ \
+            if (cx.tram_fast) {    /* the rows were prefetched with the batch: only the pointer moves (a split column's pointers are set by the kernel) */ \
+                if (!cx.split) { SL_EACH { int32_t& rp = cx.tp[2 * T + 1][k]; rp += n_m; rp -= (rp >= size) ? size : 0; } } \
+            } else {                                                                                             \
                 const float* const ring = cx.ring[T];                                                            \
                 for (int m = 0; m < n_m; ++m, I.qa += I.sa) {                                                    \
                     Vec<K> v;                                                                                    \
@@ -339,6 +342,13 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
 #undef SL_ADDR
 #undef SL_ADDR_C
     }
+}
+
+// (x + inc) mod size for 0 <= x < size, inc >= 0; rings longer than the increment (the common case) need no division
+__device__ __forceinline__ int ring_add(int x, int inc, int size) {
+    x += inc;
+    if (size > inc) return x - ((x >= size) ? size : 0);
+    return size > 0 ? x % size : 0;
 }
 
 template <int K, bool TRAM>
@@ -431,6 +441,7 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
     // fetches was written a constant number of sample periods earlier (`dist`).  A batch's READs are fetched while the
     // previous batch is still being computed: that is the same data as long as dist > 2 M.
     cx.tram_fast = true;
+    cx.split = TRAM && P > 1;
     cx.ring[0] = p.itram + inst0; cx.ring[1] = p.xtram + inst0; cx.rsize[0] = p.itram_size; cx.rsize[1] = p.xtram_size;
     int32_t tp0[4][K];                                  // iw, ir, xw, xr at the start of the current batch
     int tr_next[2][K];                                  // ring slot of the streams' first sample of the NEXT batch to fetch
@@ -440,6 +451,8 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
         for (int k = 0; k < K; ++k) {
             tp0[0][k] = p.ptrs[inst0 + k]; tp0[1][k] = p.ptrs[N + inst0 + k];
             tp0[2][k] = p.ptrs[2 * N + inst0 + k]; tp0[3][k] = p.ptrs[3 * N + inst0 + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cx.tp[j][k] = tp0[j][k];    // (a column with one thread just lets them run)
         }
         bool safe = true;
 #pragma unroll
@@ -466,6 +479,9 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
                 }
             }
         }
+        // threads sharing a column write their samples' slots in no particular order: a written ring must not be
+        // shorter than a batch (two samples of one batch would meet in one slot)
+        if (P > 1 && ((p.tr_ops[0] > 0 && cx.rsize[0] < M) || (p.tr_ops[2] > 0 && cx.rsize[1] < M))) safe = false;
         if (P > 1) {                                    // threads sharing a column must agree: different warps, the same instances
             __shared__ int s_unsafe;
             if (threadIdx.x == 0) s_unsafe = 0;
@@ -475,32 +491,44 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
             cx.tram_fast = (s_unsafe == 0);
         } else cx.tram_fast = __all_sync(0xffffffffu, safe);
     }
-    // fetches this thread's rows [lo, hi) of a batch of nm samples of stream t, then moves the stream on by the batch
+    // Running global address of each stream's next row for THIS thread (one add per row, a reset where the ring wraps);
+    // tr_skip = rows between it and the thread's first row of the next batch (the other threads' shares).
+    const float* tr_ptr[2][K];
+    int tr_skip[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        tr_ptr[0][k] = cx.ring[0] + (size_t)(TRAM && p.tr_on[0] ? tr_next[0][k] : 0) * N + k;
+        tr_ptr[1][k] = cx.ring[1] + (size_t)(TRAM && p.tr_on[1] ? tr_next[1][k] : 0) * N + k;
+    }
     auto fetch_stream = [&](auto tc, const int nm, const uint32_t boff) {
         constexpr int t = decltype(tc)::value;
-        const int size = cx.rsize[t];
         const float* const ring = cx.ring[t];
-        const float* const ring_end = ring + (size_t)size * N;
+        const size_t ring_len = (size_t)cx.rsize[t] * N;
+        const float* const ring_end = ring + ring_len;
         const int lo = my_lo(nm), hi = my_hi(nm);
-        const float* ptr[K];
+        const int skip = tr_skip[t] + lo;               // (prefetching implies size > 2 M >= skip)
+        if (skip) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            int idx = tr_next[t][k] + lo; idx -= (idx >= size) ? size : 0;      // (prefetching implies size > 2 M)
-            ptr[k] = ring + (size_t)idx * N + k;
-            tr_next[t][k] += nm; tr_next[t][k] -= (tr_next[t][k] >= size) ? size : 0;
+            for (int k = 0; k < K; ++k)
+                if (k == 0 || !tr_same[t]) {
+                    const float* q = tr_ptr[t][k] + (size_t)skip * N;
+                    tr_ptr[t][k] = (q >= ring_end + k) ? q - ring_len : q;
+                }
         }
+        tr_skip[t] = nm - hi;
         unsigned char* d = reinterpret_cast<unsigned char*>(at(p.tr_stage[t] + boff)) + (uint32_t)lo * row_bytes;
         for (int m = lo; m < hi; ++m, d += row_bytes) {
-            if (K > 1 && tr_same[t]) cp_async<4 * K>(d, ptr[0]);
+            if (K > 1 && tr_same[t]) cp_async<4 * K>(d, tr_ptr[t][0]);
             else {
 #pragma unroll
-                for (int k = 0; k < K; ++k) cp_async<4>(d + 4 * k, ptr[k]);
+                for (int k = 0; k < K; ++k) cp_async<4>(d + 4 * k, tr_ptr[t][k]);
             }
 #pragma unroll
-            for (int k = 0; k < K; ++k) {                  // (the address itself tells where the ring ends)
-                const float* const nx = ptr[k] + N;
-                ptr[k] = (nx == ring_end + k) ? ring + k : nx;
-            }
+            for (int k = 0; k < K; ++k)                    // (the address itself tells where the ring ends)
+                if (k == 0 || !tr_same[t]) {
+                    const float* const nx = tr_ptr[t][k] + N;
+                    tr_ptr[t][k] = (nx == ring_end + k) ? ring + k : nx;
+                }
         }
     };
     auto fetch_tram = [&](int s0, uint32_t boff) {
@@ -535,21 +563,21 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
             const int step = cx.tram_fast ? max(1, hi - lo) : 1;
             owner = (lo < hi) && (hi == mb);
             for (int m0 = lo; m0 < hi; m0 += step) {
-                if (p.has_tram) {
+                if (cx.split) {                         // TRAM pointers at sample m0 (every pointer moves tr_ops per sample period)
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {       // TRAM pointers at sample m0 (every pointer moves tr_ops per sample period)
+                    for (int k = 0; k < K; ++k) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) cx.tp[j][k] = (tp0[j][k] + m0 * p.tr_ops[j]) % max(1, cx.rsize[j >> 1]);
+                        for (int j = 0; j < 4; ++j) if (p.tr_ops[j]) cx.tp[j][k] = ring_add(tp0[j][k], m0 * p.tr_ops[j], cx.rsize[j >> 1]);
                     }
                 }
                 if (p.ccr_live) sl_exec<K, false, true, TRAM>(p, cx, m0, m0 + step);
                 else sl_exec<K, false, false, TRAM>(p, cx, m0, m0 + step);
             }
-            if (p.has_tram) {
+            if (cx.split) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) tp0[j][k] = (tp0[j][k] + mb * p.tr_ops[j]) % max(1, cx.rsize[j >> 1]);
+                    for (int j = 0; j < 4; ++j) if (p.tr_ops[j]) tp0[j][k] = ring_add(tp0[j][k], mb * p.tr_ops[j], cx.rsize[j >> 1]);
                 }
             }
         }
@@ -566,8 +594,8 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
             for (int k = 0; k < K; ++k) {
                 if (p.acc_writer) p.acc[inst0 + k] = (double)cx.acc_last[k];
                 if (TRAM && p.has_tram) {
-                    p.ptrs[inst0 + k] = tp0[0][k]; p.ptrs[N + inst0 + k] = tp0[1][k];
-                    p.ptrs[2 * N + inst0 + k] = tp0[2][k]; p.ptrs[3 * N + inst0 + k] = tp0[3][k];
+                    p.ptrs[inst0 + k] = cx.split ? tp0[0][k] : cx.tp[0][k]; p.ptrs[N + inst0 + k] = cx.split ? tp0[1][k] : cx.tp[1][k];
+                    p.ptrs[2 * N + inst0 + k] = cx.split ? tp0[2][k] : cx.tp[2][k]; p.ptrs[3 * N + inst0 + k] = cx.split ? tp0[3][k] : cx.tp[3][k];
                 }
                 p.counts[inst0 + k] += (unsigned long long)p.n_samples * (unsigned long long)p.n_instrs;
             }
