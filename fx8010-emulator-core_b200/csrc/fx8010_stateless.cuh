@@ -21,6 +21,9 @@
 //                    batch b is computed (their stage rows stand in for the target register) as long as that distance
 //                    exceeds two batches — checked per thread at kernel start, voted per warp; a warp with a shorter
 //                    delay runs the same code one sample at a time with synchronous reads, which is the sequential order.
+//                    When the ring is the program's only state across sample periods, the samples of a batch are
+//                    independent: P threads then share one instance column and take M / P samples of every batch each
+//                    (P times the warps for the same instances), meeting at one __syncthreads per batch.
 // Programs with anything else carried across instructions, SKIP, noise or MACMV take the sample-major kernels.
 //
 // Stateless programs (nothing carried, no TRAM) are additionally cut along time into segments across blockIdx.y; only
