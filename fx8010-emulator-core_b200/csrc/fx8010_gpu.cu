@@ -668,7 +668,9 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     if (h->tune_chunk) chunk = h->tune_chunk;
     auto smem = [&](int b, int k, int ch) { return smem_bytes(nr, C, b, k, h->n_smem_tabs, ch); };
     auto fits = [&](int b, int k) { return smem(b, k, chunk) <= h->smem_optin; };
-    while (B > 32 && ((long)((N / K + B - 1) / B) * max_seg < 2L * h->num_sms || smem(B, K, chunk) > 80 * 1024)) B >>= 1;
+    // (cfg5, K = 2: 64- and 128-thread blocks 120 ms, 32-thread blocks 128 ms — the warps of a block share instruction
+    //  and constant fetches — so shrink blocks only until every SM has one)
+    while (B > 32 && ((long)((N / K + B - 1) / B) * max_seg < (long)h->num_sms || smem(B, K, chunk) > 80 * 1024)) B >>= 1;
     if (h->tune_B) B = h->tune_B;
     while (!fits(B, K) && chunk > 4) chunk >>= 1;
     while (!fits(B, K) && K > 1) K >>= 1;
