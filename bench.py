@@ -44,7 +44,7 @@ def workload(name: str):
     if name == "cfg3":
         return progs.cfg3_delay(1000), 16384, 16, "configs[2]: idelay feedback delay line (itramsize 1000), 16384 instances x 1024-sample blocks per GPU"
     if name == "cfg4":
-        return progs.CFG4_ONEPOLE, 65536, 8, "configs[3]: INTERP one-pole low-pass bank, 65536 instances x 1024-sample blocks per GPU"
+        return progs.CFG4_ONEPOLE, 65536, 8, "configs[3]: INTERP one-pole low-pass bank, 65536 instances in total (sharded across the GPUs) x 1024-sample blocks"
     if name == "cfg5":
         return progs.cfg5_allops(), 32768, 8, "configs[4]: 512-instruction all-opcode program, 32768 instances x 1024-sample blocks per GPU"
     raise SystemExit(f"unknown config {name}")
@@ -124,24 +124,37 @@ OP_COST = {"macs": (4, 0), "macsn": (4, 0), "macints": (4, 0), "acc3": (4, 0), "
            "interp": (6, 3), "skip": (4, 0), "idelay": (0, 0), "xdelay": (0, 0), "end": (0, 0)}
 
 
+def pipe_peaks():
+    """Measured issue rates (lane-ops per clock per SM) from profiles/pipe_peaks.json (tests/pipe_peaks.cu, run on
+    a B200 of this pool); nominal 128 / 64 when the file is missing."""
+    p = os.path.join(ROOT, "profiles", "pipe_peaks.json")
+    try:
+        d = json.load(open(p))["pipes"]
+        return (min(d["fadd_f32"]["lane_ops_per_clk_per_sm"], d["fmul_f32"]["lane_ops_per_clk_per_sm"]),
+                min(d["dadd_f64"]["lane_ops_per_clk_per_sm"], d["dmul_f64"]["lane_ops_per_clk_per_sm"]),
+                "measured (profiles/pipe_peaks.json: FADD/FMUL and DADD/DMUL lane-ops per clock per SM)")
+    except Exception:
+        return 128.0, 64.0, "nominal (128 FP32 / 64 FP64 lane-ops per clock per SM)"
+
+
 def compute_roofline(text: str, executed_per_step: float, n_inst: int, step_s: float, sm_mhz: float, bytes_per: int, hbm_gbs: float):
     """SURVEY.md §8d for compute-bound programs: t_roofline = max(bytes / BW_HBM, sum FP32 ops / P32, sum FP64 ops / P64)
     with the sums from the program's opcode histogram scaled by the executed fraction (skipped instructions do no
-    arithmetic), P32 = 128 and P64 = 64 lane-ops per clock and SM at the SM clock seen during the run (nominal pipe
-    widths, not microbenchmarked)."""
+    arithmetic), P32 / P64 = the measured FP32 / FP64 issue rates per clock and SM at the SM clock seen during the run."""
     ops = [ln.split()[0] for ln in text.lower().splitlines() if ln.split() and ln.split()[0] in OP_COST]
     f32 = sum(OP_COST[o][0] for o in ops)
     f64 = sum(OP_COST[o][1] for o in ops)
     frac = executed_per_step / (len(ops) * float(n_inst) * BLOCK)          # executed / issued
     clk = (sm_mhz or 1965.0) * 1e6
-    t32 = f32 * frac * n_inst * BLOCK / (148 * 128 * clk)
-    t64 = f64 * frac * n_inst * BLOCK / (148 * 64 * clk)
+    p32, p64, src = pipe_peaks()
+    t32 = f32 * frac * n_inst * BLOCK / (148 * p32 * clk)
+    t64 = f64 * frac * n_inst * BLOCK / (148 * p64 * clk)
     thbm = bytes_per * n_inst * BLOCK / (hbm_gbs * 1e9)
     t_roof = max(t32, t64, thbm)
     return {"bound": "fp32-pipe" if t_roof == t32 else ("fp64-pipe" if t_roof == t64 else "hbm"),
             "t_roofline_us": 1e6 * t_roof, "t_measured_us": 1e6 * step_s, "frac": t_roof / step_s,
             "fp32_ops_per_sample": f32 * frac, "fp64_ops_per_sample": f64 * frac, "executed_fraction": frac,
-            "peaks": "nominal: 148 SMs x 128 FP32 / 64 FP64 lane-ops per clock at the SM clock sampled during the run"}
+            "peaks": f"{src}: {p32:.1f} FP32 / {p64:.1f} FP64 lane-ops per clock per SM x 148 SMs at the SM clock sampled during the run"}
 
 
 def ncu_traffic(cfg: str):
@@ -192,6 +205,173 @@ def cpu_reference_rate(text: str, cfg: str, target_seconds: float, threads: int)
             "dsp_instr_per_s": None, "sample": f"oracle port, {n} instances x {4096 * reps} samples on {threads} threads, {secs:.2f} s"}
 
 
+def sample_instances(n: int, k: int, rng) -> np.ndarray:
+    """Instances the oracle re-computes: first, last and middle of this rank's range, the rest random."""
+    pick = {i for i in (0, 1, n - 1, n - 2, n // 2, n // 2 - 1) if 0 <= i < n}
+    while len(pick) < min(k, n):
+        pick.add(int(rng.integers(0, n)))
+    return np.array(sorted(pick))
+
+
+def oracle_blocks(text: str, prog, idx, controls: dict, x_blocks: list):
+    """The reference (oracle/_ref) — or the C restatement when that binary is absent — over the sampled instances:
+    x_blocks[b] is [S][N]; returns (outputs per block [S][k], final registers [n_regs][k], counters [k], kind)."""
+    from oracle import pyoracle as po
+    k = len(idx)
+    if po.have_reference():
+        outs = [np.zeros((x.shape[0], k), np.float32) for x in x_blocks]
+        regs = np.zeros((len(prog.registers()), k), np.float32)
+        counts = np.zeros(k, np.uint64)
+        for j, i in enumerate(idx):
+            r = po.Reference(text)
+            assert r.loaded
+            for name, v in controls.items():
+                r.set_register(name, float(v[i]))
+            for b, x in enumerate(x_blocks):
+                outs[b][:, j] = r.process(np.ascontiguousarray(x[:, i])).ravel()
+            regs[:, j] = r.register_values()
+            counts[j] = r.instruction_counter & 0xffffffff
+        return outs, regs, counts, "reference"
+    img = po.Image(prog.instructions(), prog.registers(), prog.itram_size, prog.xtram_size, prog.controls(), prog.tables())
+    orc = po.Oracle(img, k, 1)
+    for name, v in controls.items():
+        orc.set_register(prog.reg_index(name), np.ascontiguousarray(v[idx]))
+    outs = [orc.process(np.ascontiguousarray(x[:, idx]).reshape(1, x.shape[0], k))[0] for x in x_blocks]
+    return outs, orc.registers.copy(), orc.counts.copy(), "restatement"
+
+
+class Workload:
+    """One BASELINE config on this rank: handle, controls, rotating device buffers; times blocks of 1 024 samples."""
+
+    def __init__(self, fx, torch, cfg: str, n_inst: int, local_rank: int, rank: int, itram: int = 1000):
+        self.fx, self.torch, self.cfg, self.n = fx, torch, cfg, n_inst
+        self.text, _, self.bytes_per, self.label = workload(cfg)
+        if cfg == "cfg3":
+            self.text = progs.cfg3_delay(itram)
+        self.rank, self.local_rank = rank, local_rank
+        self.prog = fx.Program(self.text)
+        assert self.prog.loaded, self.prog.errors()
+        self.controls = controls_for(cfg, self.prog, n_inst, np.random.default_rng(progs.SEED + rank))
+        self.block_bytes = 4 * n_inst * BLOCK
+        # inputs: rotate over enough buffer pairs that a step never finds its data in L2
+        self.n_bufs = max(2, -(-2 * L2_BYTES // (2 * self.block_bytes)) + 1)
+        rng = np.random.default_rng(progs.SEED + 17 * rank)
+        amp = (0.9, 0.9) if cfg == "cfg5" else (0.05, 0.99)
+        if cfg == "cfg3":
+            self.host_in = [progs.impulse_noise(n_inst, BLOCK, rng) for _ in range(2)]
+        else:
+            self.host_in = [progs.sine_bank(n_inst, BLOCK, rng, start=b * BLOCK, amp_lo=amp[0], amp_hi=amp[1]) for b in range(2)]
+        self.d_in = [torch.from_numpy(self.host_in[b % 2]).cuda() for b in range(self.n_bufs)]
+        self.d_out = [torch.empty_like(self.d_in[0]) for _ in range(self.n_bufs)]
+        self.stream = torch.cuda.Stream()
+        self.st = self.stream.cuda_stream
+        self.gpu = self.new_handle()
+
+    def new_handle(self):
+        g = self.fx.Gpu(self.n, 1, self.local_rank)
+        g.load_program(self.prog)
+        for name, v in self.controls.items():
+            g.set_controls(self.prog.reg_index(name), v)
+        return g
+
+    def pointers(self, g, steps: int, first: int = 0):
+        return g.block_pointers([self.d_in[(first + i) % self.n_bufs] for i in range(steps)],
+                                [self.d_out[(first + i) % self.n_bufs] for i in range(steps)])
+
+    def timed(self, steps: int, warmup: int, repeats: int, barrier):
+        """`repeats` timed regions of exactly `steps` blocks each through ONE fx8010_gpu_process_blocks call
+        (CUDA events on the launching stream); returns the per-region milliseconds and the launches of one region."""
+        torch, g = self.torch, self.gpu
+        warm = g.block_pointers([self.d_in[i % self.n_bufs] for i in range(max(warmup, self.n_bufs))],
+                                [self.d_out[i % self.n_bufs] for i in range(max(warmup, self.n_bufs))])
+        g.process_blocks_raw(warm, BLOCK, self.st)            # touches every buffer of the rotation
+        ptrs = self.pointers(g, steps)
+        g.process_blocks_raw(ptrs, BLOCK, self.st)            # the timed call itself, once, untimed (plan + encoding cached)
+        barrier()
+        ms, launches = [], 0
+        for _ in range(repeats):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            l0 = g.launch_info().kernel_launches
+            with torch.cuda.stream(self.stream):
+                e0.record(self.stream)
+                g.process_blocks_raw(ptrs, BLOCK, self.st)
+                e1.record(self.stream)
+            barrier()
+            ms.append(e0.elapsed_time(e1))
+            launches = g.launch_info().kernel_launches - l0
+        return ms, int(launches)
+
+    def per_call(self, steps: int, barrier, exclusive: bool):
+        """One fx8010_gpu_process_batch call per step from this Python loop (what round 1 timed)."""
+        torch, g = self.torch, self.gpu
+        g.set_option(self.fx.OPT_STREAM_EXCLUSIVE, 1 if exclusive else 0)
+        for i in range(self.n_bufs):
+            g.process_device(self.d_in[i], self.d_out[i], BLOCK, self.st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(self.stream):
+            e0.record(self.stream)
+            for i in range(steps):
+                g.process_device(self.d_in[i % self.n_bufs], self.d_out[i % self.n_bufs], BLOCK, self.st)
+            e1.record(self.stream)
+        barrier()
+        g.set_option(self.fx.OPT_STREAM_EXCLUSIVE, 0)
+        return e0.elapsed_time(e1) / steps
+
+    def isolated(self, reps: int = 10):
+        """One block alone on an idle GPU (launch + kernel + drain), microseconds."""
+        torch, g = self.torch, self.gpu
+        us = []
+        for i in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            with torch.cuda.stream(self.stream):
+                e0.record(self.stream)
+                g.process_device(self.d_in[i % self.n_bufs], self.d_out[i % self.n_bufs], BLOCK, self.st)
+                e1.record(self.stream)
+            torch.cuda.synchronize()
+            us.append(1e3 * e0.elapsed_time(e1))
+        return statistics.median(us)
+
+    def parity(self, steps: int, n_check: int = 64):
+        """The timed call again on a FRESH handle (same geometry: same instance count, block length, buffer rotation and
+        fused-launch plan), against the reference on a sample of instances: outputs of every block whose buffer
+        survives the rotation, final registers and executed-instruction counters, bit for bit."""
+        torch = self.torch
+        g = self.new_handle()
+        try:
+            rng = np.random.default_rng(progs.SEED + 1000 + self.rank)
+            idx = sample_instances(self.n, n_check, rng)
+            g.process_blocks_raw(self.pointers(g, steps), BLOCK, self.st)
+            g.synchronize(self.st)
+            outs, regs, counts, kind = oracle_blocks(self.text, self.prog, idx, self.controls, [self.host_in[(i % self.n_bufs) % 2] for i in range(steps)])
+            bad = 0
+            d_idx = torch.from_numpy(idx.astype(np.int64)).cuda()
+            survivors = range(max(0, steps - self.n_bufs), steps)
+            for i in survivors:
+                y = self.d_out[i % self.n_bufs].index_select(1, d_idx).cpu().numpy()
+                bad += int(np.count_nonzero(y.view(np.uint32) != outs[i].view(np.uint32)))
+            gr = g.registers()[:, idx]
+            bad += int(np.count_nonzero(gr.view(np.uint32) != regs.view(np.uint32)))
+            gc = g.counts()[idx]
+            bad += int(np.count_nonzero((gc & np.uint64(0xffffffff)) != (counts & np.uint64(0xffffffff))))
+            return {"checked_instances": int(len(idx)), "checked_blocks": len(list(survivors)), "blocks_run": steps, "mismatches": bad, "oracle": kind,
+                    "what": "outputs of the surviving blocks, final register file, executed-instruction counters; first/last/middle of the rank's range + random"}
+        finally:
+            g.close()
+
+    def executed_per_step(self):
+        g = self.new_handle()
+        g.process_device(self.d_in[0], self.d_out[0], BLOCK, self.st); g.synchronize(self.st)
+        c = g.count_total()
+        g.close()
+        return c
+
+    def close(self):
+        self.gpu.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,8 +380,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--instances", type=int, default=0, help="override instances per GPU")
+    ap.add_argument("--itram", type=int, default=1000, help="cfg3: ring size")
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; the median is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the cfg4 / cfg5 records of the scaling line")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -209,6 +393,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     text, n_inst, bytes_per, label = workload(args.config)
+    if args.config == "cfg3":
+        text = progs.cfg3_delay(args.itram)
+        label = label.replace("itramsize 1000", f"itramsize {args.itram}")
+    if args.config == "cfg4":
+        n_inst = max(1, n_inst // world)                  # 65 536 in total, sharded
     if args.instances:
         n_inst = args.instances
     instr_per_sample = sum(progs.opcode_histogram(text).values())
@@ -224,7 +413,6 @@ def main():
         # timed: K steps of the same bounded sample
         rng = np.random.default_rng(progs.SEED)
         ns = max(1024, int(base["value"] / threads * per_step))
-        vals = []
         if po.have_reference():
             ctl = controls_for(args.config, None, threads, rng)
             x = progs.sine_bank(threads, min(ns, 48000), rng).T.copy()
@@ -244,7 +432,7 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
                 "dsp_instr_per_s": ips,
-                "config": {"workload": label, "program_instructions_per_sample": instr_per_sample},
+                "config": {"workload": label, "instances_per_gpu": n_inst, "block_samples": BLOCK, "program_instructions_per_sample": instr_per_sample},
                 "cpu_baseline": {"value": value, "unit": "instance-samples/s", "cores": threads, "kind": kind,
                                  "sample": f"per step: {threads} threads x 1 instance x {ns} samples, one process() per sample"},
                 "e2e": {"value": value, "unit": "instance-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -260,26 +448,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     fx = importlib.import_module(PKG)
-    rng = np.random.default_rng(progs.SEED + rank)
-
-    prog = fx.Program(text)
-    assert prog.loaded, prog.errors()
-    gpu = fx.Gpu(n_inst, 1, local_rank)
-    gpu.load_program(prog)
-    for name, v in controls_for(args.config, prog, n_inst, rng).items():
-        gpu.set_controls(prog.reg_index(name), v)
-
-    # inputs: rotate over enough buffer pairs that a step never finds its data in L2
-    block_bytes = 4 * n_inst * BLOCK
-    n_bufs = max(2, -(-2 * L2_BYTES // (2 * block_bytes)) + 1)
-    if args.config == "cfg3":
-        host_in = [progs.impulse_noise(n_inst, BLOCK, rng) for _ in range(2)]
-    else:
-        host_in = [progs.sine_bank(n_inst, BLOCK, rng, start=b * BLOCK) for b in range(2)]
-    d_in = [torch.from_numpy(host_in[b % 2]).cuda() for b in range(n_bufs)]
-    d_out = [torch.empty_like(d_in[0]) for _ in range(n_bufs)]
-    stream = torch.cuda.Stream()
-    st = stream.cuda_stream
 
     def barrier():
         torch.cuda.synchronize()
@@ -287,61 +455,62 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        gpu.process_device(d_in[i % n_bufs], d_out[i % n_bufs], BLOCK, st)
-    barrier()
-    launches0 = gpu.launch_info().kernel_launches
-    count0 = gpu.count_total()
+    def max_over_ranks(v: float) -> float:
+        if world > 1:
+            t = torch.tensor([v], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+        return v
+
+    def sum_over_ranks(v: float) -> float:
+        if world > 1:
+            t = torch.tensor([v], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
+        return v
+
+    peak, peak_src = measured_peak()
+    W = Workload(fx, torch, args.config, n_inst, local_rank, rank, args.itram)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.15)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for i in range(args.steps):
-            gpu.process_device(d_in[i % n_bufs], d_out[i % n_bufs], BLOCK, st)
-        e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = gpu.launch_info().kernel_launches - launches0
+    ms_all, launches = W.timed(args.steps, args.warmup, max(1, args.repeats), barrier)
+    ms_all = [max_over_ranks(m) for m in ms_all]
+    ms = statistics.median(ms_all)
     # keep the clock sampler running over a longer window of the same work so it sees load
     if rank == 0:
+        ptrs = W.pointers(W.gpu, min(32, max(args.steps, 8)))
         t_end = time.time() + 0.4
         while time.time() < t_end:
-            for i in range(50):
-                gpu.process_device(d_in[i % n_bufs], d_out[i % n_bufs], BLOCK, st)
-            gpu.synchronize(st)
+            for _ in range(4):
+                W.gpu.process_blocks_raw(ptrs, BLOCK, W.st)
+            W.gpu.synchronize(W.st)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-    total_samples = float(n_inst) * BLOCK * args.steps * world
-    value = total_samples / (ms * 1e-3)
-    info = gpu.launch_info()
+    info = W.gpu.launch_info()
+    kernel_cfg = {"grid": info.last_grid, "block": info.last_block, "time_split": info.last_time_split, "blocks_per_launch": info.last_fused_blocks,
+                  "smem_bytes": info.last_smem_bytes, "instances_per_thread": (info.kernel_variant >> 8) & 0xff, "samples_per_batch": info.kernel_variant >> 16}
+    value = float(n_inst) * BLOCK * args.steps * world / (ms * 1e-3)
+    # the same steps as one C-ABI call per step from this Python loop, and one block alone on an idle GPU
+    per_call_ms = max_over_ranks(W.per_call(args.steps, barrier, exclusive=False))
+    per_call_excl_ms = max_over_ranks(W.per_call(args.steps, barrier, exclusive=True))
+    isolated_us = W.isolated() if rank == 0 else None
+    barrier()
+    instr_per_step = sum_over_ranks(float(W.executed_per_step()))
 
-    # executed DSP instructions (END included, skipped excluded): from the device counters
-    torch.cuda.synchronize()
-    g2 = fx.Gpu(n_inst, 1, local_rank); g2.load_program(prog)
-    for name, v in controls_for(args.config, prog, n_inst, np.random.default_rng(progs.SEED + rank)).items():
-        g2.set_controls(prog.reg_index(name), v)
-    g2.process_device(d_in[0], d_out[0], BLOCK, st); g2.synchronize(st)
-    instr_per_step = g2.count_total()
-    g2.close()
+    # ---- parity of the timed call (fresh state, same geometry) against the reference on a sample of instances
+    parity = None
+    if not args.no_parity:
+        parity = W.parity(args.steps)
+        parity["mismatches"] = int(sum_over_ranks(float(parity["mismatches"])))
+        parity["checked_instances"] = int(sum_over_ranks(float(parity["checked_instances"])))
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        pin = [fx.pinned_array((1, BLOCK, n_inst)) for _ in range(2)]
-        pout = [fx.pinned_array((1, BLOCK, n_inst)) for _ in range(2)]
-        for b in range(2):
-            pin[b][0][...] = host_in[b].reshape(1, BLOCK, n_inst)
-        e2e_steps = max(10, min(args.steps, 200))
+        gpu = W.gpu
         n_host = 4                                       # page-locked in/out pairs the steps rotate over
-        pin += [fx.pinned_array((1, BLOCK, n_inst)) for _ in range(n_host - 2)]
-        pout += [fx.pinned_array((1, BLOCK, n_inst)) for _ in range(n_host - 2)]
-        for b in range(2, n_host):
-            pin[b][0][...] = host_in[b % 2].reshape(1, BLOCK, n_inst)
+        pin = [fx.pinned_array((1, BLOCK, n_inst)) for _ in range(n_host)]
+        pout = [fx.pinned_array((1, BLOCK, n_inst)) for _ in range(n_host)]
+        for b in range(n_host):
+            pin[b][0][...] = W.host_in[b % 2].reshape(1, BLOCK, n_inst)
+        e2e_steps = max(10, min(args.steps, 200))
 
         def e2e_run(wait):
             for i in range(3):
@@ -352,46 +521,81 @@ def main():
                 gpu.process_host_ptr(pin[i % n_host][0].ctypes.data, pout[i % n_host][0].ctypes.data, BLOCK, wait=wait)
             gpu.synchronize(None)                        # every step's output has reached host memory
             barrier()
-            dt = time.perf_counter() - t0
-            if world > 1:
-                t = torch.tensor([dt], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
-            return dt
+            return max_over_ranks(time.perf_counter() - t0)
         dt_sync = e2e_run(True)                          # one blocking call per step
-        dt = e2e_run(False)                              # queued calls: copies of consecutive steps overlap
+        dt = statistics.median([e2e_run(False) for _ in range(3)])    # queued calls: copies of consecutive steps overlap
         e2e = {"value": float(n_inst) * BLOCK * e2e_steps * world / dt, "unit": "instance-samples/s",
-               "h2d_bytes_per_step": block_bytes, "d2h_bytes_per_step": block_bytes, "steps": e2e_steps,
+               "h2d_bytes_per_step": W.block_bytes, "d2h_bytes_per_step": W.block_bytes, "steps": e2e_steps,
                "ms_per_step": 1e3 * dt / e2e_steps, "host_buffers": "pinned (fx8010_gpu_host_alloc)",
-               "api": "fx8010_gpu_process_batch_host_async per step + one fx8010_gpu_synchronize",
+               "api": "fx8010_gpu_process_batch_host_async per step + one fx8010_gpu_synchronize (median of 3 runs)",
+               "pcie_gbs_each_way_per_gpu": W.block_bytes * e2e_steps / dt / 1e9,
                "blocking_call_value": float(n_inst) * BLOCK * e2e_steps * world / dt_sync,
                "blocking_call_ms_per_step": 1e3 * dt_sync / e2e_steps}
+        del pin, pout
+    W.close()
 
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        alg_bytes = bytes_per * n_inst * BLOCK
-        launch_ms = ms / max(1, launches)
-        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-        line = {"metric": "instance_samples_per_s", "value": value, "unit": "instance-samples/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-                "dsp_instr_per_s": instr_per_step * world * args.steps / (ms * 1e-3),
-                "config": {"workload": label, "instances_per_gpu": n_inst, "block_samples": BLOCK,
-                           "program_instructions_per_sample": instr_per_sample,
-                           "l2": f"rotating {n_bufs} input/output buffer pairs ({2 * n_bufs * block_bytes >> 20} MiB > 126 MiB L2)",
-                           "kernel": {"grid": info.last_grid, "block": info.last_block, "time_split": info.last_time_split,
-                                      "smem_bytes": info.last_smem_bytes, "instances_per_thread": (info.kernel_variant >> 8) & 0xff, "samples_per_batch": info.kernel_variant >> 16}},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": ncu_traffic(args.config), "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": 1e3 * launch_ms},
-                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}
-        if args.config == "cfg5":        # compute-bound program: the arithmetic roofline of SURVEY.md §8d beside the HBM one
-            line["compute_roofline"] = compute_roofline(text, instr_per_step, n_inst, 1e-3 * ms / args.steps,
-                                                        (clocks or {}).get("sm_mhz"), bytes_per, peak)
-        if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_reference_rate(text, args.config, 10.0, os.cpu_count() or 1)
-        print(json.dumps(line))
-    gpu.close()
+    # ---- the configs BASELINE.json shards over the GPUs, at their per-GPU share: cfg4 = 65 536 instances
+    # in total, cfg5 = 32 768 per GPU; same timing rules, fewer steps (one cfg5 block takes tens of milliseconds)
+    sharded = None
+    if not args.no_sharded and args.config == "cfg2":
+        sharded = {}
+        for cfg, n_cfg, k_steps in (("cfg4", max(1, 65536 // world), 20), ("cfg5", 32768, 3)):
+            t_cfg, _, b_cfg, l_cfg = workload(cfg)
+            Wc = Workload(fx, torch, cfg, n_cfg, local_rank, rank)
+            m_all, l_n = Wc.timed(k_steps, 3, 3, barrier)
+            m = statistics.median([max_over_ranks(v) for v in m_all])
+            par = Wc.parity(2 if cfg == "cfg5" else k_steps, 32)
+            par["mismatches"] = int(sum_over_ranks(float(par["mismatches"])))
+            par["checked_instances"] = int(sum_over_ranks(float(par["checked_instances"])))
+            ex = sum_over_ranks(float(Wc.executed_per_step()))
+            step_s = 1e-3 * m / k_steps
+            rec = {"workload": l_cfg, "instances_per_gpu": n_cfg, "instances_total": n_cfg * world, "steps": k_steps, "ms_per_step": 1e3 * step_s,
+                   "value": float(n_cfg) * BLOCK * world / step_s, "unit": "instance-samples/s", "dsp_instr_per_s": ex / step_s,
+                   "hbm_frac": b_cfg * n_cfg * BLOCK / step_s / 1e9 / peak, "gpu_launches": l_n, "parity": par}
+            if cfg == "cfg5":
+                rec["compute_roofline"] = compute_roofline(t_cfg, ex / world, n_cfg, step_s, (clocks or {}).get("sm_mhz") if clocks else None, b_cfg, peak)
+            sharded[cfg] = rec
+            Wc.close()
+
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        return
+    alg_bytes = bytes_per * n_inst * BLOCK * args.steps / max(1, launches)      # one launch covers steps / launches blocks
+    launch_ms = ms / max(1, launches)
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    line = {"metric": "instance_samples_per_s", "value": value, "unit": "instance-samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.config == "cfg4" else "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "dsp_instr_per_s": instr_per_step * args.steps / (ms * 1e-3),
+            "config": {"workload": label, "instances_per_gpu": n_inst, "block_samples": BLOCK,
+                       "program_instructions_per_sample": instr_per_sample,
+                       "l2": f"rotating {W.n_bufs} input/output buffer pairs ({2 * W.n_bufs * W.block_bytes >> 20} MiB > 126 MiB L2), every one touched during warm-up",
+                       "timed_call": f"one fx8010_gpu_process_blocks call of {args.steps} blocks per timed region ({launches} kernel launches), median of {len(ms_all)} regions",
+                       "kernel": kernel_cfg},
+            "timed_regions_ms": ms_all,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.config), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": 1e3 * launch_ms,
+                         "blocks_per_launch": args.steps / max(1, launches)},
+            "per_call": {"what": "the same steps as one fx8010_gpu_process_batch call per step from the Python loop",
+                         "ms_per_step": per_call_ms, "hbm_frac": bytes_per * n_inst * BLOCK / (per_call_ms * 1e-3) / 1e9 / peak,
+                         "ms_per_step_stream_exclusive": per_call_excl_ms,
+                         "hbm_frac_stream_exclusive": bytes_per * n_inst * BLOCK / (per_call_excl_ms * 1e-3) / 1e9 / peak,
+                         "isolated_launch_us": isolated_us},
+            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "parity": parity}
+    if sharded:
+        line["sharded"] = sharded
+    if args.config == "cfg5":        # compute-bound program: the arithmetic roofline of SURVEY.md §8d beside the HBM one
+        line["compute_roofline"] = compute_roofline(text, instr_per_step / world, n_inst, 1e-3 * ms / args.steps,
+                                                    (clocks or {}).get("sm_mhz"), bytes_per, peak)
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_rate(text, args.config, 10.0, os.cpu_count() or 1)
+    print(json.dumps(line))
+    bad = (parity or {}).get("mismatches", 0) + sum(r["parity"]["mismatches"] for r in (sharded or {}).values())
+    if bad:
+        raise SystemExit(f"bench.py: GPU results differ from the reference ({bad} mismatching values)")
 
 
 if __name__ == "__main__":

@@ -23,6 +23,7 @@ HOST_SO = os.path.join(HERE, "libfx8010_host.so")
 
 STATUS = {0: "OK", 1: "ERR_ARG", 2: "ERR_CUDA", 3: "ERR_NO_PROGRAM", 4: "ERR_PROGRAM", 5: "ERR_CAPACITY"}
 RT_END_SKIPPED_CAP, RT_TABLE_RANGE = 1, 2
+OPT_STREAM_EXCLUSIVE = 1
 
 
 class FxError(RuntimeError):
@@ -60,7 +61,8 @@ class CControlEvent(C.Structure):
 
 class CLaunchInfo(C.Structure):
     _fields_ = [("kernel_launches", C.c_ulonglong), ("last_grid", C.c_int32), ("last_block", C.c_int32),
-                ("last_time_split", C.c_int32), ("last_smem_bytes", C.c_int32), ("kernel_variant", C.c_int32)]
+                ("last_time_split", C.c_int32), ("last_smem_bytes", C.c_int32), ("last_late_wait", C.c_int32),
+                ("last_fused_blocks", C.c_int32), ("kernel_variant", C.c_int32)]
 
 
 TRACE_DTYPE = np.dtype([("index", np.int32), ("executed", np.int32), ("r", np.float32), ("a", np.float32), ("x", np.float32),
@@ -85,6 +87,8 @@ GPU_SYMBOLS = {
     "fx8010_gpu_set_controls_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "fx8010_gpu_get_register": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "fx8010_gpu_process_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "fx8010_gpu_process_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "fx8010_gpu_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "fx8010_gpu_process_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fx8010_gpu_process_batch_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fx8010_gpu_host_alloc": (C.c_void_p, [C.c_size_t]),
@@ -387,6 +391,24 @@ class Gpu:
 
     def process_device(self, d_in, d_out, n_samples: int, stream=None):
         self._check(self.L.fx8010_gpu_process_batch(self.h, _ptr(d_in), _ptr(d_out), n_samples, stream))
+
+    def process_blocks(self, d_ins, d_outs, n_samples: int, stream=None):
+        """Consecutive blocks in one call: d_ins / d_outs are sequences of device buffers (d_ins may be None)."""
+        nb = len(d_outs)
+        outs = (C.c_void_p * max(1, nb))(*[_ptr(o) for o in d_outs])
+        ins = None if d_ins is None else (C.c_void_p * max(1, nb))(*[_ptr(i) for i in d_ins])
+        self._check(self.L.fx8010_gpu_process_blocks(self.h, ins, outs, nb, n_samples, stream))
+
+    def block_pointers(self, d_ins, d_outs):
+        """Pointer arrays for process_blocks_raw (built once, reused across calls)."""
+        nb = len(d_outs)
+        return (None if d_ins is None else (C.c_void_p * nb)(*[_ptr(i) for i in d_ins])), (C.c_void_p * nb)(*[_ptr(o) for o in d_outs]), nb
+
+    def process_blocks_raw(self, ptrs, n_samples: int, stream=None):
+        self._check(self.L.fx8010_gpu_process_blocks(self.h, ptrs[0], ptrs[1], ptrs[2], n_samples, stream))
+
+    def set_option(self, option: int, value: int):
+        self._check(self.L.fx8010_gpu_set_option(self.h, option, value))
 
     def process_device_events(self, d_in, d_out, n_samples: int, events, stream=None):
         """events: iterable of (sample, reg_index, value) with value a float (broadcast) or an array of N floats."""

@@ -22,8 +22,8 @@ KernelFn generic_kernel(int K, bool skip, bool ext);
 KernelFn short_kernel(int K, bool ext, int ni);
 // fx_stateless_kernel<K, TRAM>  (k_sl1.cu, k_sl2.cu, k_sl4.cu)
 SLKernelFn sl_kernel(int K, bool tram);
-// copies `bytes` of an encoding into program slot `slot` of the family's constant memory
-cudaError_t upload_program(Family f, const uint4* src, size_t bytes, int slot, cudaStream_t st);
+// copies `bytes` of an encoding to word `word_off` of the family's constant-memory arena
+cudaError_t upload_program(Family f, const uint4* src, size_t bytes, int word_off, cudaStream_t st);
 inline Family sl_family(int K) { return K == 4 ? FAM_SL4 : (K == 2 ? FAM_SL2 : FAM_SL1); }
 
 constexpr int SH_MAX_NI_HOST = 4;   // == SH_MAX_NI of fx8010_short.cuh (static_assert there)

@@ -21,13 +21,13 @@ using namespace fxk;
 
 namespace fxk {
 SLKernelFn sl_kernel(int K, bool tram) { return K == 4 ? sl_kernel_4(tram) : (K == 2 ? sl_kernel_2(tram) : sl_kernel_1(tram)); }
-cudaError_t upload_program(Family f, const uint4* src, size_t bytes, int slot, cudaStream_t st) {
+cudaError_t upload_program(Family f, const uint4* src, size_t bytes, int word_off, cudaStream_t st) {
     switch (f) {
-    case FAM_GENERIC: return upload_generic(src, bytes, slot, st);
-    case FAM_SHORT: return upload_short(src, bytes, slot, st);
-    case FAM_SL1: return upload_sl1(src, bytes, slot, st);
-    case FAM_SL2: return upload_sl2(src, bytes, slot, st);
-    default: return upload_sl4(src, bytes, slot, st);
+    case FAM_GENERIC: return upload_generic(src, bytes, word_off, st);
+    case FAM_SHORT: return upload_short(src, bytes, word_off, st);
+    case FAM_SL1: return upload_sl1(src, bytes, word_off, st);
+    case FAM_SL2: return upload_sl2(src, bytes, word_off, st);
+    default: return upload_sl4(src, bytes, word_off, st);
     }
 }
 }  // namespace fxk
@@ -36,12 +36,21 @@ namespace {
 
 constexpr int MAX_DEVICES = 64;
 constexpr int HOST_PIPE_BUFS = 3;
-std::mutex g_mutex;
-bool g_slot_used[MAX_DEVICES][PROG_SLOTS];
+constexpr int MAX_CHAIN = 16;            // late-waiting launches that may follow one another before a launch waits at its start again
 thread_local std::string g_create_error;
 
+// Constant-memory residency: the decoded programs of a device's handles share one arena per kernel family
+// (c_prog, fx8010_kernel.cuh).  A handle's range is allocated first-fit when it is about to launch; when the arena
+// is full the least recently launched programs are evicted (after a device synchronise: their kernels may still
+// be reading them) and simply uploaded again by their owner's next launch.  g_dev_mutex[device] is held from the
+// residency check to the kernel launch, so a program cannot lose its range between the two.
+struct ArenaBlock { int off, words; fx8010_gpu* owner; unsigned long long stamp; };
+std::mutex g_dev_mutex[MAX_DEVICES];
+std::vector<ArenaBlock> g_arena[MAX_DEVICES][FAM_COUNT];
+unsigned long long g_arena_stamp[MAX_DEVICES];
+
 struct Launch { int K, B, n_seg, seg_len, grid_x; size_t smem; int M; int chunk; int P; };   // M > 0: instruction-major kernel, samples per batch; P: threads sharing one instance column (they split each batch's samples), blockDim = B * P
-struct PlanKey { int ns = -1; unsigned align = 0; int deep = -1; };   // deep: the TRAM delays are known to allow 64-sample batches
+struct PlanKey { int ns = -1; unsigned align = 0; int deep = -1; int n_blk = -1; int wave = -1; };   // deep: the TRAM delays are known to allow 64-sample batches; n_blk: sample blocks per launch; wave: planned for overlap with the neighbouring launches
 enum RowClass { ROW_NONE = 0, ROW_RO, ROW_WO, ROW_RW, ROW_IN, ROW_TR };
 
 }  // namespace
@@ -51,7 +60,7 @@ struct fx8010_gpu {
     int num_sms = 148;
     size_t smem_optin = 227 * 1024;
     bool loaded = false;
-    int slot = -1;
+    int arena_family = -1, arena_off = -1, arena_words = 0;   // this handle's range of the family's constant-memory arena (-1: not resident)
     // program image (host copies)
     std::vector<fx8010_instr> instrs;
     std::vector<fx8010_reg> regs;
@@ -67,6 +76,7 @@ struct fx8010_gpu {
     bool load_latch = true, load_acc = true;
     std::vector<int> row_of;                     // register index -> row (-1: the program never refers to it)
     bool has_skip = false, has_ext = false, stateless = false;
+    bool nop_out = false;                        // an IDELAY/XDELAY no-op whose R is an OUTPUT register (it still refreshes the latch)
     bool encode_dirty = true;
     int n_smem_tabs = 0;
     int smem_tab_id[MAX_SMEM_TABLES] = {0, 0};
@@ -80,10 +90,15 @@ struct fx8010_gpu {
     int enc_family = -1;                         // kernel family whose constant memory holds it
     PlanKey plan_key; Launch plan = {};          // last launch plan (reused while nothing relevant changes)
     bool attr_set[3][2][2] = {};
-    // previous launch on last_stream: the buffers it writes / reads (for the PDL overlap decision)
-    struct Span { const char* out_lo = nullptr; const char* out_hi = nullptr; const char* in_lo = nullptr; const char* in_hi = nullptr;
-                  cudaStream_t stream = nullptr; bool valid = false; } prev[2];   // [0] = latest
+    // Programmatic dependent launch: the buffers read / written by every launch since (and including) the last one
+    // that waited for its predecessor at its START.  A launch that postpones its wait can still be running next to
+    // any of them, so a new launch may postpone its own wait only if it is disjoint from the whole chain.
+    struct Span { const char* out_lo; const char* out_hi; const char* in_lo; const char* in_hi; };
+    std::vector<Span> chain;
+    cudaStream_t chain_stream = nullptr;
     int use_pdl = 1;
+    int stream_exclusive = 0;                    // FX8010_OPT_STREAM_EXCLUSIVE: between this handle's launches nothing else runs on the caller's stream
+    cudaEvent_t ev_order = nullptr;              // orders a launch after this handle's earlier work on a DIFFERENT stream
     bool trace_mode = false;                     // fx8010_gpu_trace in progress: debug geometry and encoding
     fx8010_trace_entry* d_trace = nullptr; int trace_inst = 0;
     // stateless fast path (fx8010_stateless.cuh)
@@ -103,7 +118,7 @@ struct fx8010_gpu {
     int use_carry = 1;
     bool short_ok = false;                       // SKIP-free, nobody reads ccr, no noise/MACMV, every channel written: fx_short_kernel when short enough
     bool short_attr_set[3][2][SH_MAX_NI_HOST] = {};
-    int use_sl = 1, tune_M = 0, use_short = 1, tune_chunk = 0;
+    int use_sl = 1, tune_M = 0, use_short = 1, tune_chunk = 0, use_fuse = 1;
     std::vector<int> sl_class, sl_index;         // per register: RowClass and index inside its class
     int sl_n_ro = 0, sl_n_wo = 0, sl_n_rw = 0;
     int sl_M = 0;                                // batch length of the uploaded encoding (0 = generic encoding uploaded)
@@ -118,7 +133,8 @@ struct fx8010_gpu {
     unsigned long long* d_counts = nullptr; unsigned int* d_flags = nullptr; uint32_t* d_wb = nullptr; uint32_t* d_latch_ch = nullptr; uint32_t* d_reg_map = nullptr; uint32_t* d_load_rows = nullptr;
     TableEntry* d_tabs = nullptr;
     // streams
-    cudaStream_t last_stream = nullptr;
+    cudaStream_t last_stream = nullptr;          // stream of the handle's latest device work (valid only while has_last)
+    bool has_last = false;
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[HOST_PIPE_BUFS] = {}, ev_comp[HOST_PIPE_BUFS] = {}, ev_d2h[HOST_PIPE_BUFS] = {};
     float* d_stage_in[HOST_PIPE_BUFS] = {}; float* d_stage_out[HOST_PIPE_BUFS] = {};
@@ -229,13 +245,20 @@ void analyse(fx8010_gpu* h) {
     // (unused declarations, the read/write/at pseudo registers) stay in the state arrays untouched.
     std::vector<uint8_t> used(nr, 0);
     used[0] = 1;
+    h->nop_out = false;
     for (int i = 0; i < n; ++i) {
         const fx8010_instr& in = h->instrs[i];
         const Uop u = uop_of(h, in);
+        if (u == U_NOP && h->regs[in.r].type == FX_REG_OUTPUT) {  // IDELAY/XDELAY whose R is an OUTPUT register: no operation, but the
+            used[in.r] = 1; h->nop_out = true;                    // output latch is still refreshed from R afterwards (:1229-1233)
+        }
         if (u == U_END || u == U_NOP) continue;
         if (writes_r(u) || h->regs[in.r].type == FX_REG_OUTPUT) used[in.r] = 1;   // OUTPUT R feeds the latch after any op
         used[in.a] = used[in.x] = 1;
-        if (u != U_LOG && u != U_EXP) used[in.y] = 1;            // LOG/EXP never read Y (the sign operand, :1114 TODO)
+        if (u != U_LOG && u != U_EXP) used[in.y] = 1;            // LOG/EXP never read Y (the sign operand, :1114 TODO) ...
+        bool pa, px, py; int nz;
+        pre_targets(h, in, pa, px, py, nz);
+        if (py) used[in.y] = 1;                                   // ... but an INPUT register there is still preloaded (:1059)
     }
     h->reg_map.clear(); h->row_of.assign(nr, -1); h->wb.clear();
     for (int r = 0; r < nr; ++r)
@@ -247,7 +270,7 @@ void analyse(fx8010_gpu* h) {
 
     // Stateless = no sample period reads anything an earlier period wrote: then the time axis can
     // be cut into independent segments.  Conservative: SKIP / TRAM / noise / MACMV rule it out.
-    h->stateless = !h->has_skip && !h->has_ext;
+    h->stateless = !h->has_skip && !h->has_ext && !h->nop_out;
     if (h->stateless) {
         std::vector<uint8_t> defined(nr, 0);
         for (int i = 0; i < n && h->stateless; ++i) {
@@ -303,7 +326,7 @@ void analyse(fx8010_gpu* h) {
     }
     // Short-program kernel (fx8010_short.cuh): SKIP-free, no noise, no MACMV, nobody reads `ccr` (it is produced on the
     // call's last sample only), every channel has a writer (no per-sample latch traffic), INPUT operands aliased.
-    h->short_ok = !h->has_skip && h->in_alias && all_ch;
+    h->short_ok = !h->has_skip && h->in_alias && all_ch && !h->nop_out;
     for (int i = 0; i < n; ++i) {
         const fx8010_instr& in = h->instrs[i];
         const Uop u = uop_of(h, in);
@@ -355,7 +378,7 @@ void analyse(fx8010_gpu* h) {
             }
     }
     if (!tram_ok) { h->sl_n_tr = 0; }
-    h->sl_ok = !h->has_skip && !has_noise_or_macmv && (!h->sl_tram || tram_ok) && all_ch;
+    h->sl_ok = !h->has_skip && !has_noise_or_macmv && (!h->sl_tram || tram_ok) && all_ch && !h->nop_out;
     h->sl_serial = h->sl_tram;
     h->sl_carry.assign(n, 0); h->sl_carried_reg.assign(nr, 0);
     std::vector<int> n_writers(nr, 0);
@@ -567,9 +590,12 @@ void encode(fx8010_gpu* h, int K, int B, int chunk) {
     // (earlier latch updates are dead), so that writer stores straight to the output block; channels
     // nobody writes — and every channel of a program with SKIP — are served from the latch.
     std::vector<int> last_writer(C, -1);
+    std::vector<uint8_t> latch_served(C, 0);      // a no-op with an OUTPUT R refreshes the latch from the register: that channel keeps the latch path
+    for (int i = 0; i < n; ++i)
+        if (uops[i] == U_NOP && h->regs[h->instrs[i].r].type == FX_REG_OUTPUT) latch_served[h->regs[h->instrs[i].r].io_index] = 1;
     if (!skipv)
         for (int i = 0; i < n; ++i)
-            if (h->regs[h->instrs[i].r].type == FX_REG_OUTPUT && writes_r(uops[i]))
+            if (h->regs[h->instrs[i].r].type == FX_REG_OUTPUT && writes_r(uops[i]) && !latch_served[h->regs[h->instrs[i].r].io_index])
                 last_writer[h->regs[h->instrs[i].r].io_index] = i;
     h->latch_ch.clear();
     for (int c = 0; c < C; ++c) if (last_writer[c] < 0) h->latch_ch.push_back((uint32_t)c);
@@ -577,7 +603,8 @@ void encode(fx8010_gpu* h, int K, int B, int chunk) {
     int e = 0;
     for (int i = 0; i < n; ++i) {
         const fx8010_instr& in = h->instrs[i];
-        if (!skipv && (uops[i] == U_END || uops[i] == U_NOP)) continue;    // no-ops unless a SKIP counts them
+        const bool nop_latch = uops[i] == U_NOP && h->regs[in.r].type == FX_REG_OUTPUT;
+        if (!skipv && (uops[i] == U_END || uops[i] == U_NOP) && !nop_latch) continue;    // no-ops unless a SKIP counts them
         bool pa, px, py; int nz;
         pre_targets(h, in, pa, px, py, nz);
         uint32_t w0 = (uint32_t)uops[i];
@@ -587,9 +614,9 @@ void encode(fx8010_gpu* h, int K, int B, int chunk) {
         uint32_t pre_off = 0, out_off = 0, aux = (uint32_t)(in.opcode & 0xff) << 24;   // bits 24..31: table slot/id, else the opcode (trace)
         if (pa || px || py) pre_off = stage_offset(nr, C, h->regs[in.a].io_index, RS, chunk);      // X and Y use A's IOIndex (:1057-1060)
         if (nz >= 0) { w0 |= F_NOISE; aux |= reg_offset(row(nz), RS); }
-        if (h->regs[in.r].type == FX_REG_OUTPUT && uops[i] != U_END && uops[i] != U_NOP) { // :1229-1233
+        if (h->regs[in.r].type == FX_REG_OUTPUT && uops[i] != U_END && (uops[i] != U_NOP || nop_latch)) { // :1229-1233
             const int c = h->regs[in.r].io_index;
-            if (skipv) w0 |= F_OUT;
+            if (skipv || latch_served[c]) w0 |= F_OUT;
             else if (last_writer[c] == i) w0 |= F_OUT | F_OUT_DIRECT;
             w0 |= (uint32_t)c << 24;
             out_off = latch_offset(nr, c, RS);
@@ -726,12 +753,9 @@ int known_tram_distance(const fx8010_gpu* h) {
 
 // Geometry for the stateless kernel: all the parallelism a launch needs comes from cutting the time
 // axis, so K is as wide as alignment allows and the segment count fills exactly one wave.
-int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_cs, size_t out_cs, int n_samples, Launch& L) {
+int plan_stateless(fx8010_gpu* h, const float*, const float*, unsigned align, int n_samples, int n_blk, bool may_overlap, Launch& L) {
     const int N = h->N;
-    auto aligned = [&](int K) {
-        const size_t a = (size_t)K * 4;
-        return N % K == 0 && ((uintptr_t)d_in % a) == 0 && ((uintptr_t)d_out % a) == 0 && (in_cs * 4) % a == 0 && (out_cs * 4) % a == 0;
-    };
+    auto aligned = [&](int K) { return N % K == 0 && (align & (unsigned)(K * 4 - 1)) == 0; };   // align: low bits of every buffer address and channel stride (bytes)
     int K = 4;
     while (K > 1 && !aligned(K)) K >>= 1;
     bool splittable = h->sl_serial && h->sl_tram && h->use_split;     // (see the sample split below)
@@ -777,12 +801,19 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_sl_kernel(K, h->sl_tram), B, L.smem);
     occ = std::max(occ, 1);
-    // half a wave per launch: with programmatic dependent launch two consecutive launches share the SMs, and
-    // fewer, longer segments spend fewer instructions on per-thread start-up
-    long n_seg = std::max(1L, (long)h->num_sms * occ / (2 * L.grid_x));
-    // ... a launch much longer than its own ramp-up gains nothing from sharing the SMs with its neighbours: fill
-    // them, twice over so that the tail balances
-    if ((double)N * n_samples > 8.0 * 4096 * 1024) n_seg = std::max(1L, 2L * h->num_sms * occ / L.grid_x);
+    // A launch that can overlap its neighbours (late wait, programmatic dependent launch) is planned as half a wave:
+    // two consecutive launches share the SMs, and fewer, longer segments spend fewer instructions on per-thread start-up.
+    // One that waits at its start has the SMs to itself: one full wave.
+    const long slots = (long)h->num_sms * occ;
+    long n_seg = std::max(1L, slots / ((may_overlap ? 2 : 1) * L.grid_x));
+    // ... a launch much longer than its own ramp-up (many instances, or several sample blocks fused into it) is cut
+    // into work items of about 128 samples, but into no fewer than two waves' worth, so that the tail balances
+    const double work = (double)N * n_samples * n_blk;
+    if (work > 8.0 * 4096 * 1024 || n_blk > 1) {
+        const long waves2 = std::max(1L, 2L * slots / ((long)L.grid_x * n_blk));
+        n_seg = std::max<long>(waves2, std::min<long>(n_samples / 128, 4L * slots / ((long)L.grid_x * n_blk)));
+        n_seg = std::max(1L, n_seg);
+    }
     if (h->tune_seg) n_seg = h->tune_seg;
     n_seg = std::min<long>(n_seg, std::max(1, n_samples / M));
     if (h->sl_serial) n_seg = 1;             // a recurrence cannot be cut along time
@@ -793,71 +824,176 @@ int plan_stateless(fx8010_gpu* h, const float* d_in, const float* d_out, size_t 
     return FX8010_OK;
 }
 
-int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, size_t out_cs, int n_samples, cudaStream_t st) {
-    if (n_samples == 0) return FX8010_OK;
+// ---- constant-memory residency (see the comment at g_arena) ----
+void arena_release(fx8010_gpu* h) {            // g_dev_mutex[h->device] held
+    if (h->arena_family < 0) return;
+    std::vector<ArenaBlock>& v = g_arena[h->device][h->arena_family];
+    for (size_t i = 0; i < v.size(); ++i)
+        if (v[i].owner == h) { v.erase(v.begin() + i); break; }
+    h->arena_family = -1; h->arena_off = -1; h->arena_words = 0;
+}
+// Makes `words` words of family `fam`'s arena belong to `h`; `fresh` = the range is new (its contents must be uploaded).
+int arena_acquire(fx8010_gpu* h, int fam, int words, bool& fresh) {   // g_dev_mutex[h->device] held
+    fresh = false;
+    std::vector<ArenaBlock>& v = g_arena[h->device][fam];
+    const unsigned long long stamp = ++g_arena_stamp[h->device];
+    if (h->arena_family == fam && h->arena_off >= 0 && h->arena_words >= words) {
+        for (ArenaBlock& b : v) if (b.owner == h) b.stamp = stamp;
+        return FX8010_OK;
+    }
+    arena_release(h);
+    if (words > ARENA_WORDS) return fail(h, FX8010_ERR_CAPACITY, "program does not fit the constant-memory arena");
+    bool synced = false;
+    while (true) {
+        std::sort(v.begin(), v.end(), [](const ArenaBlock& a, const ArenaBlock& b) { return a.off < b.off; });
+        int off = 0, found = -1;
+        for (size_t i = 0; i <= v.size(); ++i) {                        // first fit
+            const int end = i < v.size() ? v[i].off : ARENA_WORDS;
+            if (end - off >= words) { found = off; break; }
+            if (i < v.size()) off = v[i].off + v[i].words;
+        }
+        if (found >= 0) {
+            v.push_back(ArenaBlock{found, words, h, stamp});
+            h->arena_family = fam; h->arena_off = found; h->arena_words = words;
+            fresh = true;
+            return FX8010_OK;
+        }
+        // full: the least recently launched program goes (its kernels may still be running: wait for the device once)
+        if (!synced) { FX_CUDA(h, cudaDeviceSynchronize()); synced = true; }
+        size_t lru = 0;
+        for (size_t i = 1; i < v.size(); ++i) if (v[i].stamp < v[lru].stamp) lru = i;
+        fx8010_gpu* const victim = v[lru].owner;
+        victim->arena_family = -1; victim->arena_off = -1; victim->arena_words = 0;
+        v.erase(v.begin() + lru);
+    }
+}
+
+// Work this handle queued on another stream comes first (device-side ordering, no host wait).
+int order_on(fx8010_gpu* h, cudaStream_t st) {
+    if (h->has_last && h->last_stream != st) {
+        if (cudaEventRecord(h->ev_order, h->last_stream) == cudaSuccess) FX_CUDA(h, cudaStreamWaitEvent(st, h->ev_order, 0));
+        else { cudaGetLastError(); FX_CUDA(h, cudaDeviceSynchronize()); }      // that stream no longer exists: everything on the device comes first
+        h->chain.clear();
+    }
+    h->last_stream = st; h->has_last = true;
+    return FX8010_OK;
+}
+
+// Launches n_blk consecutive sample blocks of ns samples each (block b: ins[b] -> outs[b]).  A time-split (stateless)
+// program runs up to MAX_FUSED_BLOCKS of them in ONE launch — its work items are (block, time segment, instance group)
+// and all are independent; everything else runs block after block.  `own_prev`: the operation right before this one on
+// `st` is known to be this handle's own launch (or nothing that signals programmatic completion early).
+int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, int n_blk, size_t in_cs, size_t out_cs, int n_samples, cudaStream_t st, bool own_prev) {
+    if (n_samples == 0 || n_blk == 0) return FX8010_OK;
+    {
+        const int rc = order_on(h, st);
+        if (rc) return rc;
+    }
     // per-launch executed-instruction counters are 32-bit: split very long batches
     const long long per_sample = (long long)h->instrs.size() * FX8010_MAX_PASSES;
     const int max_samples = (int)std::max<long long>(1, std::min<long long>(0x7fffffffLL, 0xffffffffLL / per_sample));
-    for (int s0 = 0; s0 < n_samples; s0 += max_samples) {
-        const int ns = std::min(max_samples, n_samples - s0);
+    if (n_samples > max_samples) {
+        for (int b = 0; b < n_blk; ++b)
+            for (int s0 = 0; s0 < n_samples; s0 += max_samples) {
+                const float* in = ins[b] ? ins[b] + (size_t)s0 * h->N : nullptr;
+                float* out = outs[b] + (size_t)s0 * h->N;
+                const int rc = launch_blocks(h, &in, &out, 1, in_cs, out_cs, std::min(max_samples, n_samples - s0), st, own_prev || b > 0 || s0 > 0);
+                if (rc) return rc;
+            }
+        return FX8010_OK;
+    }
+    const int ns = n_samples;
+    const bool fusable = h->sl_ok && h->use_sl && !h->trace_mode && !h->sl_serial && h->use_fuse;
+    for (int b0 = 0; b0 < n_blk;) {
+        const int nb = fusable ? std::min(n_blk - b0, MAX_FUSED_BLOCKS) : 1;
         if (h->encode_dirty) { select_tables(h); h->plan_key.ns = -1; }
         Launch L;
-        const float* in = d_in ? d_in + (size_t)s0 * h->N : nullptr;
-        float* out = d_out + (size_t)s0 * h->N;
         // the plan depends on the batch length and on how far the buffers are aligned
-        const unsigned align = (unsigned)(((uintptr_t)in | (uintptr_t)out | (uintptr_t)(in_cs * 4) | (uintptr_t)(out_cs * 4)) & 15u) | (in ? 16u : 0u);
+        unsigned align = 0;
+        bool any_in = false, all_in = true;
+        for (int b = b0; b < b0 + nb; ++b) {
+            align |= (unsigned)(((uintptr_t)ins[b] | (uintptr_t)outs[b]) & 15u);
+            any_in = any_in || ins[b]; all_in = all_in && ins[b];
+        }
+        if (any_in != all_in) return fail(h, FX8010_ERR_ARG, "either every block of a call has an input buffer or none has");
+        align |= (unsigned)(((uintptr_t)(in_cs * 4) | (uintptr_t)(out_cs * 4)) & 15u) | (any_in ? 16u : 0u);
         const int deep = (h->sl_ok && h->sl_tram) ? (known_tram_distance(h) > 2 * SL_MAX_M ? 1 : 0) : 0;
-        if (h->plan_key.ns == ns && h->plan_key.align == align && h->plan_key.deep == deep) L = h->plan;
+        // a launch that may overlap its neighbours (late wait) is planned as half a wave; one that waits at its start fills the SMs
+        const bool may_overlap = h->use_pdl && h->stateless && nb == 1 && (h->stream_exclusive || own_prev || b0 > 0);
+        if (h->plan_key.ns == ns && h->plan_key.align == align && h->plan_key.deep == deep && h->plan_key.n_blk == nb && h->plan_key.wave == (int)may_overlap) L = h->plan;
         else {
             L.M = 0;
-            const int rc = (h->sl_ok && h->use_sl && !h->trace_mode) ? plan_stateless(h, in, out, in_cs, out_cs, ns, L) : plan_launch(h, in, out, in_cs, out_cs, ns, L);
+            const int rc = (h->sl_ok && h->use_sl && !h->trace_mode) ? plan_stateless(h, ins[b0], outs[b0], align, ns, nb, may_overlap, L)
+                                                                     : plan_launch(h, ins[b0], outs[b0], in_cs, out_cs, ns, L);
             if (rc) return rc;
-            h->plan = L; h->plan_key.ns = ns; h->plan_key.align = align; h->plan_key.deep = deep;
+            h->plan = L; h->plan_key.ns = ns; h->plan_key.align = align; h->plan_key.deep = deep; h->plan_key.n_blk = nb; h->plan_key.wave = (int)may_overlap;
         }
         // the kernel family that will run this launch (each keeps its own constant-memory copy of the program)
         const Family fam = L.M > 0 ? sl_family(L.K) : ((use_short_kernel(h)) ? FAM_SHORT : FAM_GENERIC);
-        if (h->encode_dirty || h->enc_K != L.K || h->enc_B != L.B || h->sl_M != L.M || (L.M == 0 && h->enc_chunk != L.chunk) || h->enc_family != (int)fam) {
+        const bool reencode = h->encode_dirty || h->enc_K != L.K || h->enc_B != L.B || h->sl_M != L.M || (L.M == 0 && h->enc_chunk != L.chunk) || h->enc_family != (int)fam;
+        if (reencode) {
             // the previous upload must have left the pinned buffer before it is rewritten
             FX_CUDA(h, cudaStreamSynchronize(st));
-            if (h->last_stream && h->last_stream != st) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));
             if (L.M > 0) encode_stateless(h, L.K, L.B, L.M); else encode(h, L.K, L.B, L.chunk);
-            FX_CUDA(h, upload_program(fam, h->h_prog, sizeof(uint4) * 2 * (h->n_exec + 1), h->slot, st));
+        }
+        std::lock_guard<std::mutex> lk(g_dev_mutex[h->device]);       // residency check -> launch
+        bool fresh = false;
+        {
+            const int rc = arena_acquire(h, (int)fam, 2 * (h->n_exec + 1), fresh);
+            if (rc) return rc;
+        }
+        if (reencode || fresh) {
+            FX_CUDA(h, cudaStreamSynchronize(st));                     // kernels still reading the old image of this range
+            FX_CUDA(h, upload_program(fam, h->h_prog, sizeof(uint4) * 2 * (h->n_exec + 1), h->arena_off, st));
             h->enc_family = (int)fam;
-            if (L.M > 0) {
-                FX_CUDA(h, cudaMemcpyAsync(h->d_sl_load, h->sl_load.data(), sizeof(uint2) * h->sl_load.size(), cudaMemcpyHostToDevice, st));
-                FX_CUDA(h, cudaMemcpyAsync(h->d_sl_wb, h->sl_wb.data(), sizeof(uint2) * h->sl_wb.size(), cudaMemcpyHostToDevice, st));
-            } else
-                FX_CUDA(h, cudaMemcpyAsync(h->d_latch_ch, h->latch_ch.data(), sizeof(uint32_t) * h->latch_ch.size(), cudaMemcpyHostToDevice, st));
+            if (reencode) {
+                if (L.M > 0) {
+                    FX_CUDA(h, cudaMemcpyAsync(h->d_sl_load, h->sl_load.data(), sizeof(uint2) * h->sl_load.size(), cudaMemcpyHostToDevice, st));
+                    FX_CUDA(h, cudaMemcpyAsync(h->d_sl_wb, h->sl_wb.data(), sizeof(uint2) * h->sl_wb.size(), cudaMemcpyHostToDevice, st));
+                } else
+                    FX_CUDA(h, cudaMemcpyAsync(h->d_latch_ch, h->latch_ch.data(), sizeof(uint32_t) * h->latch_ch.size(), cudaMemcpyHostToDevice, st));
+            }
             FX_CUDA(h, cudaStreamSynchronize(st));
             h->encode_dirty = false;
+            h->chain.clear();
         }
-        // Programmatic dependent launch: the kernel may start while the previous launch on this stream
-        // drains.  It can postpone its wait to the final state write-back when it reads nothing that
-        // launch writes: stateless program (start-up reads only rows nobody writes) and I/O buffers
-        // disjoint from the previous launches'.
-        const char* out_lo = (const char*)out; const char* out_hi = out_lo + sizeof(float) * ((size_t)(h->C - 1) * out_cs + (size_t)ns * h->N);
-        const char* in_lo = (const char*)in; const char* in_hi = in ? in_lo + sizeof(float) * ((size_t)(h->C - 1) * in_cs + (size_t)ns * h->N) : in_lo;
-        auto overlap = [](const char* a0, const char* a1, const char* b0, const char* b1) { return a0 < b1 && b0 < a1; };
-        // A late-waiting launch can still be running its sample loop while the launch TWO before it
-        // drains (it starts once every block of its predecessor has started), so both must be clear.
-        bool disjoint = true;
-        for (const fx8010_gpu::Span& q : h->prev)
-            disjoint = disjoint && q.valid && q.stream == st && !overlap(out_lo, out_hi, q.out_lo, q.out_hi) &&
-                       !overlap(in_lo, in_hi, q.out_lo, q.out_hi) && !overlap(out_lo, out_hi, q.in_lo, q.in_hi);
-        const int late_wait = (h->use_pdl && h->stateless && disjoint) ? 1 : 0;
+        // Programmatic dependent launch: the kernel may start while the previous launch on this stream drains.  It can
+        // postpone its wait to the final state write-back when it reads nothing an earlier launch writes and writes
+        // nothing an earlier launch reads or writes: a stateless program (its start-up reads only rows nobody writes)
+        // whose I/O buffers are disjoint from those of EVERY launch that may still be running — all launches since the
+        // last one that waited at its start (a launch starts once all blocks of its predecessor have started, so with
+        // small grids several generations can be resident at once).  That reasoning covers this handle's own launches
+        // only, so the operation right before this one on the stream must be known to be one of them: inside a
+        // multi-block call, or when the caller set FX8010_OPT_STREAM_EXCLUSIVE.
+        fx8010_gpu::Span sp;
+        sp.out_lo = sp.out_hi = (const char*)outs[b0]; sp.in_lo = sp.in_hi = (const char*)ins[b0];
+        bool disjoint = h->chain_stream == st && !h->chain.empty() && (int)h->chain.size() < MAX_CHAIN;
+        auto overlap = [](const char* a0, const char* a1, const char* b0_, const char* b1) { return a0 < b1 && b0_ < a1; };
+        for (int b = b0; b < b0 + nb; ++b) {
+            const char* o_lo = (const char*)outs[b]; const char* o_hi = o_lo + sizeof(float) * ((size_t)(h->C - 1) * out_cs + (size_t)ns * h->N);
+            const char* i_lo = (const char*)ins[b]; const char* i_hi = ins[b] ? i_lo + sizeof(float) * ((size_t)(h->C - 1) * in_cs + (size_t)ns * h->N) : i_lo;
+            for (const fx8010_gpu::Span& q : h->chain)
+                disjoint = disjoint && !overlap(o_lo, o_hi, q.out_lo, q.out_hi) && !overlap(i_lo, i_hi, q.out_lo, q.out_hi) && !overlap(o_lo, o_hi, q.in_lo, q.in_hi);
+            sp.out_lo = std::min(sp.out_lo, o_lo); sp.out_hi = std::max(sp.out_hi, o_hi);
+            if (ins[b]) { sp.in_lo = std::min(sp.in_lo, i_lo); sp.in_hi = std::max(sp.in_hi, i_hi); }
+        }
+        const int late_wait = (may_overlap && disjoint) ? 1 : 0;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(L.grid_x, L.n_seg); cfg.blockDim = dim3(L.B * L.P); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+        cfg.gridDim = dim3(L.grid_x, L.n_seg * (L.M > 0 ? nb : 1)); cfg.blockDim = dim3(L.B * L.P); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
         cudaLaunchAttribute attrs[1];
         attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attrs[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attrs; cfg.numAttrs = h->use_pdl ? 1 : 0;
+        const float* in = ins[b0]; float* out = outs[b0];
         if (L.M > 0) {
             SLParams p = {};
             p.gpr = h->d_gpr; p.acc = h->d_acc; p.latch = h->d_latch; p.counts = h->d_counts; p.rt_flags = h->d_flags;
             p.tabs = h->d_tabs; p.load_list = h->d_sl_load; p.wb_list = h->d_sl_wb;
-            p.in = in; p.out = out; p.in_cstride = in_cs; p.out_cstride = out_cs;
+            p.n_blk = nb;
+            for (int b = 0; b < nb; ++b) { p.blk_in[b] = ins[b0 + b]; p.blk_out[b] = outs[b0 + b]; }
+            p.in_cstride = in_cs; p.out_cstride = out_cs;
             p.n_samples = ns; p.seg_len = L.seg_len; p.n_seg = L.n_seg;
-            p.N = h->N; p.C = h->C; p.n_instrs = (int)h->instrs.size(); p.n_exec = h->n_exec; p.slot = h->slot;
+            p.N = h->N; p.C = h->C; p.n_instrs = (int)h->instrs.size(); p.n_exec = h->n_exec; p.prog_off = h->arena_off;
             p.n_load = (int)h->sl_load.size(); p.n_wb = (int)h->sl_wb.size();
             p.M = L.M;
             p.stage0 = (uint32_t)L.B * L.K * 4u * (uint32_t)(h->sl_n_ro + h->sl_n_wo + h->sl_n_rw * L.M);
@@ -868,8 +1004,8 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             p.ptrs = h->d_ptrs; p.itram = h->d_itram; p.xtram = h->d_xtram; p.itram_size = h->itram_size; p.xtram_size = h->xtram_size;
             p.has_tram = h->sl_tram ? 1 : 0; p.n_tr = h->sl_n_tr; p.P = L.P;
             for (int j = 0; j < 4; ++j) p.tr_ops[j] = 0;
-            for (const fx8010_instr& in : h->instrs) {           // pointer j (iw, ir, xw, xr) moves once per sample period per executed op
-                const Uop u = uop_of(h, in);
+            for (const fx8010_instr& ins_ : h->instrs) {         // pointer j (iw, ir, xw, xr) moves once per sample period per executed op
+                const Uop u = uop_of(h, ins_);
                 if (u == U_IWRITE) p.tr_ops[0]++; else if (u == U_IREAD) p.tr_ops[1]++;
                 else if (u == U_XWRITE) p.tr_ops[2]++; else if (u == U_XREAD) p.tr_ops[3]++;
             }
@@ -896,7 +1032,7 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             p.in = in; p.out = out; p.in_cstride = in_cs; p.out_cstride = out_cs;
             p.n_samples = ns; p.seg_len = L.seg_len; p.n_seg = L.n_seg;
             p.N = h->N; p.C = h->C; p.n_regs = (int)h->reg_map.size(); p.n_instrs = (int)h->instrs.size();
-            p.n_wb = (int)h->wb.size(); p.slot = h->slot;
+            p.n_wb = (int)h->wb.size(); p.prog_off = h->arena_off;
             p.n_exec = h->n_exec; p.n_latch_ch = (int)h->latch_ch.size();
             p.n_load = (int)h->load_rows.size(); p.load_latch = h->load_latch; p.load_acc = h->load_acc;
             p.itram_size = h->itram_size; p.xtram_size = h->xtram_size;
@@ -913,21 +1049,30 @@ int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, s
             if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
             FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
         }
-        h->prev[1] = h->prev[0];
-        h->prev[0].out_lo = out_lo; h->prev[0].out_hi = out_hi; h->prev[0].in_lo = in_lo; h->prev[0].in_hi = in_hi;
-        h->prev[0].stream = st; h->prev[0].valid = true;
+        if (!late_wait) h->chain.clear();          // this launch waited at its start: everything before it is complete
+        h->chain.push_back(sp); h->chain_stream = st;
         h->info.kernel_launches++;
-        h->info.last_grid = L.grid_x * L.n_seg; h->info.last_block = L.B * L.P; h->info.last_time_split = L.n_seg;
+        h->info.last_grid = L.grid_x * L.n_seg * (L.M > 0 ? nb : 1); h->info.last_block = L.B * L.P; h->info.last_time_split = L.n_seg;
         h->info.last_smem_bytes = (int)L.smem;
+        h->info.last_late_wait = late_wait; h->info.last_fused_blocks = nb;
         h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | ((L.M == 0 && use_short_kernel(h)) ? 32 : 0) | (L.K << 8) | (L.M << 16);
+        b0 += nb;
     }
-    h->last_stream = st;
     return FX8010_OK;
+}
+
+int launch_block(fx8010_gpu* h, const float* d_in, float* d_out, size_t in_cs, size_t out_cs, int n_samples, cudaStream_t st, bool own_prev = false) {
+    return launch_blocks(h, &d_in, &d_out, 1, in_cs, out_cs, n_samples, st, own_prev);
 }
 
 int sync_all(fx8010_gpu* h) {
     FX_CUDA(h, cudaSetDevice(h->device));
-    if (h->last_stream) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));
+    if (h->has_last && cudaStreamSynchronize(h->last_stream) != cudaSuccess) {   // (a caller's stream that no longer exists: wait for the device instead)
+        cudaGetLastError();
+        FX_CUDA(h, cudaDeviceSynchronize());
+        h->has_last = false;
+    }
+    h->chain.clear();
     FX_CUDA(h, cudaStreamSynchronize(h->s_comp));
     FX_CUDA(h, cudaStreamSynchronize(h->s_h2d));
     FX_CUDA(h, cudaStreamSynchronize(h->s_d2h));
@@ -965,6 +1110,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
              cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_events, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost(&h->h_prog, sizeof(uint4) * SLOT_WORDS) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_flags, sizeof(unsigned int)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_tabs, sizeof(TableEntry) * 2 * FX8010_TABLE_COUNT * FX8010_TABLE_ENTRIES) == cudaSuccess;
@@ -976,6 +1122,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     h->tune_K = env_int("FX8010_TUNE_K"); h->tune_B = env_int("FX8010_TUNE_B");
     h->tune_seg = env_int("FX8010_TUNE_SEG"); h->tune_sub = env_int("FX8010_TUNE_SUB");
     if (getenv("FX8010_NO_PDL")) h->use_pdl = 0;
+    if (getenv("FX8010_NO_FUSE")) h->use_fuse = 0;
     if (getenv("FX8010_NO_STATELESS")) h->use_sl = 0;
     if (getenv("FX8010_NO_SHORT")) h->use_short = 0;
     if (getenv("FX8010_NO_CARRY")) h->use_carry = 0;
@@ -999,6 +1146,7 @@ void fx8010_gpu_destroy(fx8010_gpu* h) {
     free_state(h);
     cudaFree(h->d_flags); cudaFree(h->d_tabs); cudaFree(h->d_events); cudaFree(h->d_planar_in); cudaFree(h->d_planar_out);
     if (h->ev_events) cudaEventDestroy(h->ev_events);
+    if (h->ev_order) cudaEventDestroy(h->ev_order);
     for (int i = 0; i < HOST_PIPE_BUFS; ++i) {
         cudaFree(h->d_stage_in[i]); cudaFree(h->d_stage_out[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -1009,9 +1157,9 @@ void fx8010_gpu_destroy(fx8010_gpu* h) {
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->h_prog) cudaFreeHost(h->h_prog);
-    if (h->slot >= 0) {
-        std::lock_guard<std::mutex> lk(g_mutex);
-        g_slot_used[h->device][h->slot] = false;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mutex[h->device]);
+        arena_release(h);
     }
     delete h;
 }
@@ -1043,13 +1191,10 @@ int fx8010_gpu_load_program(fx8010_gpu* h, const fx8010_program_image* im) {
     FX_CUDA(h, cudaSetDevice(h->device));
     const int rc = sync_all(h);
     if (rc) return rc;
-    if (h->slot < 0) {
-        std::lock_guard<std::mutex> lk(g_mutex);
-        for (int s = 0; s < PROG_SLOTS && h->slot < 0; ++s)
-            if (!g_slot_used[h->device][s]) { g_slot_used[h->device][s] = true; h->slot = s; }
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mutex[h->device]);
+        arena_release(h);          // the new program gets its constant-memory range at its first launch
     }
-    if (h->slot < 0) return fail(h, FX8010_ERR_CAPACITY, "all constant-memory program slots of this device are in use (destroy a handle)");
-
     h->loaded = false;
     free_state(h);
     h->instrs.assign(im->instrs, im->instrs + im->n_instrs);
@@ -1156,10 +1301,11 @@ int fx8010_gpu_set_controls_device(fx8010_gpu* h, int reg, const float* d_values
     FX_NEED_PROGRAM(h);
     if (!d_values || reg < 0 || reg >= (int)h->regs.size()) return fail(h, FX8010_ERR_ARG, "bad register index or NULL values");
     cudaStream_t st = (cudaStream_t)stream;
+    const int rc = order_on(h, st);
+    if (rc) return rc;
     FX_CUDA(h, cudaMemcpyAsync(h->d_gpr + (size_t)reg * h->N, d_values, sizeof(float) * h->N, cudaMemcpyDeviceToDevice, st));
     h->reg_uniform[reg] = 0;
     if (h->enc_sensitive[reg]) h->encode_dirty = true;
-    h->last_stream = st;
     return FX8010_OK;
 }
 
@@ -1176,9 +1322,24 @@ int fx8010_gpu_process_batch(fx8010_gpu* h, const float* d_in, float* d_out, int
     FX_NEED_PROGRAM(h);
     if (!d_out || n_samples < 0) return fail(h, FX8010_ERR_ARG, "d_out is NULL or n_samples negative");
     const size_t cs = (size_t)n_samples * h->N;
-    // queued host-buffer batches (process_batch_host_async) run on an internal stream: they come first
-    if (h->last_stream == h->s_comp && (cudaStream_t)stream != h->s_comp) FX_CUDA(h, cudaStreamSynchronize(h->s_comp));
+    // (work this handle queued on another stream — host-buffer batches run on an internal one — comes first: launch_blocks orders it)
     return launch_block(h, d_in, d_out, cs, cs, n_samples, (cudaStream_t)stream);
+}
+
+int fx8010_gpu_process_blocks(fx8010_gpu* h, const float* const* d_in, float* const* d_out, int n_blocks, int n_samples, void* stream) {
+    FX_NEED_PROGRAM(h);
+    if (!d_out || n_samples < 0 || n_blocks < 0) return fail(h, FX8010_ERR_ARG, "d_out is NULL or a count is negative");
+    for (int b = 0; b < n_blocks; ++b) if (!d_out[b]) return fail(h, FX8010_ERR_ARG, "d_out holds a NULL block");
+    const size_t cs = (size_t)n_samples * h->N;
+    std::vector<const float*> no_in;
+    if (!d_in) { no_in.assign((size_t)std::max(1, n_blocks), nullptr); d_in = no_in.data(); }
+    return launch_blocks(h, d_in, d_out, n_blocks, cs, cs, n_samples, (cudaStream_t)stream, false);
+}
+
+int fx8010_gpu_set_option(fx8010_gpu* h, int option, int value) {
+    if (!h) return FX8010_ERR_ARG;
+    if (option == FX8010_OPT_STREAM_EXCLUSIVE) { h->stream_exclusive = value ? 1 : 0; h->chain.clear(); return FX8010_OK; }
+    return fail(h, FX8010_ERR_ARG, "unknown option");
 }
 
 int fx8010_gpu_process_batch_events(fx8010_gpu* h, const float* d_in, float* d_out, int n_samples,
@@ -1195,7 +1356,10 @@ int fx8010_gpu_process_batch_events(fx8010_gpu* h, const float* d_in, float* d_o
             return fail(h, FX8010_ERR_ARG, "control event: bad register, sample out of range or list not sorted by sample");
         if (!ev.broadcast) ++per_instance;
     }
-    if (h->last_stream == h->s_comp && st != h->s_comp) FX_CUDA(h, cudaStreamSynchronize(h->s_comp));
+    {
+        const int rc = order_on(h, st);
+        if (rc) return rc;
+    }
     // per-instance value arrays go to the device up front (the caller may reuse them when this call returns)
     if (per_instance * N > h->events_floats) {
         const int rc = sync_all(h);
@@ -1204,7 +1368,6 @@ int fx8010_gpu_process_batch_events(fx8010_gpu* h, const float* d_in, float* d_o
         FX_CUDA(h, cudaMalloc(&h->d_events, sizeof(float) * per_instance * N));
         h->events_floats = per_instance * N;
     } else if (per_instance) {                           // an earlier call's copies out of d_events must have been consumed
-        if (h->last_stream) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));
         FX_CUDA(h, cudaStreamSynchronize(st));
     }
     size_t slot = 0;
@@ -1233,7 +1396,6 @@ int fx8010_gpu_process_batch_events(fx8010_gpu* h, const float* d_in, float* d_o
                 h->reg_uniform[ev.reg_index] = 0;
             }
             if (h->enc_sensitive[ev.reg_index]) h->encode_dirty = true;
-            h->last_stream = st;
         }
         if (s0 >= n_samples) break;
         const int s1 = (e < n_events) ? std::min(n_samples, (int)events[e].sample) : n_samples;
@@ -1276,7 +1438,10 @@ int fx8010_gpu_process_batch_planar(fx8010_gpu* h, const float* d_in, float* d_o
         FX_CUDA(h, cudaMalloc(&h->d_planar_out, sizeof(float) * need));
         h->planar_floats = need;
     }
-    if (h->last_stream == h->s_comp && st != h->s_comp) FX_CUDA(h, cudaStreamSynchronize(h->s_comp));
+    {
+        const int rc = order_on(h, st);
+        if (rc) return rc;
+    }
     const dim3 blk(32, 8);
     if (d_in) {     // [C][N][S] -> [C][S][N]
         fx_transpose_kernel<<<dim3((unsigned)((S + 31) / 32), (unsigned)((N + 31) / 32), (unsigned)C), blk, 0, st>>>(d_in, h->d_planar_in, (int)N, (int)S);
@@ -1315,7 +1480,10 @@ static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_s
         }
         h->stage_floats = need;
     }
-    if (h->last_stream && h->last_stream != h->s_comp) FX_CUDA(h, cudaStreamSynchronize(h->last_stream));   // earlier device-side batches come first
+    {   // earlier device-side batches come first
+        const int rc = order_on(h, h->s_comp);
+        if (rc) return rc;
+    }
     // pipe_seq counts sub-blocks over the life of the staging buffers, so that asynchronous calls chain:
     // sub-block q reuses the buffers of sub-block q - HOST_PIPE_BUFS once those have been consumed / drained
     for (long s0 = 0; s0 < n_samples; s0 += sub, ++h->pipe_seq) {
@@ -1329,7 +1497,7 @@ static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_s
         FX_CUDA(h, cudaEventRecord(h->ev_h2d[buf], h->s_h2d));
         FX_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_h2d[buf], 0));
         if (h->pipe_seq >= HOST_PIPE_BUFS) FX_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_d2h[buf], 0));    // stage_out[buf] drained
-        const int rc = launch_block(h, in ? h->d_stage_in[buf] : nullptr, h->d_stage_out[buf], (size_t)sub * N, (size_t)sub * N, (int)len, h->s_comp);
+        const int rc = launch_block(h, in ? h->d_stage_in[buf] : nullptr, h->d_stage_out[buf], (size_t)sub * N, (size_t)sub * N, (int)len, h->s_comp, true);   // (the internal stream carries this handle's launches only)
         if (rc) return rc;
         FX_CUDA(h, cudaEventRecord(h->ev_comp[buf], h->s_comp));
         FX_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[buf], 0));

@@ -7,8 +7,8 @@
 // diverges: a per-context skip counter turns into a write predicate.  The GPR file is a
 // structure-of-arrays tile in shared memory (gpr[reg][thread][K], one 4/8/16-byte access per
 // operand, bank-conflict free); accumulator, LFSR, TRAM pointers and counters live in hardware
-// registers.  Input samples stream HBM -> shared through a ring of cp.async stages that runs three
-// sample periods ahead (one 16-byte LDGSTS per thread and sample at K = 4); outputs go back with
+// registers.  Input samples stream HBM -> shared through two cp.async buffers of `chunk` sample periods each (while
+// one is consumed the next is in flight; one 16-byte LDGSTS per thread and sample at K = 4); outputs go back with
 // coalesced 16-byte stores straight from registers.
 //
 // Semantics follow the reference's FX8010::process (reference source/FX8010.cpp:1023-1249) op by
@@ -51,9 +51,12 @@ constexpr uint32_t F_PRE_ANY = F_PRE_A | F_PRE_X | F_PRE_Y;
 //        input-stage offset of the preload channel,  latch offset of the output channel }
 // The encoding depends on the launch geometry (RS) and is redone by the host when that changes.
 constexpr int MAX_INSTR = FX8010_MAX_INSTRUCTIONS;
-constexpr int PROG_SLOTS = 2;            // live programs per device (one slot per handle)
-constexpr int SLOT_WORDS = 2 * (MAX_INSTR + 1);
-static __constant__ uint4 c_prog[PROG_SLOTS][SLOT_WORDS];   // one copy per kernel translation unit (see fx8010_families.h)
+constexpr int SLOT_WORDS = 2 * (MAX_INSTR + 1);           // a maximum-length program (plus its pad instruction)
+constexpr int ARENA_WORDS = 2 * SLOT_WORDS;              // 64 064 B of the 64 KiB constant bank: two maximum-length programs or dozens of short ones
+// Decoded programs of all live handles of a device share this arena (one per kernel translation unit, see
+// fx8010_families.h); the host allocates ranges first-fit and evicts the least recently launched program when it
+// is full (fx8010_gpu.cu::arena_acquire), so the number of live handles is not bounded by constant memory.
+static __constant__ uint4 c_prog[ARENA_WORDS];
 
 constexpr int MAX_CHUNK = 64;             // input stage: two buffers of `chunk` samples per channel; while one is consumed the
                                          // other is in flight (a recurrence needs ~30 sample rows in flight per thread to
@@ -90,7 +93,7 @@ struct Params {
     int seg_len;                // samples per time segment (== S when serial)
     int n_seg;
     // geometry
-    int N, C, n_regs, n_instrs, n_wb, slot;   // n_regs = shared-memory rows
+    int N, C, n_regs, n_instrs, n_wb, prog_off;   // n_regs = shared-memory rows; prog_off = first word of the program in c_prog
     int n_exec;                 // encoded instructions (END/NOP are dropped for SKIP-free programs)
     int n_latch_ch;             // entries of latch_ch
     int n_load;                 // entries of load_rows
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(128, 3) fx_interp_kernel(const Params p) {
     const bool last_seg = (seg == p.n_seg - 1);
     const int s_begin = seg * p.seg_len;
     const int s_end = min(p.n_samples, s_begin + p.seg_len);
-    const uint4* const prog = c_prog[p.slot];
+    const uint4* const prog = c_prog + p.prog_off;
     const int RS = B * K;                                  // register stride (floats)
 
     // Programmatic dependent launch: let the next launch on the stream start filling SMs as this one

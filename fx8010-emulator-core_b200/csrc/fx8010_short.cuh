@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128, 3) fx_short_kernel(const Params p) {
     const bool last_seg = (seg == p.n_seg - 1);
     const int s_begin = seg * p.seg_len;
     const int s_end = min(p.n_samples, s_begin + p.seg_len);
-    const uint4* const prog = c_prog[p.slot];
+    const uint4* const prog = c_prog + p.prog_off;
     const int RS = B * K;
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -46,6 +46,7 @@ constexpr int SL_STRIDE_SHIFT = 20;          // [20:31) bytes between consecutiv
 constexpr uint32_t SL_BUF = 1u << 31;        // input-stage row: add the offset of the current stage buffer
 constexpr uint32_t F_ST_LAST = 1u << 17;     // R is never read by the program: store it on the batch-final sample only
 constexpr int SL_MAX_M = 64;             // a serial (recurrent) launch has few warps: its batch is also how far the input stage runs ahead of the arithmetic
+constexpr int MAX_FUSED_BLOCKS = 32;         // sample blocks one launch of a time-split program can cover
 constexpr int SL_CARRY_SHIFT = 18;           // w0 bits 18..20: operand A / X / Y is this instruction's OWN result of the previous sample
                                              // (a self recurrence): row (m - 1) mod M on the first sample of a batch, then forwarded
                                              // in a hardware register — the recurrence never waits for shared memory
@@ -61,11 +62,14 @@ struct SLParams {
     const TableEntry* tabs;
     const uint2* load_list;     // (operand word, register index): read-only rows fetched at start
     const uint2* wb_list;       // (operand word, register index): rows written back by the owner of the last sample
-    const float* in;
-    float* out;
+    // I/O: a launch covers n_blk consecutive sample blocks of n_samples each (more than one only for time-split
+    // programs: block, time segment and instance group are then all independent work items; blockIdx.y = blk * n_seg + seg)
+    const float* blk_in[MAX_FUSED_BLOCKS];    // element (c, s, i) of block b at blk_in[b][c * in_cstride + s * N + i]; all NULL or none
+    float* blk_out[MAX_FUSED_BLOCKS];
+    int n_blk;
     size_t in_cstride, out_cstride;
     int n_samples, seg_len, n_seg;
-    int N, C, n_instrs, n_exec, slot, n_load, n_wb;
+    int N, C, n_instrs, n_exec, prog_off, n_load, n_wb;
     int M;                      // samples per batch (power of two <= SL_MAX_M)
     uint32_t stage0;            // byte offset of the input stage rows: [C][2 buffers][M]
     int n_smem_tabs;
@@ -365,7 +369,10 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
     const int tslot_raw = blockIdx.x * B + tid;
     const bool valid = tslot_raw * K < N;
     const int inst0 = valid ? tslot_raw * K : N - K;
-    const int seg = blockIdx.y;
+    const int blk = (p.n_blk > 1) ? (int)blockIdx.y / p.n_seg : 0;       // sample block of the call this thread block works on
+    const int seg = (int)blockIdx.y - blk * p.n_seg;
+    const float* const in_base = p.blk_in[blk];
+    float* const out_base = p.blk_out[blk];
     const int s_begin = seg * p.seg_len;
     const int s_end = min(p.n_samples, s_begin + p.seg_len);
     const uint32_t row_bytes = (uint32_t)B * K * 4u;
@@ -384,17 +391,17 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
     auto my_hi = [&](int nm) { return min(nm, part * sub + sub); };
 
     // input stage: batch starting at sample s0 -> buffer at byte offset boff (channel 0 unrolled)
-    const bool has_in = (p.in != nullptr);
+    const bool has_in = (in_base != nullptr);
     auto fetch_batch = [&](int s0, uint32_t boff) {
         if (has_in && s0 < s_end) {
             const int nm = min(M, s_end - s0);
             const int lo = my_lo(nm), hi = my_hi(nm);
-            const float* g = p.in + (size_t)(s0 + lo) * N + inst0;
+            const float* g = in_base + (size_t)(s0 + lo) * N + inst0;
             unsigned char* d = reinterpret_cast<unsigned char*>(at(p.stage0 + boff)) + (uint32_t)lo * row_bytes;
 #pragma unroll 4
             for (int m = lo; m < hi; ++m, d += row_bytes, g += N) cp_async<4 * K>(d, g);
             for (int c = 1; c < C; ++c) {
-                const float* gc = p.in + (size_t)c * p.in_cstride + (size_t)(s0 + lo) * N + inst0;
+                const float* gc = in_base + (size_t)c * p.in_cstride + (size_t)(s0 + lo) * N + inst0;
                 const uint32_t base = p.stage0 + (uint32_t)c * 2u * buf_bytes + boff;
                 for (int m = lo; m < hi; ++m, gc += N) cp_async<4 * K>(at(base + (uint32_t)m * row_bytes), gc);
             }
@@ -431,12 +438,12 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
     SLCtx<K> cx;
     cx.col_s = (uint32_t)__cvta_generic_to_shared(col);
     cx.tab_s = (uint32_t)__cvta_generic_to_shared(s_tab) + (uint32_t)(tid & (TAB_REPL - 1)) * 16u;
-    cx.prog = c_prog[p.slot];
+    cx.prog = c_prog + p.prog_off;
     cx.N = N; cx.Nl = pin64s((uint64_t)N); cx.inst0 = inst0; cx.valid = valid; cx.boff = 0; cx.flags = 0;
     cx.n_exec = p.n_exec; cx.out_cstride = p.out_cstride;
 #pragma unroll
     for (int k = 0; k < K; ++k) cx.acc_last[k] = 0.0f;
-    cx.out_b = p.out + (size_t)s_begin * N + inst0;
+    cx.out_b = out_base + (size_t)s_begin * N + inst0;
     const size_t out_step = (size_t)M * N;
 
     // ---- TRAM: pointers, and the READ streams (source/FX8010.cpp:934-967) prefetched like input channels ----
@@ -553,6 +560,9 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
         fetch_tram(s0 + M, cx.boff ^ buf_bytes);
         cp_async_commit();
         cp_async_wait<1>();
+        // a column whose delay is too short for prefetching is run by its first thread alone, which then reads stage rows
+        // the other threads of the column fetched: their copies must have landed and be visible
+        if (TRAM && P > 1 && !cx.tram_fast) __syncthreads();
         bool owner = true;                              // this thread computes the batch's last sample (final state, if it is the call's last)
         if (!TRAM) {
             if (p.ccr_live) sl_exec<K, false, true, TRAM>(p, cx, 0, mb);
@@ -584,7 +594,7 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
                 }
             }
         }
-        if (s0 + mb == p.n_samples && valid && owner) {
+        if (s0 + mb == p.n_samples && blk == p.n_blk - 1 && valid && owner) {
             // This thread owns the call's last sample: leave the final state behind (cold path).
             if (p.pdl_late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // state writes follow
             sl_exec<K, true, true, TRAM>(p, cx, mb - 1, mb);
@@ -600,7 +610,7 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
                     p.ptrs[inst0 + k] = cx.split ? tp0[0][k] : cx.tp[0][k]; p.ptrs[N + inst0 + k] = cx.split ? tp0[1][k] : cx.tp[1][k];
                     p.ptrs[2 * N + inst0 + k] = cx.split ? tp0[2][k] : cx.tp[2][k]; p.ptrs[3 * N + inst0 + k] = cx.split ? tp0[3][k] : cx.tp[3][k];
                 }
-                p.counts[inst0 + k] += (unsigned long long)p.n_samples * (unsigned long long)p.n_instrs;
+                p.counts[inst0 + k] += (unsigned long long)p.n_samples * (unsigned long long)p.n_instrs * (unsigned long long)p.n_blk;
             }
         }
         cx.boff ^= buf_bytes;

@@ -10,8 +10,8 @@ template <int K> static KernelFn pick(bool skip, bool ext) {
 KernelFn generic_kernel(int K, bool skip, bool ext) {
     return K == 4 ? pick<4>(skip, ext) : (K == 2 ? pick<2>(skip, ext) : pick<1>(skip, ext));
 }
-cudaError_t upload_generic(const uint4* src, size_t bytes, int slot, cudaStream_t st) {
-    return cudaMemcpyToSymbolAsync(c_prog, src, bytes, sizeof(uint4) * (size_t)SLOT_WORDS * slot, cudaMemcpyHostToDevice, st);
+cudaError_t upload_generic(const uint4* src, size_t bytes, int word_off, cudaStream_t st) {
+    return cudaMemcpyToSymbolAsync(c_prog, src, bytes, sizeof(uint4) * (size_t)word_off, cudaMemcpyHostToDevice, st);
 }
 
 }  // namespace fxk

@@ -18,8 +18,8 @@ template <int K> static KernelFn pick(bool ext, int ni) { return ext ? pick<K, t
 KernelFn short_kernel(int K, bool ext, int ni) {
     return K == 4 ? pick<4>(ext, ni) : (K == 2 ? pick<2>(ext, ni) : pick<1>(ext, ni));
 }
-cudaError_t upload_short(const uint4* src, size_t bytes, int slot, cudaStream_t st) {
-    return cudaMemcpyToSymbolAsync(c_prog, src, bytes, sizeof(uint4) * (size_t)SLOT_WORDS * slot, cudaMemcpyHostToDevice, st);
+cudaError_t upload_short(const uint4* src, size_t bytes, int word_off, cudaStream_t st) {
+    return cudaMemcpyToSymbolAsync(c_prog, src, bytes, sizeof(uint4) * (size_t)word_off, cudaMemcpyHostToDevice, st);
 }
 
 }  // namespace fxk

@@ -35,10 +35,13 @@ void FX8010::ensureUploaded() {
             throw std::runtime_error(msg);
         }
     }
-    if (uploaded_instrs_ != front_.instructions().size() || uploaded_regs_ != front_.registers().size()) {
+    // The image the device holds is stale after ANY later loadFile/loadText/initialize (they append, like the
+    // reference, source/FX8010.cpp:777-875 — but an edit that keeps the counts equal must be noticed too).  A reload
+    // puts every instance back into the state of a freshly loaded object (see FX8010.h).
+    if (!uploaded_ || uploaded_generation_ != front_.generation()) {
         check(fx8010_gpu_load_program(gpu_, front_.image()), "load_program");
-        uploaded_instrs_ = front_.instructions().size();
-        uploaded_regs_ = front_.registers().size();
+        uploaded_ = true;
+        uploaded_generation_ = front_.generation();
     }
 }
 
@@ -91,14 +94,14 @@ void FX8010::processBlockDevicePlanar(const float* d_in, float* d_out, int n_sam
 }
 
 int FX8010::getInstructionCounter() {
-    if (!gpu_ || uploaded_instrs_ == (size_t)-1) return 0;
+    if (!gpu_ || !uploaded_) return 0;
     std::vector<unsigned long long> c((size_t)instances_);
     check(fx8010_gpu_get_instruction_counts(gpu_, c.data()), "get_instruction_counts");
     return (int)(unsigned int)c[0];                             // the reference counter is a 32-bit int
 }
 
 unsigned long long FX8010::getInstructionCounterTotal() {
-    if (!gpu_ || uploaded_instrs_ == (size_t)-1) return 0;
+    if (!gpu_ || !uploaded_) return 0;
     unsigned long long t = 0;
     check(fx8010_gpu_get_instruction_count(gpu_, &t), "get_instruction_count");
     return t;
@@ -120,7 +123,7 @@ int FX8010::setRegisterValue(const std::string& key, float value) {
     const int idx = front_.findRegister(key);
     if (idx < 0) return 1;
     front_.registers()[idx].value = value;                      // initial value of a later upload
-    if (gpu_ && uploaded_regs_ == front_.registers().size())
+    if (gpu_ && uploaded_ && uploaded_generation_ == front_.generation())
         check(fx8010_gpu_set_controls(gpu_, idx, &value, 1), "set_controls");
     return 0;
 }
@@ -136,7 +139,7 @@ int FX8010::setRegisterValues(const std::string& key, const float* values) {
 float FX8010::getRegisterValue(const std::string& key) {
     const int idx = front_.findRegister(key);
     if (idx < 0) return 1;                                      // the reference's "not found" value (:265)
-    if (gpu_ && uploaded_regs_ == front_.registers().size()) {
+    if (gpu_ && uploaded_ && uploaded_generation_ == front_.generation()) {
         std::vector<float> v((size_t)instances_);
         check(fx8010_gpu_get_register(gpu_, idx, v.data()), "get_register");
         return v[0];

@@ -31,7 +31,10 @@ public:
     void initialize();                                         // re-runs the constructor's set-up (appends, like the reference)
     std::vector<float> process(const std::vector<float>& inputSamples);   // one sample period (:57)
     int getInstructionCounter();                               // executed instructions of instance 0 (:60)
-    bool loadFile(const std::string& path);                    // (:62)
+    bool loadFile(const std::string& path);                    // (:62) appends to what is loaded, like the reference; the next process*
+                                                               // call uploads the new image, which RESETS the run-time state of every
+                                                               // instance (registers, TRAM, accumulator, LFSR, counters) — the reference
+                                                               // object keeps its state across an appending load
     struct MyError {
         std::string errorDescription = "";
         int errorRow = 1;
@@ -77,7 +80,8 @@ private:
     int instances_ = 1;
     int device_ = 0;
     fx8010_gpu* gpu_ = nullptr;
-    size_t uploaded_instrs_ = (size_t)-1, uploaded_regs_ = 0;
+    bool uploaded_ = false;                                    // the device holds the image of generation uploaded_generation_
+    unsigned long uploaded_generation_ = 0;
     std::vector<float> in_block_, out_block_;
 };
 

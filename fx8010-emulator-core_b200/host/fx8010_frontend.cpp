@@ -93,6 +93,7 @@ Frontend::Frontend(int num_channels) : num_channels_(num_channels) { initialize(
 // What the reference's constructor-time initialize() sets up (source/FX8010.cpp:16-125).  Like
 // there it is public and APPENDS when called again; lookups find registers 0..3 first either way.
 void Frontend::initialize() {
+    ++generation_;
     channels_at_init_ = num_channels_;
     errors_.clear();
     errors_.push_back({errorText(ERR_NONE, num_channels_), 1});   // entry 0 is always "no error" (:38-42)
@@ -317,6 +318,7 @@ bool Frontend::parseLine(const std::string& s) {
 }
 
 bool Frontend::loadText(const std::string& text) {
+    ++generation_;
     std::istringstream in(text);
     std::vector<std::string> lines;
     std::string line;

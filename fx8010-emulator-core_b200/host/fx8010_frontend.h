@@ -61,6 +61,7 @@ public:
     int channels() const { return num_channels_; }
     void setChannels(int c) { num_channels_ = c; }
     bool ready() const { return ready_; }
+    unsigned long generation() const { return generation_; }   // bumped by every initialize() / loadText(): the decoded image may have changed
     // Relaxed mode (off by default = the reference's exact accept/reject behaviour): also accepts what the
     // reference's README shows but its patterns reject: `itramsize N` with any or no
     // trailing blanks, CR-LF line ends, blanks around and blank lines after the final `end`.
@@ -95,6 +96,7 @@ private:
     int row_counter_ = 1;             // reference errorCounter: never reset between loads
     int itram_size_ = 0, xtram_size_ = 0;
     bool ready_ = false;
+    unsigned long generation_ = 0;
     bool relaxed_ = false;
     std::vector<double> log_tables_, exp_tables_;
     std::vector<fx8010_reg> image_regs_;

@@ -15,7 +15,9 @@
  *     With n_instances == 1 this is the reference's per-sample vector repeated over time.
  *   - per-instance state blocks are laid out [register][instance].
  *   - calls on one handle are serialised by the caller; different handles (GPUs) may be
- *     driven from different host threads / processes.
+ *     driven from different host threads / processes.  Any number of handles may be live on
+ *     a device.  Work queued on different streams by one handle is ordered on the device in
+ *     call order (a stream switch inserts an event wait).
  *   - there is NO CPU fallback: every compute entry point fails with FX8010_ERR_CUDA when no
  *     CUDA device is usable.
  */
@@ -68,7 +70,7 @@ enum fx8010_runtime_flag {
 };
 
 #define FX8010_MAX_PASSES        8      /* program re-runs per sample while END stays skipped     */
-#define FX8010_MAX_INSTRUCTIONS  1000   /* decoded programs live in __constant__ memory (2 slots x 32 KiB) */
+#define FX8010_MAX_INSTRUCTIONS  1000   /* decoded programs live in __constant__ memory (a 64 KiB arena shared by a device's handles) */
 #define FX8010_TABLE_COUNT       32     /* reference source/FX8010.cpp:63                          */
 #define FX8010_TABLE_ENTRIES     64     /* 32 mirrored + 32 generated, source/FX8010.cpp:73-105    */
 #define FX8010_LFSR_SEED1        0x70f4f854u /* include/FX8010.h:290 */
@@ -123,6 +125,16 @@ FX8010_API void fx8010_gpu_destroy(fx8010_gpu* h);
  * pointers 0, accumulator 0, LFSR seeds, output latch 0, counters 0). */
 FX8010_API int fx8010_gpu_load_program(fx8010_gpu* h, const fx8010_program_image* image);
 
+/* Options (fx8010_gpu_set_option).
+ * FX8010_OPT_STREAM_EXCLUSIVE (default 0): the caller promises that between two fx8010_gpu_process_batch calls of this
+ * handle on one stream nothing else is queued on that stream that launches kernels with programmatic completion
+ * events (other handles of this library included).  Consecutive launches of a program without state across sample
+ * periods may then overlap on the device (programmatic dependent launch with a postponed wait) whenever their buffers
+ * are disjoint from those of every launch that can still be running.  Without the promise every launch waits for
+ * its predecessor on the stream at its start. */
+enum fx8010_option { FX8010_OPT_STREAM_EXCLUSIVE = 1 };
+FX8010_API int fx8010_gpu_set_option(fx8010_gpu* h, int option, int value);
+
 /* ---- controls: setRegisterValue / getRegisterValue (source/FX8010.cpp:236-266) ---------- */
 
 /* values: host pointer; broadcast != 0 → values[0] goes to every instance, else values[N]. */
@@ -139,6 +151,13 @@ FX8010_API int fx8010_gpu_get_register(fx8010_gpu* h, int reg_index, float* out)
  * no INPUT operand. */
 FX8010_API int fx8010_gpu_process_batch(fx8010_gpu* h, const float* d_in, float* d_out,
                                         int n_samples, void* stream);
+/* n_blocks consecutive blocks of n_samples each in one call: block b reads d_in[b] and writes d_out[b] (arrays of
+ * DEVICE pointers, each block laid out as above; d_in may be NULL, or all of its entries NULL, when the program has no
+ * INPUT operand).  Equivalent to n_blocks fx8010_gpu_process_batch calls in order; a program without state across sample
+ * periods runs up to 32 blocks per kernel launch, and the library knows that its own launches follow one another
+ * on the stream (see FX8010_OPT_STREAM_EXCLUSIVE). */
+FX8010_API int fx8010_gpu_process_blocks(fx8010_gpu* h, const float* const* d_in, float* const* d_out, int n_blocks,
+                                         int n_samples, void* stream);
 /* Same call with HOST buffers (pageable or pinned): host→device copy, kernels and
  * device→host copy are pipelined over sample sub-blocks on internal streams; returns when
  * `out` is complete. */
@@ -246,6 +265,8 @@ typedef struct fx8010_launch_info {
     int32_t last_grid, last_block;        /* geometry of the last interpreter launch       */
     int32_t last_time_split;              /* sample segments per instance (1 = serial)     */
     int32_t last_smem_bytes;
+    int32_t last_late_wait;               /* the last launch postponed its wait for its predecessor (see FX8010_OPT_STREAM_EXCLUSIVE) */
+    int32_t last_fused_blocks;            /* sample blocks the last launch covered (fx8010_gpu_process_blocks) */
     int32_t kernel_variant;               /* bit0 SKIP, bit1 TRAM/noise/MACMV, bit2 stateless, bit3 instruction-major kernel, bit5 short-program kernel, bits 8..15 instances per thread, bits 16.. samples per batch */
 } fx8010_launch_info;
 FX8010_API int fx8010_gpu_get_launch_info(fx8010_gpu* h, fx8010_launch_info* out);

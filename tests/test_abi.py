@@ -18,7 +18,7 @@ def declared(header):
 
 def test_gpu_header_symbols_exported(fx):
     names = declared("fx8010_gpu.h")
-    assert len(names) >= 23 and "fx8010_gpu_process_batch" in names and "fx8010_gpu_create" in names
+    assert len(names) >= 25 and "fx8010_gpu_process_batch" in names and "fx8010_gpu_create" in names
     lib = ctypes.CDLL(fx.GPU_SO)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/fx8010_gpu.h but not exported"
@@ -37,7 +37,7 @@ def test_host_header_symbols_exported(fx):
 
 def test_struct_layouts_match_header(fx):
     assert ctypes.sizeof(fx.CInstr) == 24 and ctypes.sizeof(fx.CReg) == 16
-    assert ctypes.sizeof(fx.CDims) == 32 and ctypes.sizeof(fx.CLaunchInfo) == 32
+    assert ctypes.sizeof(fx.CDims) == 32 and ctypes.sizeof(fx.CLaunchInfo) == 40
 
 
 def test_no_cpu_fallback(fx):
