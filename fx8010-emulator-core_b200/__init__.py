@@ -91,6 +91,7 @@ GPU_SYMBOLS = {
     "fx8010_gpu_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "fx8010_gpu_process_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fx8010_gpu_process_batch_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "fx8010_gpu_process_batch_host_slice": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]),
     "fx8010_gpu_host_alloc": (C.c_void_p, [C.c_size_t]),
     "fx8010_gpu_host_free": (None, [C.c_void_p]),
     "fx8010_gpu_synchronize": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -109,6 +110,24 @@ GPU_SYMBOLS = {
     "fx8010_gpu_process_batch_planar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fx8010_gpu_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fx8010_gpu_get_launch_info": (C.c_int, [C.c_void_p, C.POINTER(CLaunchInfo)]),
+}
+
+MULTI_SYMBOLS = {
+    "fx8010_multi_shard_range": (None, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "fx8010_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fx8010_multi_destroy": (None, [C.c_void_p]),
+    "fx8010_multi_num_shards": (C.c_int, [C.c_void_p]),
+    "fx8010_multi_shard": (C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "fx8010_multi_load_program": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fx8010_multi_set_controls": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "fx8010_multi_get_register": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "fx8010_multi_process_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "fx8010_multi_process_batch_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "fx8010_multi_synchronize": (C.c_int, [C.c_void_p]),
+    "fx8010_multi_get_instruction_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
+    "fx8010_multi_get_registers": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fx8010_multi_get_runtime_flags": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), C.c_int]),
+    "fx8010_multi_last_error": (C.c_char_p, [C.c_void_p]),
 }
 
 HOST_SYMBOLS = {
@@ -158,7 +177,7 @@ def _bind(path, table):
 def gpu_lib():
     global _gpu
     if _gpu is None:
-        _gpu = _bind(GPU_SO, GPU_SYMBOLS)
+        _gpu = _bind(GPU_SO, {**GPU_SYMBOLS, **MULTI_SYMBOLS})
     return _gpu
 
 
@@ -498,6 +517,82 @@ class Gpu:
         i = CLaunchInfo()
         self._check(self.L.fx8010_gpu_get_launch_info(self.h, C.byref(i)))
         return i
+
+
+class MultiGpu:
+    """One program over N instances spread across several GPUs (include/fx8010_multi.h): contiguous instance ranges,
+    one host thread per device, outputs gathered into ONE host buffer [channel][sample][instance]."""
+
+    def __init__(self, devices, instances: int, channels: int = 1):
+        self.L = gpu_lib()
+        self.n, self.c = instances, channels
+        dev = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.L.fx8010_multi_create(dev, len(devices), instances, channels, C.byref(h))
+        if rc != 0:
+            raise FxError(rc, self.L.fx8010_multi_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fx8010_multi_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FxError(rc, self.L.fx8010_multi_last_error(self.h).decode())
+
+    def shards(self):
+        out = []
+        for g in range(self.L.fx8010_multi_num_shards(self.h)):
+            lo, hi = C.c_int(), C.c_int()
+            self.L.fx8010_multi_shard(self.h, g, C.byref(lo), C.byref(hi))
+            out.append((lo.value, hi.value))
+        return out
+
+    def load_program(self, prog: "Program"):
+        self._check(self.L.fx8010_multi_load_program(self.h, prog.image_ptr()))
+        self.n_regs = len(prog.registers())
+
+    def set_controls(self, reg: int, values, broadcast: bool = False):
+        v = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float32)
+        assert broadcast or v.size == self.n
+        self._check(self.L.fx8010_multi_set_controls(self.h, reg, v.ctypes.data, 1 if broadcast else 0))
+
+    def get_register(self, reg: int) -> np.ndarray:
+        out = np.zeros(self.n, dtype=np.float32)
+        self._check(self.L.fx8010_multi_get_register(self.h, reg, out.ctypes.data))
+        return out
+
+    def process_host(self, x, n_samples=None, out=None, wait: bool = True) -> np.ndarray:
+        if x is not None and not isinstance(x, int):
+            x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.c, -1, self.n)
+            n_samples = x.shape[1]
+        if out is None:
+            out = np.zeros((self.c, n_samples, self.n), dtype=np.float32)
+        f = self.L.fx8010_multi_process_batch_host if wait else self.L.fx8010_multi_process_batch_host_async
+        self._check(f(self.h, _ptr(x), _ptr(out), n_samples))
+        return out
+
+    def synchronize(self):
+        self._check(self.L.fx8010_multi_synchronize(self.h))
+
+    def registers(self) -> np.ndarray:
+        out = np.zeros((self.n_regs, self.n), dtype=np.float32)
+        self._check(self.L.fx8010_multi_get_registers(self.h, out.ctypes.data))
+        return out
+
+    def count_total(self) -> int:
+        t = C.c_ulonglong(0)
+        self._check(self.L.fx8010_multi_get_instruction_count(self.h, C.byref(t)))
+        return int(t.value)
+
+    def flags(self, clear: bool = False) -> int:
+        f = C.c_uint(0)
+        self._check(self.L.fx8010_multi_get_runtime_flags(self.h, C.byref(f), 1 if clear else 0))
+        return int(f.value)
 
 
 def shard_range(n_total: int, rank: int, world: int):

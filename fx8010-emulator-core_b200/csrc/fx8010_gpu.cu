@@ -115,6 +115,8 @@ struct fx8010_gpu {
     bool acc_writer = false;                     // some instruction sets the accumulator
     std::vector<uint8_t> sl_carry;               // per instruction: bit o set = operand o (A, X, Y) is the instruction's own previous result
     std::vector<uint8_t> sl_carried_reg;         // per register: some instruction carries it from sample to sample
+    std::vector<uint8_t> sl_fuse;                // per instruction: 0, or 0x80 | bits (fx8010_stateless.cuh F_FUSE) when the NEXT executed instruction is fused into it
+    int use_pairs = 1;
     int use_carry = 1;
     bool short_ok = false;                       // SKIP-free, nobody reads ccr, no noise/MACMV, every channel written: fx_short_kernel when short enough
     bool short_attr_set[3][2][SH_MAX_NI_HOST] = {};
@@ -126,6 +128,7 @@ struct fx8010_gpu {
     uint2* d_sl_load = nullptr; uint2* d_sl_wb = nullptr;
     bool sl_attr_set[2][3] = {};                 // MaxDynamicSharedMemorySize set for kernel <K, SKIP, EXT>
     int n_exec = 0;                              // encoded instructions
+    int n_unpred = 0;                            // ... of which no SKIP can reach (general interpreter: counted per pass, not per instruction)
     std::vector<uint32_t> latch_ch;              // channels served from the latch every sample period
     // device state
     float* d_gpr = nullptr; double* d_acc = nullptr; uint32_t* d_lfsr = nullptr; float* d_latch = nullptr;
@@ -432,6 +435,55 @@ void analyse(fx8010_gpu* h) {
         is_read[in.x] = 1;
         if (u != U_LOG && u != U_EXP) is_read[in.y] = 1;
     }
+    // Producer/consumer pairs: an instruction whose result has exactly ONE reader — the next executed instruction, a
+    // MACS / MACSN (:1077-1094) whose other two operands hold one value for the whole batch — is run together with
+    // it: the result is forwarded in a hardware register and never stored (the register keeps a single row that only
+    // the final-state pass writes).  `log a, in, 3, 0` / `macs out, 0, a, volume` (cfg2) is the typical case.
+    h->sl_fuse.assign(n, 0);
+    std::vector<uint8_t> fused_away(nr, 0);
+    if (h->sl_ok && h->use_pairs) {
+        std::vector<int> n_reads(nr, 0);
+        bool ccr_live = false;
+        for (int i = 0; i < n; ++i) {
+            const fx8010_instr& in = h->instrs[i];
+            const Uop u = uop_of(h, in);
+            if (u == U_END || u == U_NOP) continue;
+            if (!(u == U_IREAD || u == U_XREAD)) n_reads[in.a]++;
+            n_reads[in.x]++; n_reads[in.y]++;                   // (counted even where the value is ignored: conservative)
+            if (writes_r(u) && in.r == 0) ccr_live = true;
+        }
+        if (n_reads[0]) ccr_live = true;                        // every setCCR is then materialised per sample: no pairs
+        int prev = -1;
+        for (int j = 0; j < n && !ccr_live; ++j) {
+            const fx8010_instr& c = h->instrs[j];
+            const Uop uc = uop_of(h, c);
+            if (uc == U_END || uc == U_NOP) continue;
+            const int i = prev;
+            prev = j;
+            if (i < 0 || h->sl_fuse[i]) continue;
+            const fx8010_instr& pr = h->instrs[i];
+            const Uop up = uop_of(h, pr);
+            if (!writes_r(up) || up == U_MACMV || (uc != U_MACS && uc != U_MACSN)) continue;
+            const int g = pr.r;
+            if (g == 0 || h->regs[g].type == FX_REG_OUTPUT || h->regs[g].type == FX_REG_INPUT || n_writers[g] != 1 || n_reads[g] != 1) continue;
+            if (h->sl_carry[i] || h->sl_carry[j] || h->sl_carried_reg[g]) continue;
+            bool is_stream = false;
+            for (int q = 0; q < h->sl_n_tr; ++q) if (h->sl_tr[q].reg == g) is_stream = true;
+            if (is_stream) continue;
+            const int pos = c.a == g ? 0 : (c.x == g ? 1 : (c.y == g ? 2 : -1));
+            if (pos < 0) continue;
+            const int others[2] = {pos == 0 ? c.x : c.a, pos == 2 ? c.x : c.y};
+            bool constant = true;
+            for (int o : others) constant = constant && !h->written[o] && h->regs[o].type != FX_REG_INPUT && h->row_of[o] >= 0;
+            if (!constant || (writes_r(uc) && c.r == g)) continue;
+            bool pre_a, pre_x, pre_y; int nz;
+            pre_targets(h, c, pre_a, pre_x, pre_y, nz);
+            if (pre_a || pre_x || pre_y || nz >= 0) continue;
+            h->sl_fuse[i] = (uint8_t)(0x80 | (pos != 0 ? 1 : 0) | (uc == U_MACSN ? 2 : 0) | (pos == 1 ? 4 : 0));
+            fused_away[g] = 1;
+            prev = -1;                                           // the consumer cannot start another pair
+        }
+    }
     h->sl_class.assign(nr, ROW_NONE); h->sl_index.assign(nr, 0);
     h->sl_n_ro = h->sl_n_wo = h->sl_n_rw = 0;
     if (h->sl_ok)
@@ -442,7 +494,7 @@ void analyse(fx8010_gpu* h) {
             for (int q = 0; q < h->sl_n_tr; ++q) if (h->sl_tr[q].reg == r) { h->sl_class[r] = ROW_TR; h->sl_index[r] = q; is_tr = true; }
             if (is_tr) continue;
             if (!h->written[r]) { h->sl_class[r] = ROW_RO; h->sl_index[r] = h->sl_n_ro++; }
-            else if (!is_read[r]) { h->sl_class[r] = ROW_WO; h->sl_index[r] = h->sl_n_wo++; }
+            else if (!is_read[r] || fused_away[r]) { h->sl_class[r] = ROW_WO; h->sl_index[r] = h->sl_n_wo++; }   // (a forwarded result: one row, written by the final-state pass only)
             else { h->sl_class[r] = ROW_RW; h->sl_index[r] = h->sl_n_rw++; }
         }
 }
@@ -496,8 +548,9 @@ void encode_stateless(fx8010_gpu* h, int K, int B, int M) {
             if (slot >= 0) { w0 |= F_TAB_SMEM; aux = (uint32_t)slot << 24; }
             else { w0 |= F_TAB_IMM; aux = (uint32_t)h->tab_of[i] << 24; }
         }
+        if (h->sl_fuse[i]) w0 |= F_FUSE;
         h->h_prog[2 * e] = make_uint4(w0, sl_word(h, in.r, B, K, M), sl_word(h, in.a, B, K, M), sl_word(h, in.x, B, K, M));
-        h->h_prog[2 * e + 1] = make_uint4(sl_word(h, in.y, B, K, M), aux, sl_word(h, 0, B, K, M), 0);
+        h->h_prog[2 * e + 1] = make_uint4(sl_word(h, in.y, B, K, M), aux, sl_word(h, 0, B, K, M), (uint32_t)(h->sl_fuse[i] & 0x7f));
         ++e;
     }
     h->n_exec = e;
@@ -586,6 +639,20 @@ void encode(fx8010_gpu* h, int K, int B, int chunk) {
         ccr_live[i] = live;
     }
 
+    // Accumulator liveness, same reasoning: only MACMV reads the accumulator (:1145), every other arithmetic
+    // instruction except ANDXOR overwrites it (a value nobody overwrites within one lap survives to the end of the batch).
+    std::vector<uint8_t> acc_live(n, 0);
+    for (int i = 0; i < n; ++i) {
+        if (!writes_r(uops[i]) || uops[i] == U_ANDXOR || uops[i] == U_MACMV) continue;
+        bool live = true;
+        for (int d = 1; d <= n; ++d) {
+            const int j = (i + d) % n;
+            if (uops[j] == U_MACMV) { live = true; break; }
+            if (writes_r(uops[j]) && uops[j] != U_ANDXOR && !maybe_skipped[j]) { live = false; break; }
+        }
+        acc_live[i] = live;
+    }
+
     // SKIP-free programs: the value a channel puts out is what its LAST writer in program order leaves
     // (earlier latch updates are dead), so that writer stores straight to the output block; channels
     // nobody writes — and every channel of a program with SKIP — are served from the latch.
@@ -600,7 +667,7 @@ void encode(fx8010_gpu* h, int K, int B, int chunk) {
     h->latch_ch.clear();
     for (int c = 0; c < C; ++c) if (last_writer[c] < 0) h->latch_ch.push_back((uint32_t)c);
 
-    int e = 0;
+    int e = 0, n_unpred = 0;
     for (int i = 0; i < n; ++i) {
         const fx8010_instr& in = h->instrs[i];
         const bool nop_latch = uops[i] == U_NOP && h->regs[in.r].type == FX_REG_OUTPUT;
@@ -622,6 +689,9 @@ void encode(fx8010_gpu* h, int K, int B, int chunk) {
             out_off = latch_offset(nr, c, RS);
         }
         if (ccr_live[i]) w0 |= F_CCR;
+        if (acc_live[i] || h->trace_mode) w0 |= F_ACC;
+        if (skipv && (maybe_skipped[i] || h->trace_mode)) w0 |= F_PRED;
+        else ++n_unpred;
         if (h->tab_of[i] >= 0) {
             int slot = -1;
             for (int t = 0; t < h->n_smem_tabs; ++t) if (h->smem_tab_id[t] == h->tab_of[i]) slot = t;
@@ -633,7 +703,7 @@ void encode(fx8010_gpu* h, int K, int B, int chunk) {
         h->h_prog[2 * e + 1] = make_uint4(reg_offset(row(in.y), RS), aux, pre_off, out_off);
         ++e;
     }
-    h->n_exec = e;
+    h->n_exec = e; h->n_unpred = n_unpred;
     h->h_prog[2 * e] = make_uint4((uint32_t)U_NOP, 0, 0, 0);      // pad: the kernel prefetches pc + 1
     h->h_prog[2 * e + 1] = make_uint4(0, 0, 0, 0);
     h->enc_K = K; h->enc_B = B; h->sl_M = 0; h->enc_chunk = chunk;
@@ -1033,7 +1103,7 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
             p.n_samples = ns; p.seg_len = L.seg_len; p.n_seg = L.n_seg;
             p.N = h->N; p.C = h->C; p.n_regs = (int)h->reg_map.size(); p.n_instrs = (int)h->instrs.size();
             p.n_wb = (int)h->wb.size(); p.prog_off = h->arena_off;
-            p.n_exec = h->n_exec; p.n_latch_ch = (int)h->latch_ch.size();
+            p.n_exec = h->n_exec; p.n_latch_ch = (int)h->latch_ch.size(); p.n_unpred = h->n_unpred;
             p.n_load = (int)h->load_rows.size(); p.load_latch = h->load_latch; p.load_acc = h->load_acc;
             p.itram_size = h->itram_size; p.xtram_size = h->xtram_size;
             p.n_smem_tabs = h->n_smem_tabs;
@@ -1049,13 +1119,15 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
             if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
             FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
         }
+        bool pairs = false;
+        if (L.M > 0) for (uint8_t f : h->sl_fuse) pairs = pairs || f;
         if (!late_wait) h->chain.clear();          // this launch waited at its start: everything before it is complete
         h->chain.push_back(sp); h->chain_stream = st;
         h->info.kernel_launches++;
         h->info.last_grid = L.grid_x * L.n_seg * (L.M > 0 ? nb : 1); h->info.last_block = L.B * L.P; h->info.last_time_split = L.n_seg;
         h->info.last_smem_bytes = (int)L.smem;
         h->info.last_late_wait = late_wait; h->info.last_fused_blocks = nb;
-        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | ((L.M == 0 && use_short_kernel(h)) ? 32 : 0) | (L.K << 8) | (L.M << 16);
+        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | ((L.M == 0 && use_short_kernel(h)) ? 32 : 0) | (pairs ? 64 : 0) | (L.K << 8) | (L.M << 16);
         b0 += nb;
     }
     return FX8010_OK;
@@ -1123,6 +1195,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     h->tune_seg = env_int("FX8010_TUNE_SEG"); h->tune_sub = env_int("FX8010_TUNE_SUB");
     if (getenv("FX8010_NO_PDL")) h->use_pdl = 0;
     if (getenv("FX8010_NO_FUSE")) h->use_fuse = 0;
+    if (getenv("FX8010_NO_PAIRS")) h->use_pairs = 0;
     if (getenv("FX8010_NO_STATELESS")) h->use_sl = 0;
     if (getenv("FX8010_NO_SHORT")) h->use_short = 0;
     if (getenv("FX8010_NO_CARRY")) h->use_carry = 0;
@@ -1456,11 +1529,14 @@ int fx8010_gpu_process_batch_planar(fx8010_gpu* h, const float* d_in, float* d_o
     return FX8010_OK;
 }
 
-static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_samples, bool wait) {
+// host_n: instances per row of the HOST buffers (>= N: this handle's columns are a slice of a wider [channel][sample][instance] block)
+static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_samples, bool wait, size_t host_n = 0) {
     FX_NEED_PROGRAM(h);
     if (!out || n_samples < 0) return fail(h, FX8010_ERR_ARG, "out is NULL or n_samples negative");
     if (n_samples == 0) return FX8010_OK;
     const size_t N = (size_t)h->N, C = (size_t)h->C;
+    if (host_n == 0) host_n = N;
+    if (host_n < N) return fail(h, FX8010_ERR_ARG, "host row length below the instance count");
     // sub-block: ~8 MiB of samples per channel set
     long sub = h->tune_sub ? h->tune_sub : (long)((8u << 20) / (4 * N * C));
     sub = std::max<long>(8, sub / 8 * 8);
@@ -1491,9 +1567,14 @@ static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_s
         const long len = std::min<long>(sub, n_samples - s0);
         if (h->pipe_seq >= HOST_PIPE_BUFS) FX_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_comp[buf], 0));     // stage_in[buf] consumed
         if (in)
-            for (size_t c = 0; c < C; ++c)
-                FX_CUDA(h, cudaMemcpyAsync(h->d_stage_in[buf] + c * (size_t)sub * N, in + (c * (size_t)n_samples + s0) * N,
-                                           sizeof(float) * len * N, cudaMemcpyHostToDevice, h->s_h2d));
+            for (size_t c = 0; c < C; ++c) {
+                if (host_n == N)
+                    FX_CUDA(h, cudaMemcpyAsync(h->d_stage_in[buf] + c * (size_t)sub * N, in + (c * (size_t)n_samples + s0) * N,
+                                               sizeof(float) * len * N, cudaMemcpyHostToDevice, h->s_h2d));
+                else
+                    FX_CUDA(h, cudaMemcpy2DAsync(h->d_stage_in[buf] + c * (size_t)sub * N, sizeof(float) * N, in + (c * (size_t)n_samples + s0) * host_n,
+                                                 sizeof(float) * host_n, sizeof(float) * N, (size_t)len, cudaMemcpyHostToDevice, h->s_h2d));
+            }
         FX_CUDA(h, cudaEventRecord(h->ev_h2d[buf], h->s_h2d));
         FX_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_h2d[buf], 0));
         if (h->pipe_seq >= HOST_PIPE_BUFS) FX_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_d2h[buf], 0));    // stage_out[buf] drained
@@ -1501,9 +1582,14 @@ static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_s
         if (rc) return rc;
         FX_CUDA(h, cudaEventRecord(h->ev_comp[buf], h->s_comp));
         FX_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[buf], 0));
-        for (size_t c = 0; c < C; ++c)
-            FX_CUDA(h, cudaMemcpyAsync(out + (c * (size_t)n_samples + s0) * N, h->d_stage_out[buf] + c * (size_t)sub * N,
-                                       sizeof(float) * len * N, cudaMemcpyDeviceToHost, h->s_d2h));
+        for (size_t c = 0; c < C; ++c) {
+            if (host_n == N)
+                FX_CUDA(h, cudaMemcpyAsync(out + (c * (size_t)n_samples + s0) * N, h->d_stage_out[buf] + c * (size_t)sub * N,
+                                           sizeof(float) * len * N, cudaMemcpyDeviceToHost, h->s_d2h));
+            else
+                FX_CUDA(h, cudaMemcpy2DAsync(out + (c * (size_t)n_samples + s0) * host_n, sizeof(float) * host_n, h->d_stage_out[buf] + c * (size_t)sub * N,
+                                             sizeof(float) * N, sizeof(float) * N, (size_t)len, cudaMemcpyDeviceToHost, h->s_d2h));
+        }
         FX_CUDA(h, cudaEventRecord(h->ev_d2h[buf], h->s_d2h));
     }
     if (wait) FX_CUDA(h, cudaStreamSynchronize(h->s_d2h));
@@ -1515,6 +1601,9 @@ int fx8010_gpu_process_batch_host(fx8010_gpu* h, const float* in, float* out, in
 }
 int fx8010_gpu_process_batch_host_async(fx8010_gpu* h, const float* in, float* out, int n_samples) {
     return process_host_impl(h, in, out, n_samples, false);
+}
+int fx8010_gpu_process_batch_host_slice(fx8010_gpu* h, const float* in, float* out, int n_samples, size_t host_instances, int wait) {
+    return process_host_impl(h, in, out, n_samples, wait != 0, host_instances);
 }
 
 int fx8010_gpu_synchronize(fx8010_gpu* h, void* stream) {

@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "fx8010_gpu.h"
 
 namespace fxk {
@@ -40,6 +42,11 @@ constexpr uint32_t F_TAB_SMEM = 1u << 14; // LOG/EXP: literal selector, table st
 constexpr uint32_t F_TAB_IMM = 1u << 15;  // LOG/EXP: literal selector, table in global memory
 constexpr uint32_t F_OUT_DIRECT = 1u << 16; // SKIP-free programs: the last writer of its channel in program order
                                             // stores R straight to the output block (no latch round trip)
+constexpr uint32_t F_PRED = 1u << 17;    // (general interpreter) some SKIP can reach this instruction: it runs under the per-context skip predicate
+                                         // (load-time reach analysis; instructions no SKIP can reach run unpredicated and uncounted — their
+                                         // number per pass is added to the executed-instruction counters at once)
+constexpr uint32_t F_ACC = 1u << 18;     // (general interpreter) the accumulator value this instruction leaves can be observed (a MACMV reads it
+                                         // before another instruction overwrites it); the batch-final value is always kept
 constexpr uint32_t F_PRE_ANY = F_PRE_A | F_PRE_X | F_PRE_Y;
 
 // 32-byte decoded instruction (two uint4 words).  All operand locations are ready-made BYTE offsets
@@ -62,9 +69,13 @@ constexpr int MAX_CHUNK = 64;             // input stage: two buffers of `chunk`
                                          // other is in flight (a recurrence needs ~30 sample rows in flight per thread to
                                          // cover HBM latency at full bandwidth)
 constexpr int MAX_SMEM_TABLES = 2;       // LOG/EXP tables replicated into shared memory
-constexpr int TAB_REPL = 2;              // replicas per table entry (lane parity picks one): measured best of 1/2/4/8 — more replicas cut gather
-                                         // bank conflicts but cost more per-block start-up copy than they save
-constexpr int TAB_SMEM_BYTES = FX8010_TABLE_ENTRIES * TAB_REPL * 16;   // 2 KiB per table
+#ifndef FXK_TAB_REPL
+#define FXK_TAB_REPL 8
+#endif
+constexpr int TAB_REPL = FXK_TAB_REPL;   // replicas per table entry; lane l reads replica l % TAB_REPL.  With 8 the eight lanes of a quarter warp (one
+                                         // phase of a 128-bit shared load) hit eight different 16-byte bank groups whatever their indices: the gather is
+                                         // conflict free (4 wavefronts instead of ~7 with two replicas; the shared-memory pipe is what bounds cfg2)
+constexpr int TAB_SMEM_BYTES = FX8010_TABLE_ENTRIES * TAB_REPL * 16;   // 8 KiB per table
 
 struct __align__(16) TableEntry { double y1, slope; }; // T[i], (T[i+1]-T[i])/(x2-x1) — host-computed in IEEE double
 
@@ -96,6 +107,7 @@ struct Params {
     int N, C, n_regs, n_instrs, n_wb, prog_off;   // n_regs = shared-memory rows; prog_off = first word of the program in c_prog
     int n_exec;                 // encoded instructions (END/NOP are dropped for SKIP-free programs)
     int n_latch_ch;             // entries of latch_ch
+    int n_unpred;               // encoded instructions without F_PRED that count as executed (END/NOP included): added to the counters per first pass
     int n_load;                 // entries of load_rows
     int load_latch, load_acc;   // the latches / the accumulator can be observed before the program rewrites them
     int chunk;                  // samples per input-stage buffer (power of two <= MAX_CHUNK)
@@ -182,6 +194,19 @@ __device__ __forceinline__ int32_t logic_ops(float fa, float fx, float fy) {
     if (X == 0xFFFFFF) r = A ^ Y;
     if (Y == 0) r = A & X;
     return r;
+}
+
+// INTERP, source/FX8010.cpp:1180-1187: (float)((1.0 - (double)X) * (double)A + (double)(X * Y)) for K contexts; omx = 1.0 - (double)X.
+// (Widening A and X * Y with integer-pipe bit arithmetic instead of F2F.F64.F32 — 16 lanes per clock and SM on the conversion
+//  unit, profiles/pipe_peaks.json — was measured and is SLOWER: cfg4 139 -> 170 us at 65 536 instances, 86 -> 98 us at 8 192;
+//  the five dependent integer instructions are as long a chain as the conversion's 18 cycles and cost issue slots.)
+template <int K> __device__ __forceinline__ void interp_core(const double (&omx)[K], const float (&a)[K], const float (&x)[K], const float (&y)[K], float (&out)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[k] = __double2float_rn(__dadd_rn(__dmul_rn(omx[k], (double)a[k]), (double)__fmul_rn(x[k], y[k])));
+}
+template <int K> __device__ __forceinline__ void one_minus(const float (&x)[K], double (&omx)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) omx[k] = __dsub_rn(1.0, (double)x[k]);
 }
 
 // linearInterpolate() index: static_cast<int>((x - x_min) / step), source/FX8010.cpp:285-286.
@@ -344,12 +369,13 @@ __global__ void __launch_bounds__(128, 3) fx_interp_kernel(const Params p) {
     if (tid == 0) {
         s_inv[0] = (uint32_t)p.n_exec; s_inv[1] = (uint32_t)p.n_latch_ch; s_inv[2] = (uint32_t)(p.n_samples - 1);
         s_inv[3] = (uint32_t)(p.out_cstride & 0xffffffffu); s_inv[4] = (uint32_t)(p.out_cstride >> 32);
-        s_inv[5] = (uint32_t)p.N;
+        s_inv[5] = (uint32_t)p.N; s_inv[6] = (uint32_t)p.n_unpred;
     }
     __syncthreads();                  // s_tab / s_inv visible (the only block-wide dependency)
     const int n_exec = (int)inv_read(s_inv, 0), n_latch_ch = (int)inv_read(s_inv, 1), last_s = (int)inv_read(s_inv, 2);
     const size_t out_cstride = (size_t)inv_read(s_inv, 3) | ((size_t)inv_read(s_inv, 4) << 32);
     const int Nv = (int)inv_read(s_inv, 5);        // N for use inside the sample loop
+    const unsigned int n_unpred = inv_read(s_inv, 6);
 
     const bool tracing = (K == 1 && SKIP && EXT) && p.trace != nullptr && valid && inst0 == p.trace_inst;
     const int lane_rep = tid & (TAB_REPL - 1);
@@ -365,19 +391,24 @@ __global__ void __launch_bounds__(128, 3) fx_interp_kernel(const Params p) {
             // ---- one sample period: FX8010::process, source/FX8010.cpp:1023-1249 ----
             // The final CCR / latch must be in shared memory when the batch ends (state write-back).
             const bool last_sample = (sidx == last_s);
+            const uint32_t force_flags = last_sample ? (F_CCR | F_ACC) : 0u;
             bool saw_end[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) { skip[k] = 0; saw_end[k] = false; }
             int pass = 0;
             do {
                 int trace_pc = 0;
-                auto exec_instr = [&](const uint4 wA, const uint4 wB) {
-                    const uint32_t w0 = wA.x;
+                // PRED = this instruction runs under the skip predicate (a SKIP can reach it, or this is an extra pass in which
+                // finished contexts idle); instructions no SKIP can reach take the unpredicated copy: vector stores, no
+                // per-context bookkeeping.
+                auto exec_instr = [&](auto pred_tag, const uint4 wA, const uint4 wB) {
+                    constexpr bool PRED = decltype(pred_tag)::value;
+                    const uint32_t w0 = wA.x | force_flags;           // the call's last sample materialises CCR and accumulator whatever the liveness says
                     const uint32_t uop = w0 & 0xffu;                  // (a compare tree: measured faster than the LDC + BRX jump table, 141 vs 155 ms on cfg5)
                     bool act[K];
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        if (SKIP) {                                   // :1037 / :1235-1241
+                        if (PRED) {                                   // :1037 / :1235-1241
                             act[k] = (skip[k] == 0);
                             skip[k] = (skip[k] > 0) ? skip[k] - 1 : 0; // a negative count skips exactly one
                         } else act[k] = true;
@@ -394,7 +425,7 @@ __global__ void __launch_bounds__(128, 3) fx_interp_kernel(const Params p) {
 #pragma unroll
                             for (int k = 0; k < K; ++k) v[k] = 0.0f;
                         }
-                        if (!SKIP) {
+                        if (!PRED) {
                             if (w0 & F_PRE_A) vstore<K>(pa, v);
                             if (w0 & F_PRE_X) vstore<K>(px, v);
                             if (w0 & F_PRE_Y) vstore<K>(py, v);
@@ -425,7 +456,8 @@ __global__ void __launch_bounds__(128, 3) fx_interp_kernel(const Params p) {
                     Vec<K> r;
                     bool writes_r = true;
 #define FX_EACH _Pragma("unroll") for (int k = 0; k < K; ++k)
-#define FX_ACC(val) { if (act[k]) { acc_f[k] = (val); acc_is_f[k] = true; } }
+                    const bool want_acc = (w0 & F_ACC) != 0u;         // nobody can observe the accumulator otherwise (it is overwritten first)
+#define FX_ACC(val) { if (want_acc && act[k]) { acc_f[k] = (val); acc_is_f[k] = true; } }
                     switch (uop) {
                     case U_MACS: {   // :1077-1085 (MACINTS :1095-1103 is identical)
                         FX_EACH { const float t = __fadd_rn(a[k], __fmul_rn(x[k], y[k])); FX_ACC(t); r[k] = sat1(t); } break; }
@@ -497,10 +529,11 @@ __global__ void __launch_bounds__(128, 3) fx_interp_kernel(const Params p) {
                         }
                         break; }
                     case U_INTERP: { // :1180-1187
-                        FX_EACH {
-                            const double d = __dadd_rn(__dmul_rn(__dsub_rn(1.0, (double)x[k]), (double)a[k]), (double)__fmul_rn(x[k], y[k]));
-                            const float t = __double2float_rn(d); FX_ACC(t); r[k] = sat1(t);
-                        } break; }
+                        double omx[K];
+                        float t[K];
+                        one_minus<K>(x.v, omx);
+                        interp_core<K>(omx, a.v, x.v, y.v, t);
+                        FX_EACH { FX_ACC(t[k]); r[k] = sat1(t[k]); } break; }
                     case U_SKIP:                                      // :1175-1179
                         if (SKIP) { const Vec<K> c = vload<K>(at(0));
                             FX_EACH { if (act[k] && __int2float_rn(cvt_x86(x[k])) == c[k]) skip[k] = cvt_x86(y[k]); } }
@@ -550,21 +583,21 @@ __global__ void __launch_bounds__(128, 3) fx_interp_kernel(const Params p) {
                     }
 #undef FX_ACC
                     if (writes_r) {
-                        if (!SKIP) vstore<K>(pr, r);
+                        if (!PRED) vstore<K>(pr, r);
                         else { FX_EACH { if (act[k]) pr[k] = r[k]; } }
-                        if ((w0 & F_CCR) || last_sample) {            // setCCR :211-232 (after the R store: R may be ccr)
-                            if (!SKIP) { Vec<K> c; FX_EACH { c[k] = ccr_of(r[k]); } vstore<K>(at(0), c); }
+                        if (w0 & F_CCR) {                             // setCCR :211-232 (after the R store: R may be ccr)
+                            if (!PRED) { Vec<K> c; FX_EACH { c[k] = ccr_of(r[k]); } vstore<K>(at(0), c); }
                             else { FX_EACH { if (act[k]) at(0)[k] = ccr_of(r[k]); } }
                         }
                     }
-                    if (SKIP) { FX_EACH { count[k] += act[k] ? 1u : 0u; } }   // :1222
+                    if (PRED) { FX_EACH { count[k] += act[k] ? 1u : 0u; } }   // :1222 (unpredicated instructions: p.n_unpred per first pass)
                     if (w0 & F_OUT) {                                 // :1229-1233 (after EVERY executed instruction)
                         if (!SKIP && (w0 & F_OUT_DIRECT)) {
                             // R was just written by this instruction and nothing later in the sample period
                             // touches the channel: the value is the period's output (:1248)
                             if (valid) vstore<K>(out_s + (size_t)(w0 >> 24) * out_cstride, r);
                             if (last_sample) vstore<K>(at(wB.w), r);
-                        } else if (!SKIP) vstore<K>(at(wB.w), vload<K>(pr));
+                        } else if (!PRED) vstore<K>(at(wB.w), vload<K>(pr));
                         else { float* const pl = at(wB.w); FX_EACH { if (act[k]) pl[k] = pr[k]; } }
                     }
                     if (K == 1 && SKIP && EXT) {          // debug trace (fx8010_gpu_trace), compiled into one variant only
@@ -581,11 +614,14 @@ __global__ void __launch_bounds__(128, 3) fx_interp_kernel(const Params p) {
                 };
                 {
                     uint4 nA = prog[0], nB = prog[1];
+                    const bool all_pred = SKIP && pass > 0;           // an extra pass: contexts that saw END idle through it on their skip counters
                     for (int pc = 0; pc < n_exec; ++pc) {
                         const uint4 wA = nA, wB = nB;
                         nA = prog[2 * pc + 2]; nB = prog[2 * pc + 3]; // the slot is padded with one extra instruction
-                        exec_instr(wA, wB);
+                        if (SKIP && ((wA.x & F_PRED) || all_pred)) exec_instr(std::true_type{}, wA, wB);
+                        else exec_instr(std::false_type{}, wA, wB);
                     }
+                    if (SKIP && pass == 0) { FX_EACH { count[k] += n_unpred; } }
                 }
                 ++pass;
                 if (!SKIP) break;

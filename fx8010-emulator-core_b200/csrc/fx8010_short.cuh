@@ -204,10 +204,10 @@ __global__ void __launch_bounds__(128, 3) fx_short_kernel(const Params p) {
             case U_LIMITN: {                                  // :1169-1174
                 SH_EACH { r[k] = (a[k] < y[k]) ? x[k] : y[k]; accv[k] = r[k]; } SH_WRITE(true) } break;
             case U_INTERP: {                                  // :1180-1187
-                SH_EACH {
-                    const double d = __dadd_rn(__dmul_rn(__dsub_rn(1.0, (double)x[k]), (double)a[k]), (double)__fmul_rn(x[k], y[k]));
-                    accv[k] = __double2float_rn(d); r[k] = sat1(accv[k]);
-                } SH_WRITE(true) } break;
+                double omx[K];
+                one_minus<K>(x.v, omx);
+                interp_core<K>(omx, a.v, x.v, y.v, accv.v);
+                SH_EACH { r[k] = sat1(accv[k]); } SH_WRITE(true) } break;
             case U_LOG: case U_EXP: case SH_TAB_SMEM: case SH_TAB_IMM: {   // :1113-1125, linearInterpolate :283-296
                 int idx[K];
                 double di[K];

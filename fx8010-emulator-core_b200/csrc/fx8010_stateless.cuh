@@ -46,6 +46,10 @@ constexpr int SL_STRIDE_SHIFT = 20;          // [20:31) bytes between consecutiv
 constexpr uint32_t SL_BUF = 1u << 31;        // input-stage row: add the offset of the current stage buffer
 constexpr uint32_t F_ST_LAST = 1u << 17;     // R is never read by the program: store it on the batch-final sample only
 constexpr int SL_MAX_M = 64;             // a serial (recurrent) launch has few warps: its batch is also how far the input stage runs ahead of the arithmetic
+constexpr uint32_t F_FUSE = 1u << 21;        // the NEXT instruction is a MACS/MACSN whose only varying operand is this instruction's result, and nobody
+                                             // else reads that result: both run in one sample loop, the value is forwarded in a hardware register and
+                                             // never touches shared memory (wB.w: bit 0 = forwarded into the product (X or Y) rather than the addend A,
+                                             // bit 1 = MACSN).  The cold FINAL / CCR-live copies ignore the flag and run the two instructions one by one.
 constexpr int MAX_FUSED_BLOCKS = 32;         // sample blocks one launch of a time-split program can cover
 constexpr int SL_CARRY_SHIFT = 18;           // w0 bits 18..20: operand A / X / Y is this instruction's OWN result of the previous sample
                                              // (a self recurrence): row (m - 1) mod M on the first sample of a batch, then forwarded
@@ -131,6 +135,11 @@ struct SLInstr {
     bool st_r, st_c, st_o;              // store R / CCR / the output block
     float* qo;                          // output block slot of the current sample
     int n_m;
+    // fused consumer (F_FUSE): R2 = sat(fc0 + r * fc1) (result forwarded into the product) or sat(r + fc0) (into the addend; fc0 = X2 * Y2)
+    uint32_t qr2, sr2;                  // running shared address / per-sample stride of the consumer's R
+    bool st_r2, st_o2;
+    float* qo2;
+    float fc0[4], fc1[4];
 };
 
 // Runs ONE instruction over the batch.  CM = how results are carried from sample to sample: 0 nothing (stateless
@@ -138,7 +147,7 @@ struct SLInstr {
 // The sample loop is software-pipelined over TWO operand register sets (unrolled by two, no register moves): the
 // operands of sample m + 1 go in flight before the arithmetic of sample m, operands whose row does not change are
 // read once, and a carried operand is written straight into the next set — a recurrence's chain holds arithmetic only.
-template <int K, bool FINAL, bool CCRV, int CM, bool TRAM>
+template <int K, bool FINAL, bool CCRV, int CM, bool TRAM, int FUSE = 0>     // FUSE: 0 none, 1 result forwarded into the consumer's addend, 2 into its product
 __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr& I) {
     const uint64_t Nl = cx.Nl;
     const uint32_t w0 = I.w0, uop = I.uop;
@@ -165,7 +174,14 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
             if (LOADS_XY && ly) { I.qy += I.sy; Y##NXT = lds<K>(I.qy); }                                         \
         }                                                                                                        \
         __VA_ARGS__                                                                                              \
-        SL_WRITE(SETS_ACC)                                                                                       \
+        if (FUSE == 0) { SL_WRITE(SETS_ACC) }                                                                    \
+        else {      /* the consumer MACS / MACSN (:1077-1094) on the forwarded result; this instruction's own R is dead in the bulk path */ \
+            Vec<K> r2;                                                                                           \
+            SL_EACH { r2[k] = sat1(FUSE == 1 ? __fadd_rn(r[k], I.fc0[k]) : __fadd_rn(I.fc0[k], __fmul_rn(r[k], I.fc1[k]))); } \
+            if (I.st_r2) sts<K>(I.qr2, r2);                                                                      \
+            if (I.st_o2) vstore<K>(I.qo2, r2);                                                                   \
+            I.qr2 += I.sr2; I.qo2 += Nl;                                                                         \
+        }                                                                                                        \
         if (CM == 1) A##NXT = r;                                                                                 \
         else if (CM == 2) { SL_EACH { if (I.ca) A##NXT[k] = r[k]; if (I.cx) X##NXT[k] = r[k]; if (I.cy) Y##NXT[k] = r[k]; } } \
         ++m; I.qr += I.sr; I.qccr += I.sccr; I.qo += Nl;                                                         \
@@ -218,11 +234,9 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
         double omx[K];
         SL_EACH { omx[k] = __dsub_rn(1.0, (double)X0[k]); }
         SL_LOOP(true, true,
-            if (x_varies) { SL_EACH { omx[k] = __dsub_rn(1.0, (double)x[k]); } }
-            SL_EACH {
-                const double d = __dadd_rn(__dmul_rn(omx[k], (double)a[k]), (double)__fmul_rn(x[k], y[k]));
-                accv[k] = __double2float_rn(d); r[k] = sat1(accv[k]);
-            })
+            if (x_varies) one_minus<K>(x.v, omx);
+            interp_core<K>(omx, a.v, x.v, y.v, accv.v);
+            SL_EACH { r[k] = sat1(accv[k]); })
         break; }
     case U_LOG:
     case U_EXP: {
@@ -256,7 +270,7 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
         // writeSmallDelay :909-917); T = 0 iTRAM, 1 xTRAM (a constant, so that the pointers stay in registers).
         // The final-state pass re-runs arithmetic only: TRAM state is already final.
 #define SL_TRAM_READ(T)                                                                                          \
-        if (TRAM && !FINAL) {                                                                                    \
+        if (TRAM && !FINAL && FUSE == 0) {                                                                                    \
             const int size = cx.rsize[T];                                                                        \
             if (cx.tram_fast) {    /* the rows were prefetched with the batch: only the pointer moves (a split column's pointers are set by the kernel) */ \
                 if (!cx.split) { SL_EACH { int32_t& rp = cx.tp[2 * T + 1][k]; rp += n_m; rp -= (rp >= size) ? size : 0; } } \
@@ -277,7 +291,7 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
             }                                                                                                    \
         }
 #define SL_TRAM_WRITE(T)                                                                                         \
-        if (TRAM && !FINAL) {                                                                                    \
+        if (TRAM && !FINAL && FUSE == 0) {                                                                                    \
             const int size = cx.rsize[T];                                                                        \
             float* const ring = cx.ring[T];                                                                      \
             int pos[K];                                                                                          \
@@ -343,6 +357,25 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
         I.st_o = (w0 & F_OUT_DIRECT) && cx.valid;
         I.qo = cx.out_b + (size_t)(w0 >> 24) * cx.out_cstride + (size_t)m_lo * cx.Nl;
         if (FINAL || CCRV) sl_run<K, FINAL, CCRV, 2, TRAM>(p, cx, I);          // cold paths: one general copy
+        else if (w0 & F_FUSE) {
+            // producer + consumer in one sample loop: nA / nB hold the consumer (a MACS / MACSN with two batch-constant operands)
+            const uint32_t v0 = nA.x;
+            const bool into_product = wB.w & 1u, negate = wB.w & 2u;
+            const Vec<K> ca = lds<K>(cx.col_s + (nA.z & SL_OFF_MASK)), cxx = lds<K>(cx.col_s + (nA.w & SL_OFF_MASK)), cy = lds<K>(cx.col_s + (nB.x & SL_OFF_MASK));
+            const bool fwd_x = into_product && (wB.w & 4u);                    // which factor of the product is the forwarded one
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (into_product) { const float m = fwd_x ? cy[k] : cxx[k]; I.fc0[k] = ca[k]; I.fc1[k] = negate ? -m : m; }
+                else { const float pr = __fmul_rn(cxx[k], cy[k]); I.fc0[k] = negate ? -pr : pr; I.fc1[k] = 0.0f; }
+            }
+            I.sr2 = SL_STRIDE(nA.y); I.qr2 = SL_ADDR(nA.y);
+            I.st_r2 = !(v0 & F_ST_LAST);
+            I.st_o2 = (v0 & F_OUT_DIRECT) && cx.valid;
+            I.qo2 = cx.out_b + (size_t)(v0 >> 24) * cx.out_cstride + (size_t)m_lo * cx.Nl;
+            if (into_product) sl_run<K, false, false, 0, TRAM, 2>(p, cx, I); else sl_run<K, false, false, 0, TRAM, 1>(p, cx, I);
+            ++pc;                                                              // the consumer is done
+            nA = cx.prog[2 * pc + 2]; nB = cx.prog[2 * pc + 3];
+        }
         else if (cbits == 0u) sl_run<K, false, false, 0, TRAM>(p, cx, I);
         else if (cbits == 1u) sl_run<K, false, false, 1, TRAM>(p, cx, I);
         else sl_run<K, false, false, 2, TRAM>(p, cx, I);

@@ -168,6 +168,13 @@ FX8010_API int fx8010_gpu_process_batch_host(fx8010_gpu* h, const float* in, flo
  * buffers; with pageable memory the driver makes the copies synchronous anyway). */
 FX8010_API int fx8010_gpu_process_batch_host_async(fx8010_gpu* h, const float* in, float* out, int n_samples);
 
+/* Same for a handle whose instances are a SLICE of a wider host block: `in` / `out` point at this handle's first
+ * instance inside host buffers laid out [channel][sample][host_instances] (host_instances >= n_instances); rows are
+ * moved with strided copies.  wait == 0 queues the work like the _async form.  This is what the multi-GPU executor
+ * (fx8010_multi.h) uses to gather every device's outputs into ONE host buffer. */
+FX8010_API int fx8010_gpu_process_batch_host_slice(fx8010_gpu* h, const float* in, float* out, int n_samples,
+                                                   size_t host_instances, int wait);
+
 /* ---- the caller's block loop -------------------------------------------
  * The reference's driver changes sliders BETWEEN process() calls, every 8 sample periods
  * (source/main.cpp:107-114: setRegisterValue, then process).  A batched caller would have to cut its
@@ -267,7 +274,7 @@ typedef struct fx8010_launch_info {
     int32_t last_smem_bytes;
     int32_t last_late_wait;               /* the last launch postponed its wait for its predecessor (see FX8010_OPT_STREAM_EXCLUSIVE) */
     int32_t last_fused_blocks;            /* sample blocks the last launch covered (fx8010_gpu_process_blocks) */
-    int32_t kernel_variant;               /* bit0 SKIP, bit1 TRAM/noise/MACMV, bit2 stateless, bit3 instruction-major kernel, bit5 short-program kernel, bits 8..15 instances per thread, bits 16.. samples per batch */
+    int32_t kernel_variant;               /* bit0 SKIP, bit1 TRAM/noise/MACMV, bit2 stateless, bit3 instruction-major kernel, bit5 short-program kernel, bit6 producer/consumer pairs fused, bits 8..15 instances per thread, bits 16.. samples per batch */
 } fx8010_launch_info;
 FX8010_API int fx8010_gpu_get_launch_info(fx8010_gpu* h, fx8010_launch_info* out);
 

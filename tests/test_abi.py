@@ -25,6 +25,30 @@ def test_gpu_header_symbols_exported(fx):
     assert set(names) == set(fx.GPU_SYMBOLS), "python binding table out of sync with the header"
 
 
+def test_multi_header_symbols_exported(fx):
+    names = declared("fx8010_multi.h")
+    assert "fx8010_multi_create" in names and "fx8010_multi_process_batch_host" in names
+    lib = ctypes.CDLL(fx.GPU_SO)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/fx8010_multi.h but not exported"
+    assert set(names) == set(fx.MULTI_SYMBOLS)
+
+
+def test_multi_shard_ranges_match_the_python_glue(fx):
+    """Contiguous ranges [g * N / G, (g + 1) * N / G): every instance in exactly one shard, same split as the per-rank
+    split bench.py uses under torchrun (fx.shard_range)."""
+    L = fx.gpu_lib()
+    for n, G in [(65536, 8), (262144, 8), (4096, 3), (7, 7), (1000, 6), (5, 2)]:
+        covered = 0
+        for g in range(G):
+            lo, hi = ctypes.c_int(), ctypes.c_int()
+            L.fx8010_multi_shard_range(n, g, G, ctypes.byref(lo), ctypes.byref(hi))
+            assert (lo.value, hi.value) == fx.shard_range(n, g, G)
+            assert lo.value == covered
+            covered = hi.value
+        assert covered == n
+
+
 def test_host_header_symbols_exported(fx):
     names = declared("fx8010_host.h")
     assert len(names) >= 25

@@ -304,3 +304,121 @@ def test_unread_input_preload_and_noop_latch_refresh(fx, po, text):
     from test_gpu_parity import run_case
     rng = np.random.default_rng(81)
     run_case(fx, po, text, 96, [40, 9], rng, what="corner")
+
+
+# ---- producer / consumer pairs of the instruction-major kernel -----------------------------------------------------
+
+PAIR_PROGS = {
+    "product_x_then_rw": "static a\nstatic b\ninput in_l 0\ncontrol g = 0.5\ncontrol o = 0.1\noutput out_l 0\nexp a, in_l, 7, 0\nmacs b, o, a, g\nmacsn out_l, b, 0.5, 0.25\nend",
+    "product_y_macsn": "static a\ninput in_l 0\ncontrol g = 0.7\noutput out_l 0\ninterp a, 0.25, g, in_l\nmacsn out_l, 0.1, g, a\nend",
+    "addend": "static a\ninput in_l 0\ncontrol g = 0.7\noutput out_l 0\nlimit a, in_l, 0.3, g\nmacs out_l, a, g, 0.5\nend",
+    "addend_macsn": "static a\ninput in_l 0\noutput out_l 0\ntstneg a, in_l, 0.5, 0\nmacsn out_l, a, 0.5, 0.5\nend",
+    "macints_consumer": "static a\ninput in_l 0\ncontrol g = 0.9\noutput out_l 0\nmacw a, in_l, in_l, 0.75\nmacints out_l, 0, a, g\nend",
+    "inside_delay_line": "static a\nstatic rd\nstatic t\ninput in_l 0\noutput out_l 0\nitramsize 300 \nidelay read, rd, at, 0\nmacs a, in_l, rd, 0.5\n"
+                         "idelay write, a, at, 0\nlog t, rd, 2, 0\nmacs out_l, 0.1, t, 0.5\nend",
+    "after_recurrence": "static t\nstatic s\ninput in_l 0\ncontrol c = 0.2\noutput out_l 0\ninterp s, s, c, in_l\nexp t, s, 5, 0\nmacs out_l, 0, t, 0.9\nend",
+    "two_pairs": "static a\nstatic b\nstatic d\ninput in_l 0\ncontrol g = 0.6\noutput out_l 0\nlog a, in_l, 3, 0\nmacs b, 0, a, g\nacc3 d, b, in_l, 0.1\nmacsn out_l, 0.05, d, g\nend",
+}
+
+
+@pytest.mark.parametrize("name", sorted(PAIR_PROGS))
+@pytest.mark.parametrize("mode", ["auto", "nopairs", "M2", "K1"])
+def test_producer_consumer_pairs(fx, po, name, mode, monkeypatch):
+    """A result with exactly one reader — the next instruction, a MACS/MACSN with two batch-constant operands — is
+    forwarded in a register instead of going through shared memory; same bits either way."""
+    from test_gpu_parity import run_case
+    if mode == "nopairs":
+        monkeypatch.setenv("FX8010_NO_PAIRS", "1")
+    elif mode == "M2":
+        monkeypatch.setenv("FX8010_TUNE_M", "2")
+    elif mode == "K1":
+        monkeypatch.setenv("FX8010_TUNE_K", "1")
+    rng = np.random.default_rng(90)
+    n = 200
+    ctl = {k: rng.random(n).astype(np.float32) for k in ("g", "o", "c") if f"control {k} " in PAIR_PROGS[name]}
+    info = run_case(fx, po, PAIR_PROGS[name], n, [70, 31, 1], rng, controls=ctl, what=f"{name} {mode}")
+    assert info.kernel_variant & 8, "instruction-major kernel expected"
+    assert bool(info.kernel_variant & 64) == (mode != "nopairs"), "pair fusion flag"
+
+
+# ---- the multi-GPU executor (include/fx8010_multi.h) ---------------------------------------------------------------
+
+def _multi_case(fx, po, devices, text, n, s_blocks, controls, rng, what):
+    prog = fx.Program(text)
+    assert prog.loaded, prog.errors()
+    img = po.Image(prog.instructions(), prog.registers(), prog.itram_size, prog.xtram_size, prog.controls(), prog.tables())
+    orc = po.Oracle(img, n, 1)
+    m = fx.MultiGpu(devices, n, 1)
+    try:
+        assert [hi - lo for lo, hi in m.shards()] == [fx.shard_range(n, g, len(devices))[1] - fx.shard_range(n, g, len(devices))[0] for g in range(len(devices))]
+        m.load_program(prog)
+        for name, v in controls.items():
+            m.set_controls(prog.reg_index(name), v)
+            orc.set_register(prog.reg_index(name), v)
+        pin_in, own_i = fx.pinned_array((1, max(s_blocks), n))
+        pin_out, own_o = fx.pinned_array((1, max(s_blocks), n))
+        for b, s in enumerate(s_blocks):
+            x = (1.8 * rng.random((1, s, n)) - 0.9).astype(np.float32)
+            pin_in[0, :s] = x[0]
+            y = m.process_host(pin_in[:, :s].copy(), out=None)          # pageable buffers
+            yo = orc.process(x)
+            assert_bits_equal(y, yo, f"{what} block {b}")
+        # page-locked buffers, queued calls: two blocks in flight, then one synchronize
+        xa = (1.8 * rng.random((1, s_blocks[0], n)) - 0.9).astype(np.float32)
+        xb = (1.8 * rng.random((1, s_blocks[0], n)) - 0.9).astype(np.float32)
+        pa, oa = fx.pinned_array(xa.shape); pb, ob = fx.pinned_array(xb.shape)
+        ya, oya = fx.pinned_array(xa.shape); yb, oyb = fx.pinned_array(xb.shape)
+        pa[...] = xa; pb[...] = xb
+        m.process_host(pa, out=ya, wait=False)
+        m.process_host(pb, out=yb, wait=False)
+        m.synchronize()
+        assert_bits_equal(np.array(ya), orc.process(xa), f"{what} queued block a")
+        assert_bits_equal(np.array(yb), orc.process(xb), f"{what} queued block b")
+        assert_bits_equal(m.registers(), orc.registers, f"{what} registers")
+        assert m.count_total() == int(orc.counts.sum())
+        assert m.flags() == orc.flags
+        for name in controls:
+            assert_bits_equal(m.get_register(prog.reg_index(name)), orc.registers[prog.reg_index(name)], f"{what} {name}")
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4", "random"])
+def test_multi_executor_shards_on_one_device(fx, po, name):
+    """Three shards with uneven ranges (1 000 instances) on device 0: the plumbing of the multi-GPU executor — ranges,
+    per-shard threads, strided scatter/gather into ONE host buffer — checked bit for bit, whatever the number of GPUs."""
+    rng = np.random.default_rng(101)
+    n = 1000
+    text, ctl = {"cfg2": (progs.CFG2_LOG_GAIN, {"volume": rng.random(n).astype(np.float32)}),
+                 "cfg3": (progs.cfg3_delay(100), {}),
+                 "cfg4": (progs.CFG4_ONEPOLE, {"filter_cutoff": (0.001 + 0.998 * rng.random(n)).astype(np.float32)}),
+                 "random": (progs.random_program(rng, 40, xtram=True), {})}[name]
+    _multi_case(fx, po, [0, 0, 0], text, n, [130, 57], ctl, rng, f"multi x3 {name}")
+
+
+def test_multi_executor_two_gpus(fx, po):
+    """cfg4's shape on two GPUs: 65 536 instances -> 32 768 per device, outputs gathered into one page-locked buffer."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (runs in the multi-GPU tier)")
+    rng = np.random.default_rng(102)
+    n = 65536
+    idx = sample_instances(n, 64, rng)
+    prog = fx.Program(progs.CFG4_ONEPOLE)
+    img = po.Image(prog.instructions(), prog.registers(), prog.itram_size, prog.xtram_size, prog.controls(), prog.tables())
+    orc = po.Oracle(img, len(idx), 1)
+    cutoff = (0.001 + 0.998 * np.arange(n) / (n - 1)).astype(np.float32)
+    m = fx.MultiGpu([0, 1], n, 1)
+    try:
+        m.load_program(prog)
+        m.set_controls(prog.reg_index("filter_cutoff"), cutoff)
+        orc.set_register(prog.reg_index("filter_cutoff"), cutoff[idx].copy())
+        pin, o1 = fx.pinned_array((1, 1024, n)); pout, o2 = fx.pinned_array((1, 1024, n))
+        for b in range(2):
+            pin[0] = progs.sine_bank(n, 1024, rng, start=b * 1024)
+            m.process_host(pin, out=pout)
+            yo = orc.process(np.ascontiguousarray(pin[0][:, idx]).reshape(1, 1024, len(idx)))
+            assert_bits_equal(np.ascontiguousarray(pout[0][:, idx])[None], yo, f"2 GPUs block {b}")
+        assert_bits_equal(m.registers()[:, idx], orc.registers, "2 GPUs registers")
+    finally:
+        m.close()
