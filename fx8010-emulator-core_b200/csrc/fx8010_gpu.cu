@@ -116,7 +116,7 @@ struct fx8010_gpu {
     std::vector<uint8_t> sl_carry;               // per instruction: bit o set = operand o (A, X, Y) is the instruction's own previous result
     std::vector<uint8_t> sl_carried_reg;         // per register: some instruction carries it from sample to sample
     std::vector<uint8_t> sl_fuse;                // per instruction: 0, or 0x80 | bits (fx8010_stateless.cuh F_FUSE) when the NEXT executed instruction is fused into it
-    int use_pairs = 1;
+    int use_pairs = 1, use_tsplit = 1;
     int use_carry = 1;
     bool short_ok = false;                       // SKIP-free, nobody reads ccr, no noise/MACMV, every channel written: fx_short_kernel when short enough
     bool short_attr_set[3][2][SH_MAX_NI_HOST] = {};
@@ -215,6 +215,8 @@ void pre_targets(const fx8010_gpu* h, const fx8010_instr& in, bool& pa, bool& px
         else if (h->regs[in.y].is_noise) noise_reg = in.y;
     }
 }
+
+int encoded_length(const fx8010_gpu* h);
 
 // Load-time analysis: written set, feature flags, statelessness.
 void analyse(fx8010_gpu* h) {
@@ -382,6 +384,7 @@ void analyse(fx8010_gpu* h) {
     }
     if (!tram_ok) { h->sl_n_tr = 0; }
     h->sl_ok = !h->has_skip && !has_noise_or_macmv && (!h->sl_tram || tram_ok) && all_ch && !h->nop_out;
+    if (4 * (encoded_length(h) + 1) > SLOT_WORDS) h->sl_ok = false;     // four words per instruction in this kernel's encoding: longer programs take the general interpreter
     h->sl_serial = h->sl_tram;
     h->sl_carry.assign(n, 0); h->sl_carried_reg.assign(nr, 0);
     std::vector<int> n_writers(nr, 0);
@@ -463,7 +466,8 @@ void analyse(fx8010_gpu* h) {
             if (i < 0 || h->sl_fuse[i]) continue;
             const fx8010_instr& pr = h->instrs[i];
             const Uop up = uop_of(h, pr);
-            if (!writes_r(up) || up == U_MACMV || (uc != U_MACS && uc != U_MACSN)) continue;
+            const bool tram_consumer = (uc == U_IWRITE || uc == U_XWRITE);      // `macs a, ...` / `idelay write, a, at, 0`: the result goes straight to the ring
+            if (!writes_r(up) || up == U_MACMV || (uc != U_MACS && uc != U_MACSN && !tram_consumer)) continue;
             const int g = pr.r;
             if (g == 0 || h->regs[g].type == FX_REG_OUTPUT || h->regs[g].type == FX_REG_INPUT || n_writers[g] != 1 || n_reads[g] != 1) continue;
             if (h->sl_carry[i] || h->sl_carry[j] || h->sl_carried_reg[g]) continue;
@@ -471,7 +475,7 @@ void analyse(fx8010_gpu* h) {
             for (int q = 0; q < h->sl_n_tr; ++q) if (h->sl_tr[q].reg == g) is_stream = true;
             if (is_stream) continue;
             const int pos = c.a == g ? 0 : (c.x == g ? 1 : (c.y == g ? 2 : -1));
-            if (pos < 0) continue;
+            if (pos < 0 || (tram_consumer && pos != 0)) continue;
             const int others[2] = {pos == 0 ? c.x : c.a, pos == 2 ? c.x : c.y};
             bool constant = true;
             for (int o : others) constant = constant && !h->written[o] && h->regs[o].type != FX_REG_INPUT && h->row_of[o] >= 0;
@@ -479,7 +483,8 @@ void analyse(fx8010_gpu* h) {
             bool pre_a, pre_x, pre_y; int nz;
             pre_targets(h, c, pre_a, pre_x, pre_y, nz);
             if (pre_a || pre_x || pre_y || nz >= 0) continue;
-            h->sl_fuse[i] = (uint8_t)(0x80 | (pos != 0 ? 1 : 0) | (uc == U_MACSN ? 2 : 0) | (pos == 1 ? 4 : 0));
+            if (tram_consumer) h->sl_fuse[i] = (uint8_t)(0x80 | 8 | (uc == U_XWRITE ? 16 : 0));
+            else h->sl_fuse[i] = (uint8_t)(0x80 | (pos != 0 ? 1 : 0) | (uc == U_MACSN ? 2 : 0) | (pos == 1 ? 4 : 0));
             fused_away[g] = 1;
             prev = -1;                                           // the consumer cannot start another pair
         }
@@ -549,13 +554,25 @@ void encode_stateless(fx8010_gpu* h, int K, int B, int M) {
             else { w0 |= F_TAB_IMM; aux = (uint32_t)h->tab_of[i] << 24; }
         }
         if (h->sl_fuse[i]) w0 |= F_FUSE;
-        h->h_prog[2 * e] = make_uint4(w0, sl_word(h, in.r, B, K, M), sl_word(h, in.a, B, K, M), sl_word(h, in.x, B, K, M));
-        h->h_prog[2 * e + 1] = make_uint4(sl_word(h, in.y, B, K, M), aux, sl_word(h, 0, B, K, M), (uint32_t)(h->sl_fuse[i] & 0x7f));
+        // Four words per instruction, everything pre-computed (format: fx8010_stateless.cuh, sl_exec): offset at sample 0 and
+        // bytes per sample of R, A, X, Y and CCR.  A self-carried operand (this instruction's own previous result) starts
+        // at the register's row M - 1 and does not move; bit 31 of an offset marks a stage row (the buffer in use is added).
+        const uint32_t wr = sl_word(h, in.r, B, K, M), wc = sl_word(h, 0, B, K, M);
+        const uint32_t wo[3] = {sl_word(h, in.a, B, K, M), sl_word(h, in.x, B, K, M), sl_word(h, in.y, B, K, M)};
+        uint32_t off[3], str[3];
+        for (int o = 0; o < 3; ++o) {
+            const bool carried = (h->sl_carry[i] >> o) & 1;
+            str[o] = carried ? 0u : sl_stride(wo[o]);
+            off[o] = carried ? (wo[o] & SL_OFF_MASK) + (uint32_t)(M - 1) * sl_stride(wo[o]) : ((wo[o] & SL_OFF_MASK) | (wo[o] & SL_BUF));
+        }
+        h->h_prog[4 * e] = make_uint4(w0, aux, (uint32_t)(h->sl_fuse[i] & 0x7f), 0);
+        h->h_prog[4 * e + 1] = make_uint4(wr & SL_OFF_MASK, off[0], off[1], off[2]);
+        h->h_prog[4 * e + 2] = make_uint4(sl_stride(wr), str[0], str[1], str[2]);
+        h->h_prog[4 * e + 3] = make_uint4(wc & SL_OFF_MASK, sl_stride(wc), 0, 0);
         ++e;
     }
     h->n_exec = e;
-    h->h_prog[2 * e] = make_uint4((uint32_t)U_NOP, 0, 0, 0);
-    h->h_prog[2 * e + 1] = make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < 4; ++j) h->h_prog[4 * e + j] = make_uint4(j == 0 ? (uint32_t)U_NOP : 0u, 0, 0, 0);   // pad record: the kernel prefetches pc + 1
     h->sl_load.clear(); h->sl_wb.clear();
     for (int r = 0; r < nr; ++r) {
         if (h->sl_class[r] == ROW_RO) h->sl_load.push_back(make_uint2(sl_word(h, r, B, K, M), (uint32_t)r));
@@ -821,34 +838,71 @@ int known_tram_distance(const fx8010_gpu* h) {
     return best;
 }
 
+// How many consecutive sample periods of a delay-line program are INDEPENDENT of one another, when the host can tell
+// (same knowledge as above; 0 = unknown or a register recurrence exists).  A READ at period t fetches what the WRITE of
+// period t - D stored (D = the distance above), and the WRITE of period t + (size - D) overwrites the slot the READ of
+// period t fetched; within fewer periods than both, no period sees another's effect, so they can run in any order —
+// across thread blocks: the time axis of such a launch is cut into segments exactly like a stateless program's
+// (cfg3 with itramsize >= the block length: one fully parallel launch instead of 1 024 serial sample periods).
+int known_tram_span(const fx8010_gpu* h) {
+    if (!h->tram_ptrs_pristine || !h->sl_tram || h->sl_n_tr == 0) return 0;
+    for (uint8_t c : h->sl_carry) if (c) return 0;
+    int span = 1 << 30;
+    for (const fx8010_instr& in : h->instrs) {
+        const Uop u = uop_of(h, in);
+        if (u == U_IWRITE) span = std::min(span, h->itram_size);
+        if (u == U_XWRITE) span = std::min(span, h->xtram_size);
+        if ((u == U_IWRITE || u == U_XWRITE || u == U_IREAD || u == U_XREAD) && !h->reg_uniform[in.y]) return 0;
+    }
+    for (int q = 0; q < h->sl_n_tr; ++q) {
+        const fx8010_gpu::TramStream& t = h->sl_tr[q];
+        if (t.w_yreg < 0) continue;                        // a ring nobody writes: its periods are independent anyway
+        const int size = t.isx ? h->xtram_size : h->itram_size;
+        if (size <= 0) return 0;
+        const int pos = std::min(std::max(cvt_x86_host(h->reg_value[t.yreg]), 0), size - 1);
+        const int wpos = std::min(std::max(cvt_x86_host(h->reg_value[t.w_yreg]), 0), size - 1);
+        const int d = (wpos + pos) % size;
+        const int D = (d == 0 && !t.w_first) ? size : d;   // read-after-write distance
+        if (D <= 0) return 0;
+        span = std::min(span, D);
+        if (D < size) span = std::min(span, size - D);      // write-after-read distance
+    }
+    // a ring with a WRITE but no READ stream, or a READ of a ring nobody writes, constrains nothing beyond the ring size
+    return span == (1 << 30) ? 0 : span;
+}
+constexpr int MIN_TSPLIT_SPAN = 64;      // shorter spans would mean too many tiny launches: the serial kernel (with its sample split) takes those
+
 // Geometry for the stateless kernel: all the parallelism a launch needs comes from cutting the time
 // axis, so K is as wide as alignment allows and the segment count fills exactly one wave.
-int plan_stateless(fx8010_gpu* h, const float*, const float*, unsigned align, int n_samples, int n_blk, bool may_overlap, Launch& L) {
+int plan_stateless(fx8010_gpu* h, const float*, const float*, unsigned align, int n_samples, int n_blk, bool may_overlap, bool tsplit, Launch& L) {
+    // tsplit: a delay-line program whose periods within this launch are known to be independent (known_tram_span): planned like a stateless one
+    const bool serial = h->sl_serial && !tsplit;
     const int N = h->N;
     auto aligned = [&](int K) { return N % K == 0 && (align & (unsigned)(K * 4 - 1)) == 0; };   // align: low bits of every buffer address and channel stride (bytes)
     int K = 4;
     while (K > 1 && !aligned(K)) K >>= 1;
-    bool splittable = h->sl_serial && h->sl_tram && h->use_split;     // (see the sample split below)
+    bool splittable = serial && h->sl_tram && h->use_split;     // (see the sample split below)
     for (uint8_t c : h->sl_carry) splittable = splittable && !c;
-    if (h->sl_serial)                        // one time segment: the warps come from the instances alone — keep two per SM at least
+    if (serial)                              // one time segment: the warps come from the instances alone — keep two per SM at least
         while (K > 1 && (long)N / K / 32 * (splittable ? 4 : 1) < 2L * h->num_sms * (splittable ? 2 : 1)) K >>= 1;   // (cfg4, 65 536 instances: K = 4 147 us, K = 2 158 us, K = 1 155 us; cfg3 with the split: K = 2 156 us, K = 1 180 us)
     if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
     // time-split launches: 64-thread blocks with batches of 8 samples (decode amortised over twice the samples at the
     // same shared-memory footprint as 128 x 4; cfg2: 8.7 vs 9.2 us)
-    int B = h->tune_B ? h->tune_B : (h->sl_serial ? 128 : 64);
+    int B = h->tune_B ? h->tune_B : (serial ? 128 : 64);
     while (B > 32 && (N / K + B - 1) / B * B >= 2 * (N / K) && N / K <= B / 2) B >>= 1;      // tiny N: do not launch mostly-idle blocks
-    if (h->sl_serial && !h->tune_B)          // one time segment: only N / K threads — spread them over the SMs
+    if (serial && !h->tune_B)                // one time segment: only N / K threads — spread them over the SMs
         while (B > 32 && (N / K + B - 1) / B < 2 * h->num_sms) B >>= 1;
     // A serial launch has few warps, and the batch is also how far the input stage runs ahead: make it deep.
     // (a split program decodes every instruction once per thread and batch: with a delay known to exceed two 64-sample
     //  batches the longer batch halves that cost — cfg3: 152 -> 98 us)
     const bool deep = splittable && known_tram_distance(h) > 2 * SL_MAX_M;
-    int M = h->tune_M ? h->tune_M : (h->sl_serial ? (deep ? SL_MAX_M : 32) : 8);
+    int M = h->tune_M ? h->tune_M : (serial ? ((deep || !h->sl_tram) ? SL_MAX_M : 32) : 8);   // (a register recurrence: the batch overhead — decode, fetch issue — is serial with it: cfg4 at 8 192 instances, M = 32 79 us, 64 76 us)
     // serial: all blocks are resident at once; give each its share of the SM's shared memory
     // (with more blocks than fit at once the launch runs in waves: 56 KiB keeps four 128-thread blocks per SM)
-    const size_t budget = h->sl_serial ? std::min<size_t>(h->smem_optin, std::max<size_t>(56 * 1024, (size_t)200 * 1024 / std::max(1, ((N / K + B - 1) / B + h->num_sms - 1) / h->num_sms))) : 36 * 1024;
+    const size_t budget = serial ? std::min<size_t>(h->smem_optin, std::max<size_t>(56 * 1024, (size_t)200 * 1024 / std::max(1, ((N / K + B - 1) / B + h->num_sms - 1) / h->num_sms))) : (tsplit ? 48 * 1024 : 36 * 1024);     // (a delay line keeps two more stage rows per sample)
     while (!h->tune_M && M > 1 && sl_smem_bytes(h, B, K, M) > budget) M >>= 1;
-    if (h->sl_serial && M < 2) M = 2;        // a carried operand reads row (m - 1) mod M while row m is written
+    if (tsplit) while (M > 1 && 2 * M >= known_tram_span(h)) M >>= 1;    // the READs of batch b + 1 are prefetched while batch b runs
+    if (serial && M < 2) M = 2;        // a carried operand reads row (m - 1) mod M while row m is written
     while (sl_smem_bytes(h, B, K, M) > h->smem_optin && B > 32) B >>= 1;
     if (sl_smem_bytes(h, B, K, M) > h->smem_optin) return fail(h, FX8010_ERR_CAPACITY, "register file does not fit in shared memory");
     // Sample split: a serial program whose only state across sample periods is TRAM (nothing carried in registers) has
@@ -857,7 +911,7 @@ int plan_stateless(fx8010_gpu* h, const float*, const float*, unsigned align, in
     int P = 1;
     bool any_carry = false;
     for (uint8_t c : h->sl_carry) any_carry = any_carry || c;
-    if (h->sl_serial && h->sl_tram && !any_carry && h->use_split) {
+    if (serial && h->sl_tram && !any_carry && h->use_split) {
         while (P < 8 && (long)((N / K + 31) / 32) * P < 4L * h->num_sms && B * P * 2 <= 128 && M / (P * 2) >= 8) P <<= 1;   // (each thread decodes every instruction once per batch: keep its share of the batch long)
         if (h->tune_P && (h->tune_P & (h->tune_P - 1)) == 0 && B * h->tune_P <= 128 && M / h->tune_P >= 1) P = h->tune_P;
     }
@@ -886,7 +940,7 @@ int plan_stateless(fx8010_gpu* h, const float*, const float*, unsigned align, in
     }
     if (h->tune_seg) n_seg = h->tune_seg;
     n_seg = std::min<long>(n_seg, std::max(1, n_samples / M));
-    if (h->sl_serial) n_seg = 1;             // a recurrence cannot be cut along time
+    if (serial) n_seg = 1;                   // a recurrence cannot be cut along time
     int seg_len = (int)((n_samples + n_seg - 1) / n_seg);
     seg_len = (seg_len + M - 1) / M * M;
     L.seg_len = seg_len;
@@ -972,6 +1026,20 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
             }
         return FX8010_OK;
     }
+    // Delay lines: periods closer than the known span are independent, so a block is cut into stretches of at most that
+    // many periods, each one launch cut along time like a stateless program (the stretches themselves run in order).
+    const int span = (h->sl_ok && h->use_sl && !h->trace_mode && h->use_tsplit) ? known_tram_span(h) : 0;
+    const bool tsplit = span >= MIN_TSPLIT_SPAN;
+    if (tsplit && n_samples > span) {
+        for (int b = 0; b < n_blk; ++b)
+            for (int s0 = 0; s0 < n_samples; s0 += span) {
+                const float* in = ins[b] ? ins[b] + (size_t)s0 * h->N : nullptr;
+                float* out = outs[b] + (size_t)s0 * h->N;
+                const int rc = launch_blocks(h, &in, &out, 1, in_cs, out_cs, std::min(span, n_samples - s0), st, own_prev || b > 0 || s0 > 0);
+                if (rc) return rc;
+            }
+        return FX8010_OK;
+    }
     const int ns = n_samples;
     const bool fusable = h->sl_ok && h->use_sl && !h->trace_mode && !h->sl_serial && h->use_fuse;
     for (int b0 = 0; b0 < n_blk;) {
@@ -987,13 +1055,13 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
         }
         if (any_in != all_in) return fail(h, FX8010_ERR_ARG, "either every block of a call has an input buffer or none has");
         align |= (unsigned)(((uintptr_t)(in_cs * 4) | (uintptr_t)(out_cs * 4)) & 15u) | (any_in ? 16u : 0u);
-        const int deep = (h->sl_ok && h->sl_tram) ? (known_tram_distance(h) > 2 * SL_MAX_M ? 1 : 0) : 0;
+        const int deep = ((h->sl_ok && h->sl_tram) ? (known_tram_distance(h) > 2 * SL_MAX_M ? 1 : 0) : 0) | (tsplit ? 2 : 0);
         // a launch that may overlap its neighbours (late wait) is planned as half a wave; one that waits at its start fills the SMs
         const bool may_overlap = h->use_pdl && h->stateless && nb == 1 && (h->stream_exclusive || own_prev || b0 > 0);
         if (h->plan_key.ns == ns && h->plan_key.align == align && h->plan_key.deep == deep && h->plan_key.n_blk == nb && h->plan_key.wave == (int)may_overlap) L = h->plan;
         else {
             L.M = 0;
-            const int rc = (h->sl_ok && h->use_sl && !h->trace_mode) ? plan_stateless(h, ins[b0], outs[b0], align, ns, nb, may_overlap, L)
+            const int rc = (h->sl_ok && h->use_sl && !h->trace_mode) ? plan_stateless(h, ins[b0], outs[b0], align, ns, nb, may_overlap, tsplit, L)
                                                                      : plan_launch(h, ins[b0], outs[b0], in_cs, out_cs, ns, L);
             if (rc) return rc;
             h->plan = L; h->plan_key.ns = ns; h->plan_key.align = align; h->plan_key.deep = deep; h->plan_key.n_blk = nb; h->plan_key.wave = (int)may_overlap;
@@ -1009,12 +1077,12 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
         std::lock_guard<std::mutex> lk(g_dev_mutex[h->device]);       // residency check -> launch
         bool fresh = false;
         {
-            const int rc = arena_acquire(h, (int)fam, 2 * (h->n_exec + 1), fresh);
+            const int rc = arena_acquire(h, (int)fam, (L.M > 0 ? 4 : 2) * (h->n_exec + 1), fresh);
             if (rc) return rc;
         }
         if (reencode || fresh) {
             FX_CUDA(h, cudaStreamSynchronize(st));                     // kernels still reading the old image of this range
-            FX_CUDA(h, upload_program(fam, h->h_prog, sizeof(uint4) * 2 * (h->n_exec + 1), h->arena_off, st));
+            FX_CUDA(h, upload_program(fam, h->h_prog, sizeof(uint4) * (L.M > 0 ? 4 : 2) * (h->n_exec + 1), h->arena_off, st));
             h->enc_family = (int)fam;
             if (reencode) {
                 if (L.M > 0) {
@@ -1196,6 +1264,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     if (getenv("FX8010_NO_PDL")) h->use_pdl = 0;
     if (getenv("FX8010_NO_FUSE")) h->use_fuse = 0;
     if (getenv("FX8010_NO_PAIRS")) h->use_pairs = 0;
+    if (getenv("FX8010_NO_TSPLIT")) h->use_tsplit = 0;
     if (getenv("FX8010_NO_STATELESS")) h->use_sl = 0;
     if (getenv("FX8010_NO_SHORT")) h->use_short = 0;
     if (getenv("FX8010_NO_CARRY")) h->use_carry = 0;

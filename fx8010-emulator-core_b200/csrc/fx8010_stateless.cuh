@@ -44,6 +44,7 @@ namespace fxk {
 constexpr uint32_t SL_OFF_MASK = 0xfffffu;   // [0:20)  byte offset
 constexpr int SL_STRIDE_SHIFT = 20;          // [20:31) bytes between consecutive samples of the batch, in 16-byte units
 constexpr uint32_t SL_BUF = 1u << 31;        // input-stage row: add the offset of the current stage buffer
+__host__ __device__ inline uint32_t sl_stride(uint32_t w) { return ((w >> SL_STRIDE_SHIFT) & 0x7ffu) << 4; }
 constexpr uint32_t F_ST_LAST = 1u << 17;     // R is never read by the program: store it on the batch-final sample only
 constexpr int SL_MAX_M = 64;             // a serial (recurrent) launch has few warps: its batch is also how far the input stage runs ahead of the arithmetic
 constexpr uint32_t F_FUSE = 1u << 21;        // the NEXT instruction is a MACS/MACSN whose only varying operand is this instruction's result, and nobody
@@ -55,7 +56,7 @@ constexpr int SL_CARRY_SHIFT = 18;           // w0 bits 18..20: operand A / X / 
                                              // (a self recurrence): row (m - 1) mod M on the first sample of a batch, then forwarded
                                              // in a hardware register — the recurrence never waits for shared memory
 
-// instruction: A = { uop | flags | out channel << 24, R word, A word, X word },  B = { Y word, table slot/id << 24, CCR word, 0 }
+// (the encoded instruction format is described at sl_exec below; load / write-back lists still use the packed operand word above)
 
 struct SLParams {
     float* gpr;                 // [n_regs][N]
@@ -113,7 +114,7 @@ template <int K> struct SLCtx {
     // TRAM
     int32_t tp[4][K];               // iw, ir, xw, xr of this thread's instances
     bool tram_fast;                 // the READ streams are prefetched (else: synchronous reads, one sample at a time)
-    bool split;                     // several threads share this column (P > 1): the kernel sets the pointers before every call
+    bool split;                     // the kernel sets the TRAM pointers before every sl_exec call (several threads share the column, or the READs are prefetched)
     float* ring[2];                 // iTRAM / xTRAM at this thread's first instance
     int rsize[2];
 };
@@ -147,7 +148,8 @@ struct SLInstr {
 // The sample loop is software-pipelined over TWO operand register sets (unrolled by two, no register moves): the
 // operands of sample m + 1 go in flight before the arithmetic of sample m, operands whose row does not change are
 // read once, and a carried operand is written straight into the next set — a recurrence's chain holds arithmetic only.
-template <int K, bool FINAL, bool CCRV, int CM, bool TRAM, int FUSE = 0>     // FUSE: 0 none, 1 result forwarded into the consumer's addend, 2 into its product
+template <int K, bool FINAL, bool CCRV, int CM, bool TRAM, int FUSE = 0>     // FUSE: 0 none, 1 result forwarded into the consumer's addend, 2 into its product,
+                                                                            //       3 / 4 the consumer is the iTRAM / xTRAM WRITE of the result
 __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr& I) {
     const uint64_t Nl = cx.Nl;
     const uint32_t w0 = I.w0, uop = I.uop;
@@ -175,12 +177,21 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
         }                                                                                                        \
         __VA_ARGS__                                                                                              \
         if (FUSE == 0) { SL_WRITE(SETS_ACC) }                                                                    \
-        else {      /* the consumer MACS / MACSN (:1077-1094) on the forwarded result; this instruction's own R is dead in the bulk path */ \
+        else if (FUSE <= 2) {   /* the consumer MACS / MACSN (:1077-1094) on the forwarded result; this instruction's own R is dead in the bulk path */ \
             Vec<K> r2;                                                                                           \
             SL_EACH { r2[k] = sat1(FUSE == 1 ? __fadd_rn(r[k], I.fc0[k]) : __fadd_rn(I.fc0[k], __fmul_rn(r[k], I.fc1[k]))); } \
             if (I.st_r2) sts<K>(I.qr2, r2);                                                                      \
             if (I.st_o2) vstore<K>(I.qo2, r2);                                                                   \
             I.qr2 += I.sr2; I.qo2 += Nl;                                                                         \
+        } else {                /* the consumer IDELAY / XDELAY WRITE (:1195-1198 / :1207-1210, writeSmallDelay :909-917): the result goes straight to the ring */ \
+            if (K > 1 && fw_same) { if (cx.tp[2 * FT][0] + fw_pos[0] < fw_size && cx.valid) vstore<K>(fw_q[0], r); } \
+            else { SL_EACH { if (cx.tp[2 * FT][k] + fw_pos[k] < fw_size && cx.valid) *fw_q[k] = r[k]; } }         \
+            SL_EACH {                                                                                            \
+                int32_t& wp = cx.tp[2 * FT][k];                                                                  \
+                const bool wrap = (++wp == fw_size);                                                             \
+                wp = wrap ? 0 : wp;                                                                              \
+                fw_q[k] = wrap ? fw_ring + (uint64_t)fw_pos[k] * Nl + k : fw_q[k] + Nl;                          \
+            }                                                                                                    \
         }                                                                                                        \
         if (CM == 1) A##NXT = r;                                                                                 \
         else if (CM == 2) { SL_EACH { if (I.ca) A##NXT[k] = r[k]; if (I.cx) X##NXT[k] = r[k]; if (I.cy) Y##NXT[k] = r[k]; } } \
@@ -205,6 +216,21 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
         if (dyn_sel) X0 = lds<K>(I.qx);
     }
     Vec<K> A1 = A0, X1 = X0, Y1 = Y0;
+    // fused TRAM WRITE consumer: running address of slot wp + pos per context (slots at or beyond the ring are dropped, as in SL_TRAM_WRITE)
+    constexpr int FT = FUSE == 4 ? 1 : 0;
+    int fw_pos[K];
+    float* fw_q[K];
+    bool fw_same = true;
+    const int fw_size = cx.rsize[FT];
+    float* const fw_ring = cx.ring[FT];
+    if (FUSE >= 3) {
+        const Vec<K> wy = lds<K>(I.qr2);                                 // the WRITE's offset operand (one value for the whole batch)
+        SL_EACH {
+            fw_pos[k] = min(max(cvt_x86(wy[k]), 0), fw_size - 1);
+            fw_q[k] = fw_ring + (uint64_t)(cx.tp[2 * FT][k] + fw_pos[k]) * Nl + k;
+            fw_same = fw_same && (cx.tp[2 * FT][k] + fw_pos[k] == cx.tp[2 * FT][0] + fw_pos[0]);
+        }
+    }
     switch (uop) {
     case U_MACS: SL_LOOP(true, true,
         SL_EACH { accv[k] = __fadd_rn(a[k], __fmul_rn(x[k], y[k])); r[k] = sat1(accv[k]); }) break;
@@ -233,10 +259,18 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
         const bool x_varies = lx || I.cx;         // a constant coefficient: 1.0 - X is formed once per batch
         double omx[K];
         SL_EACH { omx[k] = __dsub_rn(1.0, (double)X0[k]); }
-        SL_LOOP(true, true,
-            if (x_varies) one_minus<K>(x.v, omx);
-            interp_core<K>(omx, a.v, x.v, y.v, accv.v);
-            SL_EACH { r[k] = sat1(accv[k]); })
+        // (two copies of the loop: with `if (x_varies)` inside one, ptxas converts and selects 1 - X every sample period
+        //  — a fourth conversion-unit instruction per context on the path of a one-pole recurrence)
+        if (x_varies) {
+            SL_LOOP(true, true,
+                one_minus<K>(x.v, omx);
+                interp_core<K>(omx, a.v, x.v, y.v, accv.v);
+                SL_EACH { r[k] = sat1(accv[k]); })
+        } else {
+            SL_LOOP(true, true,
+                interp_core<K>(omx, a.v, x.v, y.v, accv.v);
+                SL_EACH { r[k] = sat1(accv[k]); })
+        }
         break; }
     case U_LOG:
     case U_EXP: {
@@ -272,9 +306,7 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
 #define SL_TRAM_READ(T)                                                                                          \
         if (TRAM && !FINAL && FUSE == 0) {                                                                                    \
             const int size = cx.rsize[T];                                                                        \
-            if (cx.tram_fast) {    /* the rows were prefetched with the batch: only the pointer moves (a split column's pointers are set by the kernel) */ \
-                if (!cx.split) { SL_EACH { int32_t& rp = cx.tp[2 * T + 1][k]; rp += n_m; rp -= (rp >= size) ? size : 0; } } \
-            } else {                                                                                             \
+            if (!cx.tram_fast) {   /* (prefetched READs never get here: sl_exec skips them, the kernel moves the pointers per batch) */ \
                 const float* const ring = cx.ring[T];                                                            \
                 for (int m = 0; m < n_m; ++m, I.qa += I.sa) {                                                    \
                     Vec<K> v;                                                                                    \
@@ -332,55 +364,76 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
 }
 
 // Runs the whole program for samples [m_lo, m_hi) of the current batch, instruction-major.
+// The encoded stream holds four words per instruction with everything the host can work out at load time already
+// worked out (fx8010_gpu.cu::encode_stateless) — per batch and instruction the thread only adds its column, the stage
+// buffer in use and, in the delay-line kernel, the first sample of its share:
+//   Q0 { uop | flags | carry | out channel << 24,  table slot/id << 24,  pair bits (F_FUSE),  0 }
+//   Q1 { byte offset of R, A, X, Y at sample 0 (a self-carried operand: its row M - 1);  bit 31: a stage row, add the buffer in use }
+//   Q2 { bytes between consecutive samples for R, A, X, Y (0: one row for the whole batch, or self-carried) }
+//   Q3 { byte offset of CCR, its bytes per sample, 0, 0 }
 template <int K, bool FINAL, bool CCRV, bool TRAM>
 __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const int m_lo, const int m_hi) {
-    uint4 nA = cx.prog[0], nB = cx.prog[1];
+    uint4 n0 = cx.prog[0], n1 = cx.prog[1], n2 = cx.prog[2], n3 = cx.prog[3];
     const int n_exec = cx.n_exec;
+    const uint32_t mlo = (uint32_t)m_lo;
     for (int pc = 0; pc < n_exec; ++pc) {
-        const uint4 wA = nA, wB = nB;
-        nA = cx.prog[2 * pc + 2]; nB = cx.prog[2 * pc + 3];
-        const uint32_t w0 = wA.x;
-        // decode once per batch: address of sample m_lo and per-sample stride of every operand, store modes
-#define SL_STRIDE(w) ((((w) >> SL_STRIDE_SHIFT) & 0x7ffu) << 4)
-#define SL_ADDR(w) (cx.col_s + ((w) & SL_OFF_MASK) + (((w) & SL_BUF) ? cx.boff : 0u) + (uint32_t)m_lo * SL_STRIDE(w))
-        // a carried operand: the row of the previous sample (row M - 1 before sample 0); later samples get it forwarded
-#define SL_ADDR_C(w) (cx.col_s + ((w) & SL_OFF_MASK) + (uint32_t)((m_lo == 0 ? p.M : m_lo) - 1) * SL_STRIDE(w))
+        const uint4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
+        n0 = cx.prog[4 * pc + 4]; n1 = cx.prog[4 * pc + 5]; n2 = cx.prog[4 * pc + 6]; n3 = cx.prog[4 * pc + 7];   // (the stream ends with one pad record)
+        const uint32_t w0 = q0.x;
+        if (TRAM) {     // a prefetched READ has nothing to execute (its rows arrive with the batch, the kernel moves the pointers); the final-state pass re-runs arithmetic only
+            const uint32_t u0 = w0 & 0xffu;
+            if ((u0 == U_IREAD || u0 == U_XREAD) && (FINAL || cx.tram_fast)) continue;
+        }
+        // address of an operand at sample m_lo: column + offset (+ the stage buffer in use) + m_lo * stride
+#define SL_Q(off, str) (cx.col_s + ((off) & 0x7fffffffu) + ((uint32_t)((int32_t)(off) >> 31) & cx.boff) + mlo * (str))
+        // a self-carried operand (the register is this instruction's own R): row M - 1 before sample 0, else the row of sample m_lo - 1
+#define SL_QC(off) (cx.col_s + (off) + (m_lo == 0 ? 0u : (uint32_t)(m_lo - p.M) * q2.x))
         SLInstr I;
-        I.w0 = w0; I.uop = w0 & 0xffu; I.aux = wB.y; I.n_m = m_hi - m_lo;
+        I.w0 = w0; I.uop = w0 & 0xffu; I.aux = q0.y; I.n_m = m_hi - m_lo;
         const uint32_t cbits = (w0 >> SL_CARRY_SHIFT) & 7u;
         I.ca = cbits & 1u; I.cx = cbits & 2u; I.cy = cbits & 4u;
-        I.sr = SL_STRIDE(wA.y); I.sa = I.ca ? 0u : SL_STRIDE(wA.z); I.sx = I.cx ? 0u : SL_STRIDE(wA.w); I.sy = I.cy ? 0u : SL_STRIDE(wB.x); I.sccr = SL_STRIDE(wB.z);
-        I.qr = SL_ADDR(wA.y); I.qa = I.ca ? SL_ADDR_C(wA.z) : SL_ADDR(wA.z); I.qx = I.cx ? SL_ADDR_C(wA.w) : SL_ADDR(wA.w);
-        I.qy = I.cy ? SL_ADDR_C(wB.x) : SL_ADDR(wB.x); I.qccr = SL_ADDR(wB.z);
+        I.sr = q2.x; I.sa = q2.y; I.sx = q2.z; I.sy = q2.w; I.sccr = q3.y;
+        I.qr = cx.col_s + q1.x + mlo * q2.x;
+        I.qa = I.ca ? SL_QC(q1.y) : SL_Q(q1.y, q2.y); I.qx = I.cx ? SL_QC(q1.z) : SL_Q(q1.z, q2.z); I.qy = I.cy ? SL_QC(q1.w) : SL_Q(q1.w, q2.w);
+        I.qccr = cx.col_s + q3.x + mlo * q3.y;
         I.st_r = FINAL || !(w0 & F_ST_LAST);
         I.st_c = FINAL || (CCRV && (w0 & F_CCR));
         I.st_o = (w0 & F_OUT_DIRECT) && cx.valid;
         I.qo = cx.out_b + (size_t)(w0 >> 24) * cx.out_cstride + (size_t)m_lo * cx.Nl;
         if (FINAL || CCRV) sl_run<K, FINAL, CCRV, 2, TRAM>(p, cx, I);          // cold paths: one general copy
+        else if ((w0 & F_FUSE) && (q0.z & 8u)) {
+            // producer + TRAM WRITE: the result is stored straight into the ring (n1.w = the WRITE's offset operand, one row)
+            if constexpr (TRAM) {
+                I.qr2 = cx.col_s + n1.w;
+                if (q0.z & 16u) sl_run<K, false, false, 0, TRAM, 4>(p, cx, I); else sl_run<K, false, false, 0, TRAM, 3>(p, cx, I);
+            }
+            ++pc;
+            n0 = cx.prog[4 * pc + 4]; n1 = cx.prog[4 * pc + 5]; n2 = cx.prog[4 * pc + 6]; n3 = cx.prog[4 * pc + 7];
+        }
         else if (w0 & F_FUSE) {
-            // producer + consumer in one sample loop: nA / nB hold the consumer (a MACS / MACSN with two batch-constant operands)
-            const uint32_t v0 = nA.x;
-            const bool into_product = wB.w & 1u, negate = wB.w & 2u;
-            const Vec<K> ca = lds<K>(cx.col_s + (nA.z & SL_OFF_MASK)), cxx = lds<K>(cx.col_s + (nA.w & SL_OFF_MASK)), cy = lds<K>(cx.col_s + (nB.x & SL_OFF_MASK));
-            const bool fwd_x = into_product && (wB.w & 4u);                    // which factor of the product is the forwarded one
+            // producer + consumer in one sample loop: n0..n2 hold the consumer (a MACS / MACSN with two batch-constant operands)
+            const uint32_t v0 = n0.x;
+            const bool into_product = q0.z & 1u, negate = q0.z & 2u;
+            const Vec<K> ca = lds<K>(cx.col_s + n1.y), cxx = lds<K>(cx.col_s + n1.z), cy = lds<K>(cx.col_s + n1.w);   // (constant rows: plain offsets; the forwarded one is not used)
+            const bool fwd_x = into_product && (q0.z & 4u);                    // which factor of the product is the forwarded one
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 if (into_product) { const float m = fwd_x ? cy[k] : cxx[k]; I.fc0[k] = ca[k]; I.fc1[k] = negate ? -m : m; }
                 else { const float pr = __fmul_rn(cxx[k], cy[k]); I.fc0[k] = negate ? -pr : pr; I.fc1[k] = 0.0f; }
             }
-            I.sr2 = SL_STRIDE(nA.y); I.qr2 = SL_ADDR(nA.y);
+            I.sr2 = n2.x; I.qr2 = cx.col_s + n1.x + mlo * n2.x;
             I.st_r2 = !(v0 & F_ST_LAST);
             I.st_o2 = (v0 & F_OUT_DIRECT) && cx.valid;
             I.qo2 = cx.out_b + (size_t)(v0 >> 24) * cx.out_cstride + (size_t)m_lo * cx.Nl;
             if (into_product) sl_run<K, false, false, 0, TRAM, 2>(p, cx, I); else sl_run<K, false, false, 0, TRAM, 1>(p, cx, I);
             ++pc;                                                              // the consumer is done
-            nA = cx.prog[2 * pc + 2]; nB = cx.prog[2 * pc + 3];
+            n0 = cx.prog[4 * pc + 4]; n1 = cx.prog[4 * pc + 5]; n2 = cx.prog[4 * pc + 6]; n3 = cx.prog[4 * pc + 7];
         }
         else if (cbits == 0u) sl_run<K, false, false, 0, TRAM>(p, cx, I);
         else if (cbits == 1u) sl_run<K, false, false, 1, TRAM>(p, cx, I);
         else sl_run<K, false, false, 2, TRAM>(p, cx, I);
-#undef SL_ADDR
-#undef SL_ADDR_C
+#undef SL_Q
+#undef SL_QC
     }
 }
 
@@ -494,6 +547,10 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
         for (int k = 0; k < K; ++k) {
             tp0[0][k] = p.ptrs[inst0 + k]; tp0[1][k] = p.ptrs[N + inst0 + k];
             tp0[2][k] = p.ptrs[2 * N + inst0 + k]; tp0[3][k] = p.ptrs[3 * N + inst0 + k];
+            if (s_begin) {          // a later time segment of a launch whose periods are independent (fx8010_gpu.cu::known_tram_span): pointers at its first period
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (p.tr_ops[j]) tp0[j][k] = ring_add(tp0[j][k], s_begin * p.tr_ops[j], cx.rsize[j >> 1]);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) cx.tp[j][k] = tp0[j][k];    // (a column with one thread just lets them run)
         }
@@ -533,6 +590,9 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
             __syncthreads();
             cx.tram_fast = (s_unsafe == 0);
         } else cx.tram_fast = __all_sync(0xffffffffu, safe);
+        // With prefetched READs the pointers are set from the batch-start values before every call (a READ then has
+        // nothing left to do and is not even decoded); only a lone thread with a short delay lets them run.
+        cx.split = (P > 1) || cx.tram_fast;
     }
     // Running global address of each stream's next row for THIS thread (one add per row, a reset where the ring wraps);
     // tr_skip = rows between it and the thread's first row of the next batch (the other threads' shares).
@@ -633,7 +693,7 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
             sl_exec<K, true, true, TRAM>(p, cx, mb - 1, mb);
             for (int i = 0; i < p.n_wb; ++i) {
                 const uint2 e = p.wb_list[i];
-                const unsigned char* src = col + (e.x & SL_OFF_MASK) + ((e.x & SL_BUF) ? cx.boff : 0u) + (uint32_t)(mb - 1) * SL_STRIDE(e.x);
+                const unsigned char* src = col + (e.x & SL_OFF_MASK) + ((e.x & SL_BUF) ? cx.boff : 0u) + (uint32_t)(mb - 1) * sl_stride(e.x);
                 vstore<K>(p.gpr + (size_t)e.y * N + inst0, vload<K>(reinterpret_cast<const float*>(src)));
             }
 #pragma unroll
@@ -649,7 +709,6 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
         cx.boff ^= buf_bytes;
     }
     if (cx.flags) atomicOr(p.rt_flags, cx.flags);
-#undef SL_STRIDE
 }
 
 }  // namespace fxk

@@ -370,8 +370,18 @@ TRAM_CASES = {
 
 
 @pytest.mark.parametrize("name", sorted(TRAM_CASES))
-@pytest.mark.parametrize("mode", ["auto", "K4", "K2M8", "no_im", "P1", "P2", "K1P4M16"])
+@pytest.mark.parametrize("mode", ["auto", "K4", "K2M8", "no_im", "P1", "P2", "K1P4M16", "serial", "tsplitK2M16", "tsplitSEG3"])
 def test_tram_instruction_major(fx, po, name, mode, monkeypatch):
+    # auto / K4 / K2M8: delay lines whose periods are known to be independent over >= 64 periods are cut along time
+    # (blocks longer than that span run as several launches); the other modes switch that off and exercise the serial
+    # kernel with its sample split
+    if mode in ("P1", "P2", "K1P4M16", "serial"):
+        monkeypatch.setenv("FX8010_NO_TSPLIT", "1")
+    if mode == "tsplitK2M16":
+        monkeypatch.setenv("FX8010_TUNE_K", "2")
+        monkeypatch.setenv("FX8010_TUNE_M", "16")
+    elif mode == "tsplitSEG3":
+        monkeypatch.setenv("FX8010_TUNE_SEG", "3")
     if mode == "K4":
         monkeypatch.setenv("FX8010_TUNE_K", "4")
     elif mode == "K2M8":
@@ -379,7 +389,7 @@ def test_tram_instruction_major(fx, po, name, mode, monkeypatch):
         monkeypatch.setenv("FX8010_TUNE_M", "8")
     elif mode == "no_im":
         monkeypatch.setenv("FX8010_NO_TRAM_IM", "1")
-    elif mode[0] == "P":        # threads per instance column (they split each batch's samples)
+    elif mode in ("P1", "P2"):  # threads per instance column (they split each batch's samples)
         monkeypatch.setenv("FX8010_TUNE_P", mode[1:])
     elif mode == "K1P4M16":
         monkeypatch.setenv("FX8010_TUNE_K", "1")
