@@ -132,6 +132,7 @@ MULTI_SYMBOLS = {
 
 HOST_SYMBOLS = {
     "fx8010_host_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int]),
+    "fx8010_host_create_multi": (C.c_void_p, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "fx8010_host_destroy": (None, [C.c_void_p]),
     "fx8010_host_last_error": (C.c_char_p, [C.c_void_p]),
     "fx8010_host_load_file": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -205,10 +206,14 @@ class Program:
     """The host front-end (class Klangraum::FX8010 through include/fx8010_host.h)."""
 
     def __init__(self, text: str | bytes | None = None, channels: int = 1, instances: int = 1, device: int = 0,
-                 path: str | None = None, relaxed: bool = False):
+                 path: str | None = None, relaxed: bool = False, devices=None):
         self.L = host_lib()
         self.channels, self.instances, self.device = channels, instances, device
-        self.h = self.L.fx8010_host_create(channels, instances, device)
+        if devices is not None:            # the facade's multi-GPU constructor: instances sharded over `devices`
+            dev = (C.c_int * len(devices))(*devices)
+            self.h = self.L.fx8010_host_create_multi(channels, instances, dev, len(devices))
+        else:
+            self.h = self.L.fx8010_host_create(channels, instances, device)
         if not self.h:
             raise ValueError("bad channel / instance count")
         self.loaded = None

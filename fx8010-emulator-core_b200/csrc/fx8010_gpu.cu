@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -880,6 +881,7 @@ int plan_stateless(fx8010_gpu* h, const float*, const float*, unsigned align, in
     const int N = h->N;
     auto aligned = [&](int K) { return N % K == 0 && (align & (unsigned)(K * 4 - 1)) == 0; };   // align: low bits of every buffer address and channel stride (bytes)
     int K = 4;
+    if (tsplit) K = 2;                       // (the delay-line kernel at K = 4 sits at its register cap: cfg3, itramsize 8192: K = 4, M = 8 97 us; K = 2, M = 16 82 us; K = 1, M = 32 84 us)
     while (K > 1 && !aligned(K)) K >>= 1;
     bool splittable = serial && h->sl_tram && h->use_split;     // (see the sample split below)
     for (uint8_t c : h->sl_carry) splittable = splittable && !c;
@@ -896,7 +898,7 @@ int plan_stateless(fx8010_gpu* h, const float*, const float*, unsigned align, in
     // (a split program decodes every instruction once per thread and batch: with a delay known to exceed two 64-sample
     //  batches the longer batch halves that cost — cfg3: 152 -> 98 us)
     const bool deep = splittable && known_tram_distance(h) > 2 * SL_MAX_M;
-    int M = h->tune_M ? h->tune_M : (serial ? ((deep || !h->sl_tram) ? SL_MAX_M : 32) : 8);   // (a register recurrence: the batch overhead — decode, fetch issue — is serial with it: cfg4 at 8 192 instances, M = 32 79 us, 64 76 us)
+    int M = h->tune_M ? h->tune_M : (serial ? ((deep || !h->sl_tram) ? SL_MAX_M : 32) : (tsplit ? 16 : 8));   // (a register recurrence: the batch overhead — decode, fetch issue — is serial with it: cfg4 at 8 192 instances, M = 32 79 us, 64 76 us)
     // serial: all blocks are resident at once; give each its share of the SM's shared memory
     // (with more blocks than fit at once the launch runs in waves: 56 KiB keeps four 128-thread blocks per SM)
     const size_t budget = serial ? std::min<size_t>(h->smem_optin, std::max<size_t>(56 * 1024, (size_t)200 * 1024 / std::max(1, ((N / K + B - 1) / B + h->num_sms - 1) / h->num_sms))) : (tsplit ? 48 * 1024 : 36 * 1024);     // (a delay line keeps two more stage rows per sample)
@@ -932,11 +934,24 @@ int plan_stateless(fx8010_gpu* h, const float*, const float*, unsigned align, in
     long n_seg = std::max(1L, slots / ((may_overlap ? 2 : 1) * L.grid_x));
     // ... a launch much longer than its own ramp-up (many instances, or several sample blocks fused into it) is cut
     // into work items of about 128 samples, but into no fewer than two waves' worth, so that the tail balances
+    // ... a launch much longer than its own ramp-up (many instances, or several sample blocks fused into it): all thread
+    // blocks do the same amount of work, so the last wave is as long as a full one however few blocks it holds — pick
+    // the segment count whose block count sits just below a whole number of waves (cfg2, 20 blocks per launch: 3 segments =
+    // 0.93 waves instead of 8 = 2.47), preferring few long segments (less per-block start-up) once every SM is busy.
     const double work = (double)N * n_samples * n_blk;
     if (work > 8.0 * 4096 * 1024 || n_blk > 1) {
-        const long waves2 = std::max(1L, 2L * slots / ((long)L.grid_x * n_blk));
-        n_seg = std::max<long>(waves2, std::min<long>(n_samples / 128, 4L * slots / ((long)L.grid_x * n_blk)));
-        n_seg = std::max(1L, n_seg);
+        const long items = (long)L.grid_x * n_blk;
+        const long max_seg = std::max(1L, (long)n_samples / std::max(M, 16));
+        long best = 1; double best_cost = 1e30;
+        for (long c = 1; c <= max_seg; ++c) {
+            const double w = (double)items * c / (double)slots;
+            const double waves = std::ceil(w - 1e-9);
+            double cost = waves / w;                                  // time relative to perfectly divisible work
+            if (w < 0.8) cost += (0.8 - w) * 4.0;                     // not enough blocks to fill the SMs
+            cost += 0.01 * (double)c / (double)max_seg * 4.0;         // mild preference for fewer, longer segments
+            if (cost < best_cost - 1e-9) { best_cost = cost; best = c; }
+        }
+        n_seg = best;
     }
     if (h->tune_seg) n_seg = h->tune_seg;
     n_seg = std::min<long>(n_seg, std::max(1, n_samples / M));
@@ -1029,7 +1044,9 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
     // Delay lines: periods closer than the known span are independent, so a block is cut into stretches of at most that
     // many periods, each one launch cut along time like a stateless program (the stretches themselves run in order).
     const int span = (h->sl_ok && h->use_sl && !h->trace_mode && h->use_tsplit) ? known_tram_span(h) : 0;
-    const bool tsplit = span >= MIN_TSPLIT_SPAN;
+    // (worth it when the block needs at most two launches — cfg3 at 16 384 instances x 1 024 periods: span 100, eleven launches,
+    //  198 us against 139 us for the serial kernel with its sample split; span 1 000, two launches, 111 against 112; one launch, 82)
+    const bool tsplit = span >= MIN_TSPLIT_SPAN && 2L * span >= n_samples;
     if (tsplit && n_samples > span) {
         for (int b = 0; b < n_blk; ++b)
             for (int s0 = 0; s0 < n_samples; s0 += span) {

@@ -10,15 +10,19 @@ FX8010::FX8010(int numChannels) : front_(numChannels) {}
 FX8010::FX8010(int numChannels, int numInstances, int device)
     : front_(numChannels), instances_(numInstances), device_(device) {}
 
+FX8010::FX8010(int numChannels, int numInstances, const std::vector<int>& devices)
+    : front_(numChannels), instances_(numInstances), device_(devices.empty() ? 0 : devices[0]), devices_(devices) {}
+
 FX8010::~FX8010() {
     if (gpu_) fx8010_gpu_destroy(gpu_);
+    if (multi_) fx8010_multi_destroy(multi_);
 }
 
 void FX8010::initialize() { front_.initialize(); }
 
 void FX8010::check(int rc, const char* what) {
     if (rc == FX8010_OK) return;
-    std::string msg = std::string("FX8010 (B200): ") + what + " failed: " + fx8010_gpu_last_error(gpu_);
+    std::string msg = std::string("FX8010 (B200): ") + what + " failed: " + (multi_ ? fx8010_multi_last_error(multi_) : fx8010_gpu_last_error(gpu_));
     throw std::runtime_error(msg);
 }
 
@@ -27,6 +31,22 @@ bool FX8010::loadText(const std::string& source) { return front_.loadText(source
 
 void FX8010::ensureUploaded() {
     if (!front_.ready()) throw std::runtime_error("FX8010 (B200): process() before a successful loadFile()");
+    if (devices_.size() > 1) {                                 // instances sharded over several GPUs
+        if (!multi_) {
+            const int rc = fx8010_multi_create(devices_.data(), (int)devices_.size(), instances_, front_.channels(), &multi_);
+            if (rc != FX8010_OK) {
+                std::string msg = std::string("FX8010 (B200): no multi-GPU executor: ") + fx8010_multi_last_error(nullptr);
+                multi_ = nullptr;
+                throw std::runtime_error(msg);
+            }
+        }
+        if (!uploaded_ || uploaded_generation_ != front_.generation()) {
+            check(fx8010_multi_load_program(multi_, front_.image()), "load_program");
+            uploaded_ = true;
+            uploaded_generation_ = front_.generation();
+        }
+        return;
+    }
     if (!gpu_) {
         const int rc = fx8010_gpu_create(device_, instances_, front_.channels(), &gpu_);
         if (rc != FX8010_OK) {
@@ -47,6 +67,7 @@ void FX8010::ensureUploaded() {
 
 fx8010_gpu* FX8010::gpuHandle() {
     ensureUploaded();
+    if (multi_) throw std::runtime_error("FX8010 (B200): this object drives several GPUs; there is no single device handle");
     return gpu_;
 }
 
@@ -57,7 +78,8 @@ std::vector<float> FX8010::process(const std::vector<float>& inputSamples) {
     out_block_.assign(C * N, 0.0f);
     for (size_t c = 0; c < C && c < inputSamples.size(); ++c)
         for (size_t i = 0; i < N; ++i) in_block_[c * N + i] = inputSamples[c];
-    check(fx8010_gpu_process_batch_host(gpu_, in_block_.data(), out_block_.data(), 1), "process_batch_host");
+    if (multi_) check(fx8010_multi_process_batch_host(multi_, in_block_.data(), out_block_.data(), 1), "process_batch_host");
+    else check(fx8010_gpu_process_batch_host(gpu_, in_block_.data(), out_block_.data(), 1), "process_batch_host");
     std::vector<float> out(C);
     for (size_t c = 0; c < C; ++c) out[c] = out_block_[c * N];
     return out;
@@ -65,17 +87,20 @@ std::vector<float> FX8010::process(const std::vector<float>& inputSamples) {
 
 void FX8010::processBlock(const float* in, float* out, int n_samples) {
     ensureUploaded();
-    check(fx8010_gpu_process_batch_host(gpu_, in, out, n_samples), "process_batch_host");
+    if (multi_) check(fx8010_multi_process_batch_host(multi_, in, out, n_samples), "process_batch_host");
+    else check(fx8010_gpu_process_batch_host(gpu_, in, out, n_samples), "process_batch_host");
 }
 
 void FX8010::processBlockDevice(const float* d_in, float* d_out, int n_samples, void* stream) {
     ensureUploaded();
+    if (multi_) throw std::runtime_error("FX8010 (B200): device-pointer members need a single device");
     check(fx8010_gpu_process_batch(gpu_, d_in, d_out, n_samples, stream), "process_batch");
 }
 
 void FX8010::processBlockDeviceWithControls(const float* d_in, float* d_out, int n_samples,
                                             const std::vector<ControlChange>& changes, void* stream) {
     ensureUploaded();
+    if (multi_) throw std::runtime_error("FX8010 (B200): device-pointer members need a single device");
     std::vector<fx8010_control_event> ev;
     std::vector<float> vals(changes.size());
     for (size_t i = 0; i < changes.size(); ++i) {
@@ -90,10 +115,18 @@ void FX8010::processBlockDeviceWithControls(const float* d_in, float* d_out, int
 
 void FX8010::processBlockDevicePlanar(const float* d_in, float* d_out, int n_samples, void* stream) {
     ensureUploaded();
+    if (multi_) throw std::runtime_error("FX8010 (B200): device-pointer members need a single device");
     check(fx8010_gpu_process_batch_planar(gpu_, d_in, d_out, n_samples, stream), "process_batch_planar");
 }
 
 int FX8010::getInstructionCounter() {
+    if (multi_ && uploaded_) {                                  // instance 0 lives on the first shard
+        int lo = 0, hi = 0;
+        fx8010_gpu* g0 = fx8010_multi_shard(multi_, 0, &lo, &hi);
+        std::vector<unsigned long long> c((size_t)(hi - lo));
+        if (fx8010_gpu_get_instruction_counts(g0, c.data()) != FX8010_OK) throw std::runtime_error("FX8010 (B200): get_instruction_counts failed");
+        return (int)(unsigned int)c[0];
+    }
     if (!gpu_ || !uploaded_) return 0;
     std::vector<unsigned long long> c((size_t)instances_);
     check(fx8010_gpu_get_instruction_counts(gpu_, c.data()), "get_instruction_counts");
@@ -101,6 +134,11 @@ int FX8010::getInstructionCounter() {
 }
 
 unsigned long long FX8010::getInstructionCounterTotal() {
+    if (multi_ && uploaded_) {
+        unsigned long long t = 0;
+        check(fx8010_multi_get_instruction_count(multi_, &t), "get_instruction_count");
+        return t;
+    }
     if (!gpu_ || !uploaded_) return 0;
     unsigned long long t = 0;
     check(fx8010_gpu_get_instruction_count(gpu_, &t), "get_instruction_count");
@@ -123,7 +161,9 @@ int FX8010::setRegisterValue(const std::string& key, float value) {
     const int idx = front_.findRegister(key);
     if (idx < 0) return 1;
     front_.registers()[idx].value = value;                      // initial value of a later upload
-    if (gpu_ && uploaded_ && uploaded_generation_ == front_.generation())
+    if (multi_ && uploaded_ && uploaded_generation_ == front_.generation())
+        check(fx8010_multi_set_controls(multi_, idx, &value, 1), "set_controls");
+    else if (gpu_ && uploaded_ && uploaded_generation_ == front_.generation())
         check(fx8010_gpu_set_controls(gpu_, idx, &value, 1), "set_controls");
     return 0;
 }
@@ -132,16 +172,18 @@ int FX8010::setRegisterValues(const std::string& key, const float* values) {
     const int idx = front_.findRegister(key);
     if (idx < 0) return 1;
     ensureUploaded();
-    check(fx8010_gpu_set_controls(gpu_, idx, values, 0), "set_controls");
+    if (multi_) check(fx8010_multi_set_controls(multi_, idx, values, 0), "set_controls");
+    else check(fx8010_gpu_set_controls(gpu_, idx, values, 0), "set_controls");
     return 0;
 }
 
 float FX8010::getRegisterValue(const std::string& key) {
     const int idx = front_.findRegister(key);
     if (idx < 0) return 1;                                      // the reference's "not found" value (:265)
-    if (gpu_ && uploaded_ && uploaded_generation_ == front_.generation()) {
+    if ((gpu_ || multi_) && uploaded_ && uploaded_generation_ == front_.generation()) {
         std::vector<float> v((size_t)instances_);
-        check(fx8010_gpu_get_register(gpu_, idx, v.data()), "get_register");
+        if (multi_) check(fx8010_multi_get_register(multi_, idx, v.data()), "get_register");
+        else check(fx8010_gpu_get_register(gpu_, idx, v.data()), "get_register");
         return v[0];
     }
     return front_.registers()[idx].value;
@@ -151,7 +193,8 @@ int FX8010::getRegisterValues(const std::string& key, float* out) {
     const int idx = front_.findRegister(key);
     if (idx < 0) return 1;
     ensureUploaded();
-    check(fx8010_gpu_get_register(gpu_, idx, out), "get_register");
+    if (multi_) check(fx8010_multi_get_register(multi_, idx, out), "get_register");
+    else check(fx8010_gpu_get_register(gpu_, idx, out), "get_register");
     return 0;
 }
 

@@ -14,6 +14,7 @@
 
 #include "fx8010_frontend.h"
 #include "fx8010_gpu.h"
+#include "fx8010_multi.h"
 
 #if defined(__GNUC__)
 #define FX8010_CLASS __attribute__((visibility("default")))
@@ -50,6 +51,10 @@ public:
 
     // ---- batched extension ------------------------------------------------------------------------
     FX8010(int numChannels, int numInstances, int device);
+    // numInstances spread over several GPUs of one box (contiguous instance ranges, include/fx8010_multi.h): the host-buffer
+    // members (process, processBlock, set/getRegisterValue(s), the counters) work as on one device and gather into the
+    // caller's buffers; the device-pointer members have no single device to refer to and throw
+    FX8010(int numChannels, int numInstances, const std::vector<int>& devices);
     bool loadText(const std::string& source);
     void setRelaxedSyntax(bool on) { front_.setRelaxed(on); }   // accept the README's forms too (see fx8010_frontend.h)
     int getInstances() const { return instances_; }
@@ -80,6 +85,8 @@ private:
     int instances_ = 1;
     int device_ = 0;
     fx8010_gpu* gpu_ = nullptr;
+    std::vector<int> devices_;                                 // more than one entry: the multi-GPU executor below is used instead of gpu_
+    fx8010_multi* multi_ = nullptr;
     bool uploaded_ = false;                                    // the device holds the image of generation uploaded_generation_
     unsigned long uploaded_generation_ = 0;
     std::vector<float> in_block_, out_block_;

@@ -2,6 +2,7 @@
 #include <cstring>
 #include <exception>
 #include <string>
+#include <vector>
 
 #include "FX8010.h"
 #include "fx8010_host.h"
@@ -10,6 +11,7 @@ struct fx8010_host {
     Klangraum::FX8010 fx;
     std::string err;
     fx8010_host(int c, int n, int d) : fx(c, n, d) {}
+    fx8010_host(int c, int n, const std::vector<int>& devs) : fx(c, n, devs) {}
 };
 
 namespace {
@@ -29,6 +31,10 @@ extern "C" {
 fx8010_host* fx8010_host_create(int c, int n, int d) {
     if (c <= 0 || n <= 0) return nullptr;
     return new fx8010_host(c, n, d);
+}
+fx8010_host* fx8010_host_create_multi(int c, int n, const int* devices, int n_devices) {
+    if (c <= 0 || n <= 0 || !devices || n_devices <= 0) return nullptr;
+    return new fx8010_host(c, n, std::vector<int>(devices, devices + n_devices));
 }
 void fx8010_host_destroy(fx8010_host* h) { delete h; }
 const char* fx8010_host_last_error(fx8010_host* h) { return h ? h->err.c_str() : ""; }

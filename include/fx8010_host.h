@@ -20,6 +20,8 @@ typedef struct fx8010_host fx8010_host;
 
 /* FX8010(int numChannels) / the batched constructor FX8010(channels, instances, device) */
 FX8010_API fx8010_host* fx8010_host_create(int n_channels, int n_instances, int device);
+/* FX8010(channels, instances, devices): the instances spread over several GPUs (include/fx8010_multi.h) */
+FX8010_API fx8010_host* fx8010_host_create_multi(int n_channels, int n_instances, const int* devices, int n_devices);
 FX8010_API void fx8010_host_destroy(fx8010_host* h);
 FX8010_API const char* fx8010_host_last_error(fx8010_host* h);
 

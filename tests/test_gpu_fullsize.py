@@ -422,3 +422,27 @@ def test_multi_executor_two_gpus(fx, po):
         assert_bits_equal(m.registers()[:, idx], orc.registers, "2 GPUs registers")
     finally:
         m.close()
+
+
+def test_facade_multi_device_constructor(fx, po):
+    """Klangraum::FX8010(channels, instances, devices): the reference's class surface over several shards (two on device 0
+    here): setRegisterValue(s), processBlock, the counters and the per-sample process() keep their meaning."""
+    rng = np.random.default_rng(103)
+    n = 600
+    prog = fx.Program(progs.CFG2_LOG_GAIN, instances=n, devices=[0, 0])
+    assert prog.loaded
+    img = po.Image(prog.instructions(), prog.registers(), prog.itram_size, prog.xtram_size, prog.controls(), prog.tables())
+    orc = po.Oracle(img, n, 1)
+    vol = rng.random(n).astype(np.float32)
+    assert prog.set_register_values("volume", vol) == 0
+    orc.set_register("volume", vol)
+    x = progs.sine_bank(n, 96, rng).reshape(1, 96, n)
+    assert_bits_equal(prog.process_block(x), orc.process(x), "facade multi processBlock")
+    assert prog.set_register("volume", 0.25) == 0
+    orc.set_register("volume", np.full(n, 0.25, np.float32))
+    y1 = prog.process(np.full((3, 1), 0.5, np.float32))           # per-sample legacy call: instance 0, same input for all
+    yo = orc.process(np.full((1, 3, n), 0.5, np.float32))
+    assert_bits_equal(y1[:, 0], yo[0, :, 0], "facade multi process()")
+    assert prog.instruction_counter_total == int(orc.counts.sum())
+    assert prog.instruction_counter == int(orc.counts[0])
+    assert prog.get_register("volume") == np.float32(0.25)
