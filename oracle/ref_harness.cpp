@@ -41,9 +41,11 @@ using Klangraum::FX8010;
 
 namespace {
 struct CoutSilencer {
-    std::streambuf* old;
-    std::ostringstream sink;
-    CoutSilencer() : old(std::cout.rdbuf(sink.rdbuf())) {}
+    std::ostringstream sink;     // declared (hence constructed) BEFORE it is handed to std::cout: with `old` first, its
+    std::streambuf* old;         // initialiser ran on the unconstructed stream and std::cout wrote through a garbage
+                                 // buffer pointer while the reference's constructor printed — an intermittent SIGSEGV
+                                 // (found with the ASan/UBSan build of this harness, profiles/r02_reference_asan_ubsan.txt)
+    CoutSilencer() : old(nullptr) { old = std::cout.rdbuf(sink.rdbuf()); }
     ~CoutSilencer() { std::cout.rdbuf(old); }
 };
 
