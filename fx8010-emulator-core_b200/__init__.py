@@ -92,6 +92,7 @@ GPU_SYMBOLS = {
     "fx8010_gpu_process_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fx8010_gpu_process_batch_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fx8010_gpu_process_batch_host_slice": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]),
+    "fx8010_gpu_process_batch_host_broadcast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]),
     "fx8010_gpu_host_alloc": (C.c_void_p, [C.c_size_t]),
     "fx8010_gpu_host_free": (None, [C.c_void_p]),
     "fx8010_gpu_synchronize": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -123,6 +124,7 @@ MULTI_SYMBOLS = {
     "fx8010_multi_get_register": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "fx8010_multi_process_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fx8010_multi_process_batch_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "fx8010_multi_process_batch_host_broadcast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "fx8010_multi_synchronize": (C.c_int, [C.c_void_p]),
     "fx8010_multi_get_instruction_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
     "fx8010_multi_get_registers": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -456,6 +458,15 @@ class Gpu:
         self._check(self.L.fx8010_gpu_process_batch_host(self.h, _ptr(x), _ptr(out), n_samples))
         return out
 
+    def process_host_broadcast(self, x, out=None, wait: bool = True) -> np.ndarray:
+        """x: [C][S] — one input signal for all instances; returns / fills out [C][S][N]."""
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.c, -1)
+        if out is None:
+            out = np.zeros((self.c, x.shape[1], self.n), dtype=np.float32)
+        self._check(self.L.fx8010_gpu_process_batch_host_broadcast(self.h, _ptr(x), _ptr(out), x.shape[1], 0, 1 if wait else 0))
+        self._keep_bcast = x
+        return out
+
     def process_host_ptr(self, in_ptr: int, out_ptr: int, n_samples: int, wait: bool = True):
         f = self.L.fx8010_gpu_process_batch_host if wait else self.L.fx8010_gpu_process_batch_host_async
         self._check(f(self.h, in_ptr, out_ptr, n_samples))
@@ -579,6 +590,15 @@ class MultiGpu:
             out = np.zeros((self.c, n_samples, self.n), dtype=np.float32)
         f = self.L.fx8010_multi_process_batch_host if wait else self.L.fx8010_multi_process_batch_host_async
         self._check(f(self.h, _ptr(x), _ptr(out), n_samples))
+        return out
+
+    def process_host_broadcast(self, x, out=None, wait: bool = True) -> np.ndarray:
+        """x: [C][S] — one input signal for all instances of all shards."""
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.c, -1)
+        if out is None:
+            out = np.zeros((self.c, x.shape[1], self.n), dtype=np.float32)
+        self._check(self.L.fx8010_multi_process_batch_host_broadcast(self.h, _ptr(x), _ptr(out), x.shape[1], 1 if wait else 0))
+        self._keep_bcast = x
         return out
 
     def synchronize(self):

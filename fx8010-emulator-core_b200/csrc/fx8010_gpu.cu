@@ -142,6 +142,7 @@ struct fx8010_gpu {
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[HOST_PIPE_BUFS] = {}, ev_comp[HOST_PIPE_BUFS] = {}, ev_d2h[HOST_PIPE_BUFS] = {};
     float* d_stage_in[HOST_PIPE_BUFS] = {}; float* d_stage_out[HOST_PIPE_BUFS] = {};
+    float* d_bcast[HOST_PIPE_BUFS] = {}; size_t bcast_floats = 0;     // [C][sub] staging of a broadcast input (process_batch_host_broadcast)
     size_t stage_floats = 0;
     unsigned long long pipe_seq = 0;             // sub-blocks pushed through the staging buffers so far
     // tuning overrides (0 = heuristic)
@@ -1307,7 +1308,7 @@ void fx8010_gpu_destroy(fx8010_gpu* h) {
     if (h->ev_events) cudaEventDestroy(h->ev_events);
     if (h->ev_order) cudaEventDestroy(h->ev_order);
     for (int i = 0; i < HOST_PIPE_BUFS; ++i) {
-        cudaFree(h->d_stage_in[i]); cudaFree(h->d_stage_out[i]);
+        cudaFree(h->d_stage_in[i]); cudaFree(h->d_stage_out[i]); cudaFree(h->d_bcast[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
         if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
         if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
@@ -1615,8 +1616,17 @@ int fx8010_gpu_process_batch_planar(fx8010_gpu* h, const float* d_in, float* d_o
     return FX8010_OK;
 }
 
+// One input value per channel and sample period for ALL instances (a parameter sweep driven by one signal): [rows] -> [rows][N]
+static __global__ void fx_broadcast_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int N) {
+    const int row = blockIdx.y;
+    const float v = src[row];
+    float* d = dst + (size_t)row * N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) d[i] = v;
+}
+
 // host_n: instances per row of the HOST buffers (>= N: this handle's columns are a slice of a wider [channel][sample][instance] block)
-static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_samples, bool wait, size_t host_n = 0) {
+// bcast: `in` holds ONE value per channel and sample period ([channel][sample]); it is copied as it is and spread over the instances on the device
+static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_samples, bool wait, size_t host_n = 0, bool bcast = false) {
     FX_NEED_PROGRAM(h);
     if (!out || n_samples < 0) return fail(h, FX8010_ERR_ARG, "out is NULL or n_samples negative");
     if (n_samples == 0) return FX8010_OK;
@@ -1642,6 +1652,13 @@ static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_s
         }
         h->stage_floats = need;
     }
+    if (bcast && in && (size_t)(C * sub) > h->bcast_floats) {
+        const int rc = sync_all(h);
+        if (rc) return rc;
+        for (int i = 0; i < HOST_PIPE_BUFS; ++i) { cudaFree(h->d_bcast[i]); h->d_bcast[i] = nullptr; }
+        for (int i = 0; i < HOST_PIPE_BUFS; ++i) FX_CUDA(h, cudaMalloc(&h->d_bcast[i], sizeof(float) * C * sub));
+        h->bcast_floats = (size_t)(C * sub);
+    }
     {   // earlier device-side batches come first
         const int rc = order_on(h, h->s_comp);
         if (rc) return rc;
@@ -1652,7 +1669,10 @@ static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_s
         const int buf = (int)(h->pipe_seq % HOST_PIPE_BUFS);
         const long len = std::min<long>(sub, n_samples - s0);
         if (h->pipe_seq >= HOST_PIPE_BUFS) FX_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_comp[buf], 0));     // stage_in[buf] consumed
-        if (in)
+        if (in && bcast)
+            for (size_t c = 0; c < C; ++c)
+                FX_CUDA(h, cudaMemcpyAsync(h->d_bcast[buf] + c * (size_t)sub, in + c * (size_t)n_samples + s0, sizeof(float) * len, cudaMemcpyHostToDevice, h->s_h2d));
+        else if (in)
             for (size_t c = 0; c < C; ++c) {
                 if (host_n == N)
                     FX_CUDA(h, cudaMemcpyAsync(h->d_stage_in[buf] + c * (size_t)sub * N, in + (c * (size_t)n_samples + s0) * N,
@@ -1664,6 +1684,14 @@ static int process_host_impl(fx8010_gpu* h, const float* in, float* out, int n_s
         FX_CUDA(h, cudaEventRecord(h->ev_h2d[buf], h->s_h2d));
         FX_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_h2d[buf], 0));
         if (h->pipe_seq >= HOST_PIPE_BUFS) FX_CUDA(h, cudaStreamWaitEvent(h->s_comp, h->ev_d2h[buf], 0));    // stage_out[buf] drained
+        if (in && bcast) {
+            for (size_t c = 0; c < C; ++c) {
+                fx_broadcast_kernel<<<dim3((unsigned)std::min<size_t>(64, (N + 255) / 256), (unsigned)len), 256, 0, h->s_comp>>>(
+                    h->d_bcast[buf] + c * (size_t)sub, h->d_stage_in[buf] + c * (size_t)sub * N, (int)len, (int)N);
+                h->info.kernel_launches++;
+            }
+            FX_CUDA(h, cudaGetLastError());
+        }
         const int rc = launch_block(h, in ? h->d_stage_in[buf] : nullptr, h->d_stage_out[buf], (size_t)sub * N, (size_t)sub * N, (int)len, h->s_comp, true);   // (the internal stream carries this handle's launches only)
         if (rc) return rc;
         FX_CUDA(h, cudaEventRecord(h->ev_comp[buf], h->s_comp));
@@ -1690,6 +1718,9 @@ int fx8010_gpu_process_batch_host_async(fx8010_gpu* h, const float* in, float* o
 }
 int fx8010_gpu_process_batch_host_slice(fx8010_gpu* h, const float* in, float* out, int n_samples, size_t host_instances, int wait) {
     return process_host_impl(h, in, out, n_samples, wait != 0, host_instances);
+}
+int fx8010_gpu_process_batch_host_broadcast(fx8010_gpu* h, const float* in, float* out, int n_samples, size_t host_instances, int wait) {
+    return process_host_impl(h, in, out, n_samples, wait != 0, host_instances, true);
 }
 
 int fx8010_gpu_synchronize(fx8010_gpu* h, void* stream) {

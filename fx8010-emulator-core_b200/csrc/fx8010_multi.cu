@@ -166,6 +166,12 @@ static int multi_process(fx8010_multi* m, const float* in, float* out, int n_sam
 int fx8010_multi_process_batch_host(fx8010_multi* m, const float* in, float* out, int n_samples) { return multi_process(m, in, out, n_samples, 1); }
 int fx8010_multi_process_batch_host_async(fx8010_multi* m, const float* in, float* out, int n_samples) { return multi_process(m, in, out, n_samples, 0); }
 
+int fx8010_multi_process_batch_host_broadcast(fx8010_multi* m, const float* in, float* out, int n_samples, int wait) {
+    if (!m || !out || n_samples < 0) return FX8010_ERR_ARG;
+    const size_t N = (size_t)m->N;
+    return run_all(m, [=](Shard& s) { return fx8010_gpu_process_batch_host_broadcast(s.h, in, out + s.lo, n_samples, N, wait); });
+}
+
 int fx8010_multi_synchronize(fx8010_multi* m) {
     if (!m) return FX8010_ERR_ARG;
     return run_all(m, [](Shard& s) { return fx8010_gpu_synchronize(s.h, nullptr); });

@@ -165,17 +165,8 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
             if (I.st_o) vstore<K>(p.latch + (size_t)(w0 >> 24) * cx.N + cx.inst0, r);                             \
             if (SETS_ACC) cx.acc_last = accv;                                                                    \
         }
-    // one sample: operands in set CUR, the next sample's go to set NXT
-#define SL_HALF(SETS_ACC, LOADS_XY, CUR, NXT, ...)                                                               \
-    {                                                                                                            \
-        Vec<K>&a = A##CUR, &x = X##CUR, &y = Y##CUR; Vec<K> r, accv;                                             \
-        (void)x; (void)y;                                                                                        \
-        if (!FINAL && m + 1 < n_m) {                                                                             \
-            if (la) { I.qa += I.sa; A##NXT = lds<K>(I.qa); }                                                     \
-            if (LOADS_XY && lx) { I.qx += I.sx; X##NXT = lds<K>(I.qx); }                                         \
-            if (LOADS_XY && ly) { I.qy += I.sy; Y##NXT = lds<K>(I.qy); }                                         \
-        }                                                                                                        \
-        __VA_ARGS__                                                                                              \
+    // what one sample's result does: this instruction's own stores, or its fused consumer; then every running address moves on
+#define SL_EMIT(SETS_ACC)                                                                                        \
         if (FUSE == 0) { SL_WRITE(SETS_ACC) }                                                                    \
         else if (FUSE <= 2) {   /* the consumer MACS / MACSN (:1077-1094) on the forwarded result; this instruction's own R is dead in the bulk path */ \
             Vec<K> r2;                                                                                           \
@@ -193,9 +184,22 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
                 fw_q[k] = wrap ? fw_ring + (uint64_t)fw_pos[k] * Nl + k : fw_q[k] + Nl;                          \
             }                                                                                                    \
         }                                                                                                        \
+        I.qr += I.sr; I.qccr += I.sccr; I.qo += Nl;
+    // one sample: operands in set CUR, the next sample's go to set NXT
+#define SL_HALF(SETS_ACC, LOADS_XY, CUR, NXT, ...)                                                               \
+    {                                                                                                            \
+        Vec<K>&a = A##CUR, &x = X##CUR, &y = Y##CUR; Vec<K> r, accv;                                             \
+        (void)x; (void)y;                                                                                        \
+        if (!FINAL && m + 1 < n_m) {                                                                             \
+            if (la) { I.qa += I.sa; A##NXT = lds<K>(I.qa); }                                                     \
+            if (LOADS_XY && lx) { I.qx += I.sx; X##NXT = lds<K>(I.qx); }                                         \
+            if (LOADS_XY && ly) { I.qy += I.sy; Y##NXT = lds<K>(I.qy); }                                         \
+        }                                                                                                        \
+        __VA_ARGS__                                                                                              \
+        SL_EMIT(SETS_ACC)                                                                                        \
         if (CM == 1) A##NXT = r;                                                                                 \
         else if (CM == 2) { SL_EACH { if (I.ca) A##NXT[k] = r[k]; if (I.cx) X##NXT[k] = r[k]; if (I.cy) Y##NXT[k] = r[k]; } } \
-        ++m; I.qr += I.sr; I.qccr += I.sccr; I.qo += Nl;                                                         \
+        ++m;                                                                                                     \
     }
 #define SL_LOOP(SETS_ACC, LOADS_XY, ...)                                                                         \
     {                                                                                                            \
@@ -275,6 +279,36 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
     case U_LOG:
     case U_EXP: {
         const uint32_t tb_s = cx.tab_s + (I.aux >> 24) * (uint32_t)TAB_SMEM_BYTES;
+        if (!FINAL && CM == 0 && (w0 & F_TAB_SMEM)) {
+            // A literal table staged in shared memory, nothing carried (the waveshaper of cfg2): TWO samples per iteration with one
+            // range test for both, so that the 2 K dependency chains (F2F -> 3 x FP64 -> gather -> 3 x FP64 -> F2F, about 110 cycles
+            // each) sit in ONE basic block and ptxas interleaves them; the operands of the next pair are fetched meanwhile.
+#define SL_TAB_FAST(src, dst) SL_EACH { double di; const double xd = (double)src[k]; const int ix = table_index_inrange(xd, di); double y1, sl; \
+                                        lds_f64x2(tb_s + (uint32_t)ix * (TAB_REPL * 16u), y1, sl); dst[k] = table_finish(xd, di, y1, sl); }
+#define SL_TAB_SLOW(src, dst) SL_EACH { const bool in_range = fabsf(src[k]) <= 1.0f; double di; const double xd = (double)src[k]; int ix; \
+                                        if (in_range) ix = table_index_inrange(xd, di); else { ix = table_index_wild(src[k]); di = (double)ix; cx.flags |= FX8010_RT_TABLE_RANGE; } /* rule U6 */ \
+                                        double y1, sl; lds_f64x2(tb_s + (uint32_t)ix * (TAB_REPL * 16u), y1, sl); dst[k] = table_finish(xd, di, y1, sl); }
+            int m = 0;
+            Vec<K> B0 = A0, B1 = A0;
+            if (n_m > 1 && la) { I.qa += I.sa; B1 = lds<K>(I.qa); }
+            _Pragma("unroll 1") while (m + 1 < n_m) {
+                Vec<K> N0 = B0, N1 = B1;
+                if (la && m + 2 < n_m) { I.qa += I.sa; N0 = lds<K>(I.qa); }
+                if (la && m + 3 < n_m) { I.qa += I.sa; N1 = lds<K>(I.qa); }
+                bool wild = false;
+                SL_EACH { wild |= !(fabsf(B0[k]) <= 1.0f) || !(fabsf(B1[k]) <= 1.0f); }
+                Vec<K> r0, r1;
+                if (!wild) { SL_TAB_FAST(B0, r0) SL_TAB_FAST(B1, r1) }
+                else { SL_TAB_SLOW(B0, r0) SL_TAB_SLOW(B1, r1) }
+                { Vec<K>& r = r0; Vec<K>& accv = r0; SL_EMIT(true) }
+                { Vec<K>& r = r1; Vec<K>& accv = r1; SL_EMIT(true) }
+                B0 = N0; B1 = N1; m += 2;
+            }
+            if (m < n_m) { Vec<K> r; SL_TAB_SLOW(B0, r) Vec<K>& accv = r; SL_EMIT(true) }
+#undef SL_TAB_FAST
+#undef SL_TAB_SLOW
+            break;
+        }
         SL_LOOP(true, false,
             if (dyn_sel && lx && m + 1 < n_m) { I.qx += I.sx; if (m & 1) X0 = lds<K>(I.qx); else X1 = lds<K>(I.qx); }
             int idx[K];
@@ -359,6 +393,7 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
     }
 #undef SL_EACH
 #undef SL_WRITE
+#undef SL_EMIT
 #undef SL_HALF
 #undef SL_LOOP
 }

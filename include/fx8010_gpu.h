@@ -175,6 +175,13 @@ FX8010_API int fx8010_gpu_process_batch_host_async(fx8010_gpu* h, const float* i
 FX8010_API int fx8010_gpu_process_batch_host_slice(fx8010_gpu* h, const float* in, float* out, int n_samples,
                                                    size_t host_instances, int wait);
 
+/* One input signal for ALL instances (a parameter sweep: N filter settings listening to the same audio, BASELINE.json
+ * configs[3]): `in` is a HOST buffer [n_channels][n_samples] — 4 bytes per channel and sample period instead of 4 N — copied
+ * as it is and spread over the instances on the device; `out` as in the _slice form ([channel][sample][host_instances],
+ * host_instances == 0 means n_instances).  Halves the PCIe traffic of a step, which is what bounds the host-buffer path. */
+FX8010_API int fx8010_gpu_process_batch_host_broadcast(fx8010_gpu* h, const float* in, float* out, int n_samples,
+                                                       size_t host_instances, int wait);
+
 /* ---- the caller's block loop -------------------------------------------
  * The reference's driver changes sliders BETWEEN process() calls, every 8 sample periods
  * (source/main.cpp:107-114: setRegisterValue, then process).  A batched caller would have to cut its

@@ -48,6 +48,8 @@ FX8010_API int fx8010_multi_process_batch_host(fx8010_multi* m, const float* in,
 /* Same, but returns once every device has QUEUED its work (consecutive calls pipeline copies and kernels per
  * device); fx8010_multi_synchronize waits for everything. */
 FX8010_API int fx8010_multi_process_batch_host_async(fx8010_multi* m, const float* in, float* out, int n_samples);
+/* One input signal for all instances: `in` is [n_channels][n_samples] (fx8010_gpu_process_batch_host_broadcast per shard). */
+FX8010_API int fx8010_multi_process_batch_host_broadcast(fx8010_multi* m, const float* in, float* out, int n_samples, int wait);
 FX8010_API int fx8010_multi_synchronize(fx8010_multi* m);
 
 /* Executed instructions summed over all instances (getInstructionCounter, source/FX8010.cpp:986-989). */

@@ -30,5 +30,16 @@ for name, text, n, ctl in (("cfg2_weak", progs.CFG2_LOG_GAIN, 4096 * G, "volume"
         ts.append((time.perf_counter() - t0) / 20)
     dt = float(np.median(ts[1:]))
     out[name] = {"instances": n, "ms_per_step": 1e3 * dt, "instance_samples_per_s": n * S / dt, "pcie_gbs_each_way_total": 4 * n * S / dt / 1e9}
+    if name == "cfg4_strong":       # the parameter sweep driven by ONE input signal: [channel][sample] in, [channel][sample][instance] out
+        xb = np.ascontiguousarray(x[:, :1].T)          # [1][S]
+        ts = []
+        for rep in range(4):
+            t0 = time.perf_counter()
+            for i in range(20):
+                m.process_host_broadcast(xb, out=bufs[i % 3][1][0], wait=False)
+            m.synchronize()
+            ts.append((time.perf_counter() - t0) / 20)
+        dt = float(np.median(ts[1:]))
+        out["cfg4_strong_broadcast_input"] = {"instances": n, "ms_per_step": 1e3 * dt, "instance_samples_per_s": n * S / dt, "pcie_gbs_d2h_total": 4 * n * S / dt / 1e9}
     m.close()
 print(json.dumps(out))

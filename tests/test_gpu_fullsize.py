@@ -446,3 +446,28 @@ def test_facade_multi_device_constructor(fx, po):
     assert prog.instruction_counter_total == int(orc.counts.sum())
     assert prog.instruction_counter == int(orc.counts[0])
     assert prog.get_register("volume") == np.float32(0.25)
+
+
+@pytest.mark.parametrize("shards", [0, 3])
+def test_broadcast_input(fx, po, shards):
+    """One input signal for all instances (a parameter sweep, BASELINE.json configs[3]): the host hands over [channel][sample]
+    only; same results as feeding every instance a copy.  shards = 0: one handle; 3: the multi-GPU executor."""
+    rng = np.random.default_rng(104)
+    n, s = 777, 300
+    prog = fx.Program(progs.CFG4_ONEPOLE)
+    img = po.Image(prog.instructions(), prog.registers(), prog.itram_size, prog.xtram_size, prog.controls(), prog.tables())
+    orc = po.Oracle(img, n, 1)
+    cutoff = (0.001 + 0.998 * rng.random(n)).astype(np.float32)
+    orc.set_register("filter_cutoff", cutoff)
+    g = fx.MultiGpu([0] * shards, n, 1) if shards else fx.Gpu(n, 1)
+    try:
+        g.load_program(prog)
+        g.set_controls(prog.reg_index("filter_cutoff"), cutoff)
+        for b in range(2):
+            x = (1.8 * rng.random((1, s)) - 0.9).astype(np.float32)
+            y = g.process_host_broadcast(x)
+            yo = orc.process(np.repeat(x[:, :, None], n, axis=2))
+            assert_bits_equal(y, yo, f"broadcast block {b}")
+        assert_bits_equal(g.registers(), orc.registers, "broadcast registers")
+    finally:
+        g.close()
