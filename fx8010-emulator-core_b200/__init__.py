@@ -62,7 +62,7 @@ class CControlEvent(C.Structure):
 class CLaunchInfo(C.Structure):
     _fields_ = [("kernel_launches", C.c_ulonglong), ("last_grid", C.c_int32), ("last_block", C.c_int32),
                 ("last_time_split", C.c_int32), ("last_smem_bytes", C.c_int32), ("last_late_wait", C.c_int32),
-                ("last_fused_blocks", C.c_int32), ("kernel_variant", C.c_int32)]
+                ("last_fused_blocks", C.c_int32), ("last_tma", C.c_int32), ("reserved", C.c_int32), ("kernel_variant", C.c_int32)]
 
 
 TRACE_DTYPE = np.dtype([("index", np.int32), ("executed", np.int32), ("r", np.float32), ("a", np.float32), ("x", np.float32),

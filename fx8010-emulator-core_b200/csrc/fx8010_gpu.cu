@@ -5,6 +5,7 @@
 // What the reference does per object and per sample (reference source/FX8010.cpp:1023-1249,
 // one FX8010 object = one DSP instance) happens here per handle and per block of samples for
 // N instances at once.
+#include <cuda.h>            // CUtensorMap and its enums only: cuTensorMapEncodeTiled is resolved at run time (no libcuda link)
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -118,6 +119,7 @@ struct fx8010_gpu {
     std::vector<uint8_t> sl_carried_reg;         // per register: some instruction carries it from sample to sample
     std::vector<uint8_t> sl_fuse;                // per instruction: 0, or 0x80 | bits (fx8010_stateless.cuh F_FUSE) when the NEXT executed instruction is fused into it
     int use_pairs = 1, use_tsplit = 1;
+    int use_tma = 1;                             // 0 never, 1 launches with one time segment (recurrences), 2 every eligible launch
     int use_carry = 1;
     bool short_ok = false;                       // SKIP-free, nobody reads ccr, no noise/MACMV, every channel written: fx_short_kernel when short enough
     bool short_attr_set[3][2][SH_MAX_NI_HOST] = {};
@@ -1008,6 +1010,30 @@ int arena_acquire(fx8010_gpu* h, int fam, int words, bool& fresh) {   // g_dev_m
     }
 }
 
+// The launch's input block as a 2-D tensor for bulk tensor copies (TMA): [rows][N] float32, box = [M rows][B * K instances].
+// Returns false when the driver entry point is missing or the shape does not qualify (the kernel then stages with cp.async).
+bool make_input_map(const float* in, size_t N, size_t rows, int box_cols, int box_rows, SLTensorMap* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) encode = (EncodeFn)fn;
+        else cudaGetLastError();
+    }
+    if (!encode || box_cols > 256 || box_rows > 256 || (N * 4) % 16 != 0 || ((uintptr_t)in & 15u)) return false;
+    static_assert(sizeof(CUtensorMap) == sizeof(SLTensorMap), "CUtensorMap is 128 bytes");
+    const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)N * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(in), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Work this handle queued on another stream comes first (device-side ordering, no host wait).
 int order_on(fx8010_gpu* h, cudaStream_t st) {
     if (h->has_last && h->last_stream != st) {
@@ -1176,6 +1202,15 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
                 p.tr_wfirst[x] = t.w_first;
             }
             p.pdl_late_wait = late_wait;
+            p.use_tma = 0;
+            // Bulk tensor copies (TMA) for the input stage: one instruction per batch and channel instead of one cp.async per thread and
+            // sample row.  Pays where the per-batch overhead is serial with a recurrence (cfg4 at 8 192 instances: 67 -> 59 us, at 65 536:
+            // 125 -> 121 us); a time-split launch loses a little to the block-wide barrier per batch (cfg2 per launch: 8.5 -> 8.6 us) and keeps cp.async.
+            if ((h->use_tma == 2 || (h->use_tma == 1 && L.n_seg == 1 && h->sl_serial)) && !h->sl_tram && nb == 1 && in && L.P == 1 && in_cs % (size_t)h->N == 0) {
+                const size_t rpc = in_cs / (size_t)h->N;
+                if (make_input_map(in, (size_t)h->N, (size_t)(h->C - 1) * rpc + (size_t)ns, L.B * L.K, L.M, &p.in_map)) { p.use_tma = 1; p.tma_rows_per_channel = (int)rpc; }
+            }
+            h->info.last_tma = p.use_tma;
             SLKernelFn fn = pick_sl_kernel(L.K, h->sl_tram);
             bool& attr = h->sl_attr_set[h->sl_tram ? 1 : 0][L.K == 4 ? 2 : (L.K == 2 ? 1 : 0)];
             if (!attr) { FX_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)); attr = true; }
@@ -1283,6 +1318,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     if (getenv("FX8010_NO_FUSE")) h->use_fuse = 0;
     if (getenv("FX8010_NO_PAIRS")) h->use_pairs = 0;
     if (getenv("FX8010_NO_TSPLIT")) h->use_tsplit = 0;
+    if (getenv("FX8010_USE_TMA")) h->use_tma = atoi(getenv("FX8010_USE_TMA"));
     if (getenv("FX8010_NO_STATELESS")) h->use_sl = 0;
     if (getenv("FX8010_NO_SHORT")) h->use_short = 0;
     if (getenv("FX8010_NO_CARRY")) h->use_carry = 0;

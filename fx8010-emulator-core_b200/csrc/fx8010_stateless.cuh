@@ -58,7 +58,15 @@ constexpr int SL_CARRY_SHIFT = 18;           // w0 bits 18..20: operand A / X / 
 
 // (the encoded instruction format is described at sl_exec below; load / write-back lists still use the packed operand word above)
 
-struct SLParams {
+// A CUtensorMap (128 bytes, 64-byte aligned), opaque here: the host encodes it (fx8010_gpu.cu::make_input_map), the kernel only
+// passes its address to cp.async.bulk.tensor.
+struct alignas(64) SLTensorMap { unsigned char bytes[128]; };
+
+struct alignas(64) SLParams {
+    SLTensorMap in_map;         // use_tma: the launch's input block as a 2-D tensor [rows][N], box = [M rows][B * K instances]
+    int use_tma;                // the input stage is filled by ONE bulk tensor copy per batch, channel and thread block (TMA, completion on an
+                                // mbarrier) instead of one cp.async per thread and sample row
+    int tma_rows_per_channel;   // rows between two channels of the input block (in_cstride / N)
     float* gpr;                 // [n_regs][N]
     double* acc;                // [N]
     float* latch;               // [C][N]
@@ -472,6 +480,17 @@ __device__ __forceinline__ void sl_exec(const SLParams& p, SLCtx<K>& cx, const i
     }
 }
 
+// ---- bulk tensor copies (TMA) into the input stage: mbarrier + cp.async.bulk.tensor ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
+    asm volatile("{\n\t.reg .pred P1;\n\tFXK_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra FXK_DONE;\n\tbra FXK_WAIT;\n\tFXK_DONE:\n\t}" ::"r"(bar), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint32_t bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+
 // (x + inc) mod size for 0 <= x < size, inc >= 0; rings longer than the increment (the common case) need no division
 __device__ __forceinline__ int ring_add(int x, int inc, int size) {
     x += inc;
@@ -480,8 +499,8 @@ __device__ __forceinline__ int ring_add(int x, int inc, int size) {
 }
 
 template <int K, bool TRAM>
-__global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const __grid_constant__ SLParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int P = TRAM ? p.P : 1;                      // threads per instance column; they split each batch's samples
     const int B = blockDim.x / P;                      // instance threads (columns) per block
     const int part = TRAM ? (int)threadIdx.x / B : 0;  // this thread's share of every batch: samples [part, part + 1) * M / P
@@ -528,6 +547,24 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
             }
         }
     };
+    // TMA variant of the input stage (delay-free kernel only): thread 0 arms one mbarrier per stage buffer with the bytes of a
+    // batch and issues ONE bulk tensor copy per channel ([M rows][B * K instances], rows past the block's range or the
+    // tensor's end are harmless / zero-filled); everybody waits on the barrier's phase instead of cp.async.wait_group.
+    const bool tma = !TRAM && p.use_tma && has_in;
+    __shared__ __align__(8) unsigned long long s_mbar[2];
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(s_mbar);
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)p.n_smem_tabs * TAB_SMEM_BYTES + p.stage0;   // column 0 of the stage rows
+    auto fetch_tma = [&](int s0, uint32_t boff) {
+        if (threadIdx.x == 0 && s0 < s_end) {
+            const uint32_t bar = bar_s + (boff ? 8u : 0u);
+            mbar_expect_tx(bar, (uint32_t)C * buf_bytes);
+            for (int c = 0; c < C; ++c)
+                tma_load_2d(stage_s + (uint32_t)c * 2u * buf_bytes + boff, &p.in_map, bar, blockIdx.x * B * K, c * p.tma_rows_per_channel + s0);
+        }
+    };
+    if (tma) {
+        if (threadIdx.x == 0) { mbar_init(bar_s, 1); mbar_init(bar_s + 8u, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    } else
     fetch_batch(s_begin, 0);                            // (its group is committed after the TRAM streams joined it, below)
     if (!has_in && part == 0) {                         // no input block: INPUT operands read silence (their rows are the stage rows)
         Vec<K> z;
@@ -678,16 +715,23 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const SLParams p) 
     };
     fetch_tram(s_begin, 0);
     cp_async_commit();
+    if (tma) fetch_tma(s_begin, 0);                     // (after the block-wide barrier above: the mbarriers are initialised and visible)
 
     for (int s0 = s_begin; s0 < s_end; s0 += M, cx.out_b += out_step) {
         const int mb = min(M, s_end - s0);
         // threads sharing a column work on different samples of the same batch: nobody starts fetching batch b + 1's
         // TRAM reads before everybody's writes of batch b - 1 are out
         if (TRAM && P > 1) __syncthreads();
+        if (tma) {
+            __syncthreads();                            // everybody is done reading the buffer the next copy overwrites
+            fetch_tma(s0 + M, cx.boff ^ buf_bytes);
+            mbar_wait(bar_s + (cx.boff ? 8u : 0u), (uint32_t)(((s0 - s_begin) / M) >> 1) & 1u);   // this buffer's k-th use completes phase k
+        } else {
         fetch_batch(s0 + M, cx.boff ^ buf_bytes);
         fetch_tram(s0 + M, cx.boff ^ buf_bytes);
         cp_async_commit();
         cp_async_wait<1>();
+        }
         // a column whose delay is too short for prefetching is run by its first thread alone, which then reads stage rows
         // the other threads of the column fetched: their copies must have landed and be visible
         if (TRAM && P > 1 && !cx.tram_fast) __syncthreads();

@@ -281,6 +281,8 @@ typedef struct fx8010_launch_info {
     int32_t last_smem_bytes;
     int32_t last_late_wait;               /* the last launch postponed its wait for its predecessor (see FX8010_OPT_STREAM_EXCLUSIVE) */
     int32_t last_fused_blocks;            /* sample blocks the last launch covered (fx8010_gpu_process_blocks) */
+    int32_t last_tma;                     /* the last launch staged its input with bulk tensor copies (TMA) */
+    int32_t reserved;
     int32_t kernel_variant;               /* bit0 SKIP, bit1 TRAM/noise/MACMV, bit2 stateless, bit3 instruction-major kernel, bit5 short-program kernel, bit6 producer/consumer pairs fused, bits 8..15 instances per thread, bits 16.. samples per batch */
 } fx8010_launch_info;
 FX8010_API int fx8010_gpu_get_launch_info(fx8010_gpu* h, fx8010_launch_info* out);

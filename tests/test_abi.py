@@ -61,7 +61,7 @@ def test_host_header_symbols_exported(fx):
 
 def test_struct_layouts_match_header(fx):
     assert ctypes.sizeof(fx.CInstr) == 24 and ctypes.sizeof(fx.CReg) == 16
-    assert ctypes.sizeof(fx.CDims) == 32 and ctypes.sizeof(fx.CLaunchInfo) == 40
+    assert ctypes.sizeof(fx.CDims) == 32 and ctypes.sizeof(fx.CLaunchInfo) == 48
 
 
 def test_no_cpu_fallback(fx):

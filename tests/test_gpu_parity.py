@@ -283,10 +283,13 @@ STATELESS_PROGS = {
 
 
 @pytest.mark.parametrize("name", sorted(STATELESS_PROGS))
-@pytest.mark.parametrize("mode", ["M1", "M2", "M4", "M8", "generic"])
+@pytest.mark.parametrize("mode", ["M1", "M2", "M4", "M8", "generic", "M8tma"])
 def test_stateless_kernel_modes(fx, po, name, mode, monkeypatch):
     """Stateless programs through the sample-batched kernel at every batch length and through the
     generic kernel: identical bits, identical final state (several calls, ragged lengths)."""
+    if mode == "M8tma":                 # input stage filled by bulk tensor copies (TMA) instead of cp.async
+        monkeypatch.setenv("FX8010_USE_TMA", "2")
+        mode = "M8"
     if mode == "generic":
         monkeypatch.setenv("FX8010_NO_STATELESS", "1")
     else:
@@ -315,8 +318,12 @@ CARRIED_PROGS = {
 
 
 @pytest.mark.parametrize("name", sorted(CARRIED_PROGS))
-@pytest.mark.parametrize("mode", ["auto", "M2", "M4", "K1", "K2", "nocarry", "noshort"])
+@pytest.mark.parametrize("mode", ["auto", "M2", "M4", "K1", "K2", "nocarry", "noshort", "no_tma", "tma_everywhere"])
 def test_carried_recurrences(fx, po, name, mode, monkeypatch):
+    if mode == "no_tma":                 # the input stage of a recurrence is filled by bulk tensor copies (TMA) by default
+        monkeypatch.setenv("FX8010_USE_TMA", "0")
+    elif mode == "tma_everywhere":
+        monkeypatch.setenv("FX8010_USE_TMA", "2")
     if mode[0] == "M":
         monkeypatch.setenv("FX8010_TUNE_M", mode[1:])
     elif mode[0] == "K":
