@@ -192,7 +192,7 @@ __device__ __forceinline__ void sl_run(const SLParams& p, SLCtx<K>& cx, SLInstr&
                 fw_q[k] = wrap ? fw_ring + (uint64_t)fw_pos[k] * Nl + k : fw_q[k] + Nl;                          \
             }                                                                                                    \
         }                                                                                                        \
-        I.qr += I.sr; I.qccr += I.sccr; I.qo += Nl;
+        if (FUSE == 0) { I.qr += I.sr; I.qccr += I.sccr; I.qo += Nl; }      /* (a fused producer stores nothing of its own in the bulk path) */
     // one sample: operands in set CUR, the next sample's go to set NXT
 #define SL_HALF(SETS_ACC, LOADS_XY, CUR, NXT, ...)                                                               \
     {                                                                                                            \
