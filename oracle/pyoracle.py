@@ -21,7 +21,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
-REF_SO = os.path.join(HERE, "_ref", "libfx8010_ref.so")
+REF_SO = os.environ.get("FX_REF_SO", os.path.join(HERE, "_ref", "libfx8010_ref.so"))
 
 # enum values shared with include/fx8010_gpu.h
 OPC = dict(macs=0, macsn=1, macw=2, macwn=3, macints=4, macintw=5, acc3=6, macmv=7, andxor=8,

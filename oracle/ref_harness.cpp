@@ -53,7 +53,15 @@ FX8010* make_object(int channels) {
     void* mem = calloc(1, sizeof(FX8010));
     if (!mem) return nullptr;
     CoutSilencer s;
-    return new (mem) FX8010(channels);
+    FX8010* fx = new (mem) FX8010(channels);
+    // [U5] LOG/EXP at A == 1.0 read T[64], one element past each 64-entry table (source/FX8010.cpp:290), times (x - x1) = 0.
+    // In a bare heap that slot is whatever the allocator left behind the block: an Inf/NaN pattern there turns the result into
+    // NaN, and the next LOG then indexes with (int)NaN = INT_MIN and dies (the SIGSEGV of bench.py's parity leg on rank 6 of an
+    // 8-GPU run; reproducible on CPU).  The tables' storage is re-seated here so that the slot exists and holds 0.0 — the
+    // ledger's rule, the restatement's and the kernel's — without touching the reference's code or the values it computed.
+    for (auto* tabs : {&fx->lookupTablesLog, &fx->lookupTablesExp})
+        for (auto& t : *tabs) { t.push_back(0.0); t.pop_back(); }
+    return fx;
 }
 void free_object(FX8010* fx) {
     if (!fx) return;
