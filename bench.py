@@ -271,6 +271,8 @@ class Workload:
     def new_handle(self):
         g = self.fx.Gpu(self.n, 1, self.local_rank)
         g.load_program(self.prog)
+        # general-interpreter programs (cfg5): translated kernel, compiled before the first launch (FX8010_BENCH_TRANSLATE=0: the interpreter)
+        g.set_option(self.fx.OPT_TRANSLATE, int(os.environ.get("FX8010_BENCH_TRANSLATE", "2")))
         for name, v in self.controls.items():
             g.set_controls(self.prog.reg_index(name), v)
         return g
@@ -486,8 +488,10 @@ def main():
             W.gpu.synchronize(W.st)
     clocks = sampler.stop() if rank == 0 else None
     info = W.gpu.launch_info()
+    translated = W.gpu.translate_status()
     kernel_cfg = {"grid": info.last_grid, "block": info.last_block, "time_split": info.last_time_split, "blocks_per_launch": info.last_fused_blocks,
-                  "smem_bytes": info.last_smem_bytes, "instances_per_thread": (info.kernel_variant >> 8) & 0xff, "samples_per_batch": info.kernel_variant >> 16}
+                  "smem_bytes": info.last_smem_bytes, "instances_per_thread": (info.kernel_variant >> 8) & 0xff, "samples_per_batch": info.kernel_variant >> 16,
+                  "translated_kernel": bool(info.kernel_variant & 128)}
     value = float(n_inst) * BLOCK * args.steps * world / (ms * 1e-3)
     # the same steps as one C-ABI call per step from this Python loop, and one block alone on an idle GPU
     per_call_ms = max_over_ranks(W.per_call(args.steps, barrier, exclusive=False))
@@ -555,6 +559,7 @@ def main():
                    "value": float(n_cfg) * BLOCK * world / step_s, "unit": "instance-samples/s", "dsp_instr_per_s": ex / step_s,
                    "hbm_frac": b_cfg * n_cfg * BLOCK / step_s / 1e9 / peak, "gpu_launches": l_n, "parity": par}
             if cfg == "cfg5":
+                rec["translated"] = Wc.gpu.translate_status()      # FX8010_OPT_TRANSLATE: state 2 = the NVRTC-compiled kernel ran
                 rec["compute_roofline"] = compute_roofline(t_cfg, ex / world, n_cfg, step_s, (clocks or {}).get("sm_mhz") if clocks else None, b_cfg, peak)
             sharded[cfg] = rec
             Wc.close()
@@ -596,6 +601,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "parity": parity}
     if sharded:
         line["sharded"] = sharded
+    if args.config == "cfg5":
+        line["translated"] = translated
     if args.config == "cfg5":        # compute-bound program: the arithmetic roofline of SURVEY.md §8d beside the HBM one
         line["compute_roofline"] = compute_roofline(text, instr_per_step / world, n_inst, 1e-3 * ms / args.steps,
                                                     (clocks or {}).get("sm_mhz"), bytes_per, peak)

@@ -24,6 +24,7 @@ HOST_SO = os.path.join(HERE, "libfx8010_host.so")
 STATUS = {0: "OK", 1: "ERR_ARG", 2: "ERR_CUDA", 3: "ERR_NO_PROGRAM", 4: "ERR_PROGRAM", 5: "ERR_CAPACITY"}
 RT_END_SKIPPED_CAP, RT_TABLE_RANGE = 1, 2
 OPT_STREAM_EXCLUSIVE = 1
+OPT_TRANSLATE = 2          # 0 never, 1 background compile (default), 2 compile before the first launch
 
 
 class FxError(RuntimeError):
@@ -111,6 +112,8 @@ GPU_SYMBOLS = {
     "fx8010_gpu_process_batch_planar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fx8010_gpu_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fx8010_gpu_get_launch_info": (C.c_int, [C.c_void_p, C.POINTER(CLaunchInfo)]),
+    "fx8010_gpu_translate_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
+    "fx8010_translate_source": (C.c_longlong, [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_int)]),
 }
 
 MULTI_SYMBOLS = {
@@ -349,6 +352,19 @@ class Program:
         return self.L.fx8010_host_instruction_counter_total(self.h)
 
 
+def translate_source(prog: "Program", channels: int = 1, compile_check: bool = False):
+    """CUDA source the translator generates for a decoded program (no device needed).  Returns (source or None when the
+    program is not eligible, CUBIN size when compile_check else None)."""
+    L = gpu_lib()
+    n = L.fx8010_translate_source(prog.image_ptr(), channels, None, 0, 0, None)
+    if n < 0:
+        return None, None
+    buf = C.create_string_buffer(int(n) + 1)
+    cub = C.c_int(0)
+    L.fx8010_translate_source(prog.image_ptr(), channels, buf, int(n) + 1, 1 if compile_check else 0, C.byref(cub))
+    return buf.value.decode(), (cub.value if compile_check else None)
+
+
 class Gpu:
     """One fx8010_gpu handle: N instances of one decoded program on one GPU (include/fx8010_gpu.h)."""
 
@@ -435,6 +451,13 @@ class Gpu:
 
     def set_option(self, option: int, value: int):
         self._check(self.L.fx8010_gpu_set_option(self.h, option, value))
+
+    def translate_status(self) -> dict:
+        """State of the program translator (FX8010_OPT_TRANSLATE): 0 not attempted, 1 compiling, 2 in use, -1 not translated."""
+        st, regs, loc = C.c_int(0), C.c_int(0), C.c_int(0)
+        msg = C.create_string_buffer(4096)
+        self._check(self.L.fx8010_gpu_translate_status(self.h, C.byref(st), C.byref(regs), C.byref(loc), msg, 4096))
+        return {"state": st.value, "regs_per_thread": regs.value, "local_bytes": loc.value, "message": msg.value.decode(errors="replace")}
 
     def process_device_events(self, d_in, d_out, n_samples: int, events, stream=None):
         """events: iterable of (sample, reg_index, value) with value a float (broadcast) or an array of N floats."""

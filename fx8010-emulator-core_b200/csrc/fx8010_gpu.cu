@@ -8,13 +8,21 @@
 #include <cuda.h>            // CUtensorMap and its enums only: cuTensorMapEncodeTiled is resolved at run time (no libcuda link)
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <mutex>
+#include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fx8010_families.h"
@@ -149,6 +157,16 @@ struct fx8010_gpu {
     unsigned long long pipe_seq = 0;             // sub-blocks pushed through the staging buffers so far
     // tuning overrides (0 = heuristic)
     int tune_K = 0, tune_B = 0, tune_seg = 0, tune_sub = 0, tune_P = 0, use_split = 1;
+    // program translator (fx8010_translate.inc)
+    int use_translate = 1;                       // FX8010_OPT_TRANSLATE: 0 never, 1 background compile + switch when ready, 2 compile before the first launch
+    int tr_state = 0;                            // 0 not looked at, 1 compiling, 2 kernel loaded, -1 not eligible / failed (tr_error says why)
+    void* tr_fn = nullptr;                       // CUfunction of the translated kernel
+    int tr_regs = 0, tr_local = 0;               // its registers per thread / local-memory bytes (spills)
+    std::shared_ptr<void> tr_job;                // the running compilation
+    std::string tr_error;
+    std::vector<uint8_t> tr_folded;              // per register: its value is an immediate of the translated kernel ...
+    std::vector<float> tr_fold_value;            // ... namely this one
+    std::vector<uint8_t> tr_volatile;            // per register: the host changed it after load — never folded again
     std::string err;
     fx8010_launch_info info = {};
 };
@@ -755,6 +773,8 @@ bool use_short_kernel(const fx8010_gpu* h) {
 }
 KernelFn pick_short_kernel(int K, bool ext, int ni) { return short_kernel(K, ext, ni); }
 
+#include "fx8010_translate.inc"
+
 // Geometry of one launch: contexts per thread, block size, time split.
 int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_cs, size_t out_cs, int n_samples, Launch& L) {
     const int N = h->N, C = h->C, nr = (int)h->reg_map.size();
@@ -1082,6 +1102,14 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
             }
         return FX8010_OK;
     }
+    // Programs of the general interpreter run on their translated kernel once it exists (fx8010_translate.inc).
+    if (!(h->sl_ok && h->use_sl) && !use_short_kernel(h) && !h->trace_mode && tr_ready(h)) {
+        for (int b = 0; b < n_blk; ++b) {
+            const int rc = tr_launch(h, ins[b], outs[b], in_cs, out_cs, n_samples, st);
+            if (rc) return rc;
+        }
+        return FX8010_OK;
+    }
     const int ns = n_samples;
     const bool fusable = h->sl_ok && h->use_sl && !h->trace_mode && !h->sl_serial && h->use_fuse;
     for (int b0 = 0; b0 < n_blk;) {
@@ -1322,6 +1350,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     if (getenv("FX8010_NO_CARRY")) h->use_carry = 0;
     if (getenv("FX8010_NO_TRAM_IM")) h->use_tram_im = 0;
     if (getenv("FX8010_NO_SPLIT")) h->use_split = 0;
+    if (getenv("FX8010_TRANSLATE")) h->use_translate = std::min(2, std::max(0, atoi(getenv("FX8010_TRANSLATE"))));
     h->tune_P = env_int("FX8010_TUNE_P");
     h->tune_M = env_int("FX8010_TUNE_M");
     h->tune_chunk = env_int("FX8010_TUNE_CHUNK");
@@ -1450,6 +1479,8 @@ int fx8010_gpu_load_program(fx8010_gpu* h, const fx8010_program_image* im) {
     h->reg_uniform.assign(nr, 1);
     h->reg_value.resize(nr);
     for (size_t r = 0; r < nr; ++r) h->reg_value[r] = im->regs[r].init_value;
+    h->tr_volatile.assign(nr, 0); h->tr_folded.assign(nr, 0); h->tr_fold_value.assign(nr, 0.0f);
+    tr_reset(h);
     analyse(h);
     FX_CUDA(h, cudaMalloc(&h->d_wb, sizeof(uint32_t) * std::max<size_t>(1, h->wb.size())));
     FX_CUDA(h, cudaMalloc(&h->d_latch_ch, sizeof(uint32_t) * 256));
@@ -1488,6 +1519,7 @@ int fx8010_gpu_set_controls(fx8010_gpu* h, int reg, const float* values, int bro
         h->reg_uniform[reg] = 0;
     }
     if (h->enc_sensitive[reg]) h->encode_dirty = true;
+    tr_touch(h, reg);
     return FX8010_OK;
 }
 
@@ -1500,6 +1532,7 @@ int fx8010_gpu_set_controls_device(fx8010_gpu* h, int reg, const float* d_values
     FX_CUDA(h, cudaMemcpyAsync(h->d_gpr + (size_t)reg * h->N, d_values, sizeof(float) * h->N, cudaMemcpyDeviceToDevice, st));
     h->reg_uniform[reg] = 0;
     if (h->enc_sensitive[reg]) h->encode_dirty = true;
+    tr_touch(h, reg);
     return FX8010_OK;
 }
 
@@ -1533,6 +1566,12 @@ int fx8010_gpu_process_blocks(fx8010_gpu* h, const float* const* d_in, float* co
 int fx8010_gpu_set_option(fx8010_gpu* h, int option, int value) {
     if (!h) return FX8010_ERR_ARG;
     if (option == FX8010_OPT_STREAM_EXCLUSIVE) { h->stream_exclusive = value ? 1 : 0; h->chain.clear(); return FX8010_OK; }
+    if (option == FX8010_OPT_TRANSLATE) {
+        if (value < 0 || value > 2) return fail(h, FX8010_ERR_ARG, "FX8010_OPT_TRANSLATE takes 0, 1 or 2");
+        h->use_translate = value;
+        if (h->tr_state < 0) tr_reset(h);                    // look again (e.g. after FX8010_NVRTC was set)
+        return FX8010_OK;
+    }
     return fail(h, FX8010_ERR_ARG, "unknown option");
 }
 
@@ -1590,6 +1629,7 @@ int fx8010_gpu_process_batch_events(fx8010_gpu* h, const float* d_in, float* d_o
                 h->reg_uniform[ev.reg_index] = 0;
             }
             if (h->enc_sensitive[ev.reg_index]) h->encode_dirty = true;
+            tr_touch(h, ev.reg_index);
         }
         if (s0 >= n_samples) break;
         const int s1 = (e < n_events) ? std::min(n_samples, (int)events[e].sample) : n_samples;
@@ -1816,7 +1856,14 @@ int fx8010_gpu_set_registers(fx8010_gpu* h, const float* in) {
     const int rc = sync_all(h);
     if (rc) return rc;
     FX_CUDA(h, cudaMemcpy(h->d_gpr, in, sizeof(float) * h->regs.size() * h->N, cudaMemcpyHostToDevice));
-    std::fill(h->reg_uniform.begin(), h->reg_uniform.end(), 0);
+    for (size_t r = 0; r < h->regs.size(); ++r) {            // rows holding one bit pattern in every instance stay load-time constants
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(in) + r * (size_t)h->N;
+        bool same = true;
+        for (int i = 1; i < h->N && same; ++i) same = row[i] == row[0];
+        h->reg_uniform[r] = same ? 1 : 0;
+        if (same) memcpy(&h->reg_value[r], row, 4);
+        tr_touch(h, (int)r);
+    }
     h->encode_dirty = true;
     return FX8010_OK;
 }
@@ -1913,6 +1960,47 @@ int fx8010_gpu_trace(fx8010_gpu* h, const float* in, float* out, int n_samples, 
     }
     cleanup();
     return rc;
+}
+
+// ---- program translator: status and the host-only source generator (tests/test_translate.py) ----
+int fx8010_gpu_translate_status(fx8010_gpu* h, int* state, int* regs_per_thread, int* local_bytes, char* message, size_t message_cap) {
+    if (!h) return FX8010_ERR_ARG;
+    if (h->tr_state == 1 && h->loaded) tr_ready(h);          // pick up a finished background compilation
+    if (state) *state = h->tr_state;
+    if (regs_per_thread) *regs_per_thread = h->tr_regs;
+    if (local_bytes) *local_bytes = h->tr_local;
+    if (message && message_cap) { strncpy(message, h->tr_error.c_str(), message_cap - 1); message[message_cap - 1] = 0; }
+    return FX8010_OK;
+}
+
+// Needs no device: analyses the image as load_program would and returns the CUDA source of its translated kernel.
+long long fx8010_translate_source(const fx8010_program_image* im, int n_channels, char* buf, size_t cap, int compile_check, int* regs_or_status) {
+    if (!im || !im->instrs || !im->regs || im->n_instrs <= 0 || im->n_regs <= 0 || n_channels <= 0) return -1;
+    fx8010_gpu tmp;
+    tmp.C = n_channels; tmp.N = 1;
+    tmp.instrs.assign(im->instrs, im->instrs + im->n_instrs);
+    tmp.regs.assign(im->regs, im->regs + im->n_regs);
+    for (const fx8010_instr& in : tmp.instrs)
+        if (in.opcode < 0 || in.opcode >= FX_NUM_OPCODES || in.r < 0 || in.r >= im->n_regs || in.a < 0 || in.a >= im->n_regs ||
+            in.x < 0 || in.x >= im->n_regs || in.y < 0 || in.y >= im->n_regs) return -1;
+    for (const fx8010_reg& r : tmp.regs) if (r.io_index < 0 || r.io_index >= n_channels) return -1;
+    tmp.itram_size = im->itram_size; tmp.xtram_size = im->xtram_size;
+    tmp.reg_uniform.assign(im->n_regs, 1);
+    tmp.reg_value.resize(im->n_regs);
+    for (int r = 0; r < im->n_regs; ++r) tmp.reg_value[r] = im->regs[r].init_value;
+    tmp.tr_volatile.assign(im->n_regs, 0);
+    analyse(&tmp);
+    if (!tr_eligible(&tmp)) return -2;
+    std::vector<uint8_t> folded;
+    const std::string src = tr_generate(&tmp, folded);
+    if (buf && cap) { strncpy(buf, src.c_str(), cap - 1); buf[cap - 1] = 0; }
+    if (compile_check) {                                     // NVRTC -> sm_100a CUBIN (works without a GPU)
+        std::vector<char> cubin; std::string log;
+        const bool ok = translate_compile(src, cubin, log);
+        if (regs_or_status) *regs_or_status = ok ? (int)cubin.size() : -1;
+        if (!ok) fprintf(stderr, "fx8010_translate_source: %s\n", log.c_str());
+    }
+    return (long long)src.size();
 }
 
 const char* fx8010_gpu_last_error(fx8010_gpu* h) { return h ? h->err.c_str() : g_create_error.c_str(); }

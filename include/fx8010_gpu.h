@@ -131,8 +131,15 @@ FX8010_API int fx8010_gpu_load_program(fx8010_gpu* h, const fx8010_program_image
  * events (other handles of this library included).  Consecutive launches of a program without state across sample
  * periods may then overlap on the device (programmatic dependent launch with a postponed wait) whenever their buffers
  * are disjoint from those of every launch that can still be running.  Without the promise every launch waits for
- * its predecessor on the stream at its start. */
-enum fx8010_option { FX8010_OPT_STREAM_EXCLUSIVE = 1 };
+ * its predecessor on the stream at its start.
+ *
+ * FX8010_OPT_TRANSLATE (default 1; env FX8010_TRANSLATE): programs that need the general interpreter (SKIP, noise, MACMV,
+ * state carried between instructions) are translated into one straight-line sm_100a kernel with NVRTC — registers in
+ * hardware registers, literals as immediates, SKIP as a forward branch — with results bit-identical to the interpreter's.
+ * 0 = never; 1 = compile in a background thread when such a program first runs and switch to the kernel once it is
+ * loaded (no call waits for the compiler; until then, and on a box without libnvrtc, the interpreter kernel runs);
+ * 2 = compile before the first launch (the call waits).  fx8010_gpu_translate_status reports what happened. */
+enum fx8010_option { FX8010_OPT_STREAM_EXCLUSIVE = 1, FX8010_OPT_TRANSLATE = 2 };
 FX8010_API int fx8010_gpu_set_option(fx8010_gpu* h, int option, int value);
 
 /* ---- controls: setRegisterValue / getRegisterValue (source/FX8010.cpp:236-266) ---------- */
@@ -271,6 +278,18 @@ FX8010_API int fx8010_gpu_trace(fx8010_gpu* h, const float* in, float* out, int 
                                 fx8010_trace_entry* entries);
 
 
+/* Program translator (FX8010_OPT_TRANSLATE).  state: 0 not attempted yet, 1 compiling, 2 translated kernel in use,
+ * -1 not translated (message says why: not eligible, no libnvrtc, compiler output).  regs_per_thread / local_bytes
+ * describe the loaded kernel.  Any pointer may be NULL. */
+FX8010_API int fx8010_gpu_translate_status(fx8010_gpu* h, int* state, int* regs_per_thread, int* local_bytes,
+                                           char* message, size_t message_cap);
+/* The CUDA source the translator generates for an image (no device needed; a test and inspection aid — the generated
+ * source also compiles as plain C++ with -DFXT_HOST_CHECK, which is how tests/test_translate.py checks it on the CPU).
+ * Returns the source length (copied, truncated, into buf when given), -1 for a bad image, -2 when the program is not
+ * eligible.  compile_check != 0 also runs NVRTC for sm_100a and stores the CUBIN size (or -1) in *cubin_bytes. */
+FX8010_API long long fx8010_translate_source(const fx8010_program_image* image, int n_channels, char* buf, size_t cap,
+                                             int compile_check, int* cubin_bytes);
+
 /* Text of the last error on this handle (or of the last failed create when h == NULL). */
 FX8010_API const char* fx8010_gpu_last_error(fx8010_gpu* h);
 
@@ -283,7 +302,7 @@ typedef struct fx8010_launch_info {
     int32_t last_fused_blocks;            /* sample blocks the last launch covered (fx8010_gpu_process_blocks) */
     int32_t last_tma;                     /* the last launch staged its input with bulk tensor copies (TMA) */
     int32_t reserved;
-    int32_t kernel_variant;               /* bit0 SKIP, bit1 TRAM/noise/MACMV, bit2 stateless, bit3 instruction-major kernel, bit5 short-program kernel, bit6 producer/consumer pairs fused, bits 8..15 instances per thread, bits 16.. samples per batch */
+    int32_t kernel_variant;               /* bit0 SKIP, bit1 TRAM/noise/MACMV, bit2 stateless, bit3 instruction-major kernel, bit5 short-program kernel, bit6 producer/consumer pairs fused, bit7 translated kernel (FX8010_OPT_TRANSLATE), bits 8..15 instances per thread, bits 16.. samples per batch */
 } fx8010_launch_info;
 FX8010_API int fx8010_gpu_get_launch_info(fx8010_gpu* h, fx8010_launch_info* out);
 

@@ -1,0 +1,157 @@
+"""GPU parity of the program translator (FX8010_OPT_TRANSLATE): the NVRTC-compiled straight-line kernel against the
+oracle, bit for bit, through the C ABI — and against the interpreter kernel it replaces."""
+import time
+
+import numpy as np
+import pytest
+
+import progs
+from conftest import assert_bits_equal
+from test_gpu_parity import compare_state, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def run_translated(fx, po, text, n, blocks, rng, channels=1, controls=None, amp=0.9, what="case", mode=2, device_path=False):
+    prog, img, orc, gpu = make_pair(fx, po, text, n, channels)
+    try:
+        gpu.set_option(fx.OPT_TRANSLATE, mode)
+        for name, vals in (controls or {}).items():
+            idx = prog.reg_index(name)
+            gpu.set_controls(idx, vals)
+            orc.set_register(idx, vals)
+        start = 0
+        for s in blocks:
+            x = (2 * amp * rng.random((channels, s, n)) - amp).astype(np.float32)
+            yo = orc.process(x)
+            yg = gpu.process_host(x)
+            assert_bits_equal(yg, yo, f"{what} outputs of block at {start}")
+            start += s
+        compare_state(gpu, orc, img, what, sorted({0, n - 1, n // 2}))
+        return gpu.translate_status(), gpu.launch_info()
+    finally:
+        gpu.close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_programs_translated(fx, po, seed):
+    rng = np.random.default_rng(3000 + seed)
+    ch = 1 + seed % 2
+    text = progs.random_program(rng, 32 + 9 * seed, channels=ch, xtram=bool(seed % 3 == 0))
+    st, info = run_translated(fx, po, text, 96 + 37 * seed, [65, 31], rng, channels=ch, what=f"translated random {seed}")
+    assert st["state"] == 2, st
+    assert info.kernel_variant & 128
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_programs_unsafe_translated(fx, po, seed):
+    rng = np.random.default_rng(4000 + seed)
+    text = progs.random_program(rng, 70, safe=False, wild_tables=True)
+    st, _ = run_translated(fx, po, text, 200, [40], rng, what=f"translated unsafe {seed}")
+    assert st["state"] == 2, st
+
+
+def test_cfg5_translated(fx, po):
+    rng = np.random.default_rng(progs.SEED)
+    n = 512
+    ctl = {f"k{i}": rng.random(n).astype(np.float32) for i in range(4)}
+    st, info = run_translated(fx, po, progs.cfg5_allops(), n, [64, 32], rng, controls=ctl, what="cfg5 translated")
+    assert st["state"] == 2, st
+    assert info.kernel_variant & 128
+    assert st["regs_per_thread"] > 0
+
+
+def test_noise_macmv_tram_translated(fx, po):
+    rng = np.random.default_rng(11)
+    text = "\n".join(["static noise", "static a", "static d", "static m", "input in_l 0", "output out_l 0", "itramsize 37 ", "xtramsize 50 ",
+                      "macs a, in_l, noise, 0.125", "macmv m, a, in_l, 0.5", "macmv m, m, a, 0.25", "macs a, a, 0, 0",
+                      "idelay write, a, at, 0", "idelay read, d, at, 36", "xdelay write, d, at, 3", "xdelay read, m, at, 40",
+                      "skip ccr, ccr, 2, 1", "macs d, d, m, 0.5", "macs out_l, d, a, 0.5", "end"])
+    st, _ = run_translated(fx, po, text, 333, [90, 45], rng, what="translated noise/macmv/tram")
+    assert st["state"] == 2, st
+
+
+def test_ineligible_program_keeps_the_interpreter(fx, po):
+    rng = np.random.default_rng(5)
+    text = "\n".join(["static n = 1", "static a", "input in_l 0", "output out_l 0", "macs n, 0, 1, 1", "skip ccr, ccr, 2, n",
+                      "macs a, in_l, 0.5, 0.5", "macs out_l, a, 0, 0", "end"])
+    st, info = run_translated(fx, po, text, 64, [33], rng, what="ineligible")
+    assert st["state"] == -1 and "SKIP" in st["message"], st
+    assert not (info.kernel_variant & 128)
+
+
+def test_folded_register_changed_by_the_host(fx, po):
+    """A never-written static is an immediate of the translated kernel; when the host overwrites it the kernel is rebuilt
+    (once: the register is not folded again) and results keep matching."""
+    rng = np.random.default_rng(6)
+    n = 128
+    text = "\n".join(["static g = 0.5", "static a", "input in_l 0", "output out_l 0", "macs a, 0, in_l, g", "skip ccr, ccr, 6, 1",
+                      "macsn a, a, g, g", "macs out_l, a, g, 0.25", "end"])
+    prog, img, orc, gpu = make_pair(fx, po, text, n)
+    try:
+        gpu.set_option(fx.OPT_TRANSLATE, 2)
+        x = (1.8 * rng.random((1, 50, n)) - 0.9).astype(np.float32)
+        assert_bits_equal(gpu.process_host(x), orc.process(x), "before")
+        assert gpu.translate_status()["state"] == 2
+        g = prog.reg_index("g")
+        gpu.set_controls(g, np.float32(0.75), broadcast=True); orc.set_register(g, np.full(n, 0.75, np.float32))
+        assert_bits_equal(gpu.process_host(x), orc.process(x), "after a broadcast change")
+        assert gpu.translate_status()["state"] == 2
+        v = rng.random(n).astype(np.float32)
+        gpu.set_controls(g, v); orc.set_register(g, v)
+        assert_bits_equal(gpu.process_host(x), orc.process(x), "after a per-instance change")
+        compare_state(gpu, orc, img, "folded register")
+    finally:
+        gpu.close()
+
+
+def test_background_compile_switches_over(fx, po):
+    """Mode 1: the first launches run on the interpreter while NVRTC works in a thread; later launches use the translated
+    kernel; the output stream is the same bits throughout."""
+    rng = np.random.default_rng(7)
+    n = 256
+    text = progs.random_program(rng, 90)
+    prog, img, orc, gpu = make_pair(fx, po, text, n)
+    try:
+        gpu.set_option(fx.OPT_TRANSLATE, 1)
+        seen = set()
+        t0 = time.time()
+        while time.time() - t0 < 60:
+            x = (1.8 * rng.random((1, 16, n)) - 0.9).astype(np.float32)
+            assert_bits_equal(gpu.process_host(x), orc.process(x), "stream")
+            seen.add(bool(gpu.launch_info().kernel_variant & 128))
+            if True in seen and len(seen) == 2:
+                break
+            time.sleep(0.02)
+        assert True in seen, gpu.translate_status()
+        compare_state(gpu, orc, img, "background")
+    finally:
+        gpu.close()
+
+
+def test_translated_matches_interpreter_device_path(fx, po):
+    """Same program, same inputs: translated kernel vs interpreter kernel through process_device at 20 000 instances."""
+    import torch
+    rng = np.random.default_rng(8)
+    n, s = 20000, 48
+    text = progs.cfg5_allops(n_instr=200)
+    prog = fx.Program(text)
+    ctl = {f"k{i}": rng.random(n).astype(np.float32) for i in range(4)}
+    outs = []
+    for mode in (0, 2):
+        gpu = fx.Gpu(n, 1)
+        gpu.load_program(prog)
+        gpu.set_option(fx.OPT_TRANSLATE, mode)
+        for name, v in ctl.items():
+            gpu.set_controls(prog.reg_index(name), v)
+        x = torch.from_numpy((1.8 * np.random.default_rng(9).random((s, n)) - 0.9).astype(np.float32)).cuda()
+        y = torch.empty_like(x)
+        st = torch.cuda.current_stream().cuda_stream
+        gpu.process_device(x, y, s, st); gpu.process_device(x, y, s, st)
+        gpu.synchronize(st)
+        outs.append((y.cpu().numpy(), gpu.registers(), gpu.counts(), bool(gpu.launch_info().kernel_variant & 128)))
+        gpu.close()
+    assert outs[0][3] is False and outs[1][3] is True
+    assert_bits_equal(outs[0][0], outs[1][0], "outputs")
+    assert_bits_equal(outs[0][1], outs[1][1], "registers")
+    assert_bits_equal(outs[0][2], outs[1][2], "counters")

@@ -1,0 +1,124 @@
+"""The program translator's code generator, checked on the CPU (no GPU needed).
+
+fx8010_translate_source emits the CUDA source the GPU path compiles with NVRTC; the same source builds as plain
+C++ (-DFXT_HOST_CHECK) and is run here against the oracle, bit for bit: outputs, register file, accumulator, LFSR,
+latches, TRAM pointers and contents, executed-instruction counters, runtime flags.  A second set of tests runs NVRTC
+itself (it needs no device) to make sure the source compiles for sm_100a.
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+import progs
+from conftest import assert_bits_equal
+from translate_host import HostTranslated
+
+fx = importlib.import_module("fx8010-emulator-core_b200")
+
+
+@pytest.fixture(scope="module")
+def po():
+    from oracle import pyoracle
+    return pyoracle
+
+
+def check(po, text, n, blocks, rng, channels=1, controls=None, amp=0.9, what="case"):
+    prog = fx.Program(text, channels=channels)
+    assert prog.loaded, prog.errors()
+    img = po.Image(prog.instructions(), prog.registers(), prog.itram_size, prog.xtram_size, prog.controls(), prog.tables())
+    orc = po.Oracle(img, n, channels)
+    ht = HostTranslated(prog, n, channels)
+    for name, vals in (controls or {}).items():
+        idx = prog.reg_index(name)
+        orc.set_register(idx, vals)
+        ht.registers[idx, :] = np.asarray(vals, dtype=np.float32)
+    start = 0
+    for s in blocks:
+        x = (2 * amp * rng.random((channels, s, n)) - amp).astype(np.float32)
+        assert_bits_equal(ht.process(x), orc.process(x), f"{what} outputs of block at {start}")
+        start += s
+    assert_bits_equal(ht.registers, orc.registers, what + " registers")
+    assert_bits_equal(ht.acc, orc.acc, what + " accumulator")
+    assert_bits_equal(ht.lfsr, orc.lfsr, what + " lfsr")
+    assert_bits_equal(ht.out_latch, orc.out_latch, what + " latch")
+    assert_bits_equal(ht.tram_ptrs, orc.tram_ptrs, what + " tram pointers")
+    assert_bits_equal(ht.counts, orc.counts, what + " counters")
+    for which, size in ((0, prog.itram_size), (1, prog.xtram_size)):
+        if size:
+            for i in sorted({0, n - 1}):
+                assert_bits_equal(ht.tram(which, i), orc.tram(which, i), f"{what} tram{which}[{i}]")
+    assert int(ht.flags[0]) == orc.flags, what + " runtime flags"
+    return ht
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_programs(po, seed):
+    rng = np.random.default_rng(1000 + seed)
+    text = progs.random_program(rng, 40 + 7 * seed, channels=1 + seed % 2, xtram=bool(seed % 3 == 0))
+    check(po, text, 5, [23, 9], rng, channels=1 + seed % 2, what=f"random {seed}")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_programs_unsafe(po, seed):
+    rng = np.random.default_rng(2000 + seed)
+    text = progs.random_program(rng, 60, safe=False, wild_tables=True)
+    check(po, text, 4, [17], rng, what=f"unsafe {seed}")
+
+
+def test_cfg5_allops(po):
+    rng = np.random.default_rng(progs.SEED)
+    n = 6
+    ctl = {f"k{i}": rng.random(n).astype(np.float32) for i in range(4)}
+    ht = check(po, progs.cfg5_allops(), n, [12, 5], rng, controls=ctl, what="cfg5")
+    assert "goto L" in ht.src
+
+
+def test_skip_past_the_end_and_negative_count(po):
+    rng = np.random.default_rng(5)
+    text = "\n".join(["static a = 0.25", "static b", "input in_l 0", "output out_l 0",
+                      "macs a, in_l, 0.5, 0.5", "skip ccr, ccr, 2, -3", "macs b, a, 0.5, 0.5", "macs out_l, b, a, 1.0",
+                      "skip ccr, ccr, 2, 7", "macs b, b, 0.25, 0.25", "end"])
+    # the second SKIP would jump past END: END is then not guaranteed, so the translator must decline
+    prog = fx.Program(text)
+    assert prog.loaded
+    src, _ = fx.translate_source(prog)
+    assert src is None
+    text2 = text.replace("skip ccr, ccr, 2, 7", "skip ccr, ccr, 2, 1")
+    check(po, text2, 8, [31], rng, what="negative skip count")
+
+
+def test_skip_count_from_a_written_register_is_declined():
+    text = "\n".join(["static n = 1", "static a", "input in_l 0", "output out_l 0", "macs n, 0, 1, 1", "skip ccr, ccr, 2, n",
+                      "macs a, in_l, 0.5, 0.5", "macs out_l, a, 0, 0", "end"])
+    prog = fx.Program(text)
+    assert prog.loaded
+    assert fx.translate_source(prog)[0] is None
+
+
+def test_two_channels_input_index_quirk(po):
+    rng = np.random.default_rng(9)
+    text = "\n".join(["input in_l 0", "input in_r 1", "output out_l 0", "output out_r 1", "static t",
+                      "macs t, in_l, in_r, 0.5", "skip ccr, ccr, 6, 1", "macs out_l, t, in_r, 0.25", "macs out_r, in_r, in_l, 0.5", "end"])
+    check(po, text, 4, [19], rng, channels=2, what="two channels")
+
+
+def test_noise_macmv_tram(po):
+    rng = np.random.default_rng(11)
+    text = "\n".join(["static noise", "static a", "static d", "static m", "input in_l 0", "output out_l 0", "itramsize 37 ", "xtramsize 50 ",
+                      "macs a, in_l, noise, 0.125", "macmv m, a, in_l, 0.5", "macmv m, m, a, 0.25", "macs a, a, 0, 0",
+                      "idelay write, a, at, 0", "idelay read, d, at, 36", "xdelay write, d, at, 3", "xdelay read, m, at, 40",
+                      "skip ccr, ccr, 2, 1", "macs d, d, m, 0.5", "macs out_l, d, a, 0.5", "end"])
+    check(po, text, 3, [90, 45], rng, what="noise/macmv/tram")
+
+
+@pytest.mark.parametrize("name", ["cfg5", "random"])
+def test_source_compiles_for_sm_100a(name):
+    """NVRTC (no device needed) turns the generated source into an sm_100a CUBIN."""
+    text = progs.cfg5_allops() if name == "cfg5" else progs.random_program(np.random.default_rng(3), 64, xtram=True)
+    prog = fx.Program(text)
+    src, cubin = fx.translate_source(prog, 1, compile_check=True)
+    assert src is not None
+    if cubin == -1:
+        pytest.skip("libnvrtc not loadable here")
+    assert cubin > 1000
