@@ -809,7 +809,7 @@ int plan_launch(fx8010_gpu* h, const float* d_in, const float* d_out, size_t in_
     // (cfg5, K = 2: 64- and 128-thread blocks 120 ms, 32-thread blocks 128 ms — the warps of a block share instruction
     //  and constant fetches — so shrink blocks only until every SM has one)
     while (B > 32 && ((long)((N / K + B - 1) / B) * max_seg < (long)h->num_sms || smem(B, K, chunk) > 80 * 1024)) B >>= 1;
-    if (h->tune_B) B = h->tune_B;
+    if (h->tune_B) B = std::min(h->tune_B, 128);
     while (!fits(B, K) && chunk > 4) chunk >>= 1;
     while (!fits(B, K) && K > 1) K >>= 1;
     while (!fits(B, K) && B > 32) B >>= 1;
@@ -913,7 +913,7 @@ int plan_stateless(fx8010_gpu* h, const float*, const float*, unsigned align, in
     if (h->tune_K && aligned(h->tune_K)) K = h->tune_K;
     // time-split launches: 64-thread blocks with batches of 8 samples (decode amortised over twice the samples at the
     // same shared-memory footprint as 128 x 4; cfg2: 8.7 vs 9.2 us)
-    int B = h->tune_B ? h->tune_B : (serial ? 128 : 64);
+    int B = h->tune_B ? std::min(h->tune_B, 128) : (serial ? 128 : 64);
     while (B > 32 && (N / K + B - 1) / B * B >= 2 * (N / K) && N / K <= B / 2) B >>= 1;      // tiny N: do not launch mostly-idle blocks
     if (serial && !h->tune_B)                // one time segment: only N / K threads — spread them over the SMs
         while (B > 32 && (N / K + B - 1) / B < 2 * h->num_sms) B >>= 1;
@@ -1103,7 +1103,7 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
         return FX8010_OK;
     }
     // Programs of the general interpreter run on their translated kernel once it exists (fx8010_translate.inc).
-    if (!(h->sl_ok && h->use_sl) && !use_short_kernel(h) && !h->trace_mode && tr_ready(h)) {
+    if (!h->stateless && !(h->sl_ok && h->use_sl) && !use_short_kernel(h) && !h->trace_mode && tr_ready(h)) {
         for (int b = 0; b < n_blk; ++b) {
             const int rc = tr_launch(h, ins[b], outs[b], in_cs, out_cs, n_samples, st);
             if (rc) return rc;
@@ -1112,10 +1112,15 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
     }
     const int ns = n_samples;
     const bool fusable = h->sl_ok && h->use_sl && !h->trace_mode && !h->sl_serial && h->use_fuse;
+    // A stateless program runs on its translated streaming kernel once that exists (fx8010_translate.inc): 4 adjacent instances
+    // per thread, so the instance count and every buffer must allow 16-byte accesses.
+    bool tr_sl = h->stateless && !h->trace_mode && h->N % 4 == 0 && (in_cs * 4) % 16 == 0 && (out_cs * 4) % 16 == 0 && ((size_t)ns * h->N * 4) % 16 == 0;
+    for (int b = 0; b < n_blk && tr_sl; ++b) tr_sl = (((uintptr_t)ins[b] | (uintptr_t)outs[b]) & 15u) == 0;
+    tr_sl = tr_sl && tr_ready(h);
     for (int b0 = 0; b0 < n_blk;) {
-        const int nb = fusable ? std::min(n_blk - b0, MAX_FUSED_BLOCKS) : 1;
-        if (h->encode_dirty) { select_tables(h); h->plan_key.ns = -1; }
-        Launch L;
+        const int nb = (fusable || tr_sl) ? std::min(n_blk - b0, MAX_FUSED_BLOCKS) : 1;
+        if (h->encode_dirty && !tr_sl) { select_tables(h); h->plan_key.ns = -1; }
+        Launch L = {};
         // the plan depends on the batch length and on how far the buffers are aligned
         unsigned align = 0;
         bool any_in = false, all_in = true;
@@ -1128,7 +1133,8 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
         const int deep = ((h->sl_ok && h->sl_tram) ? (known_tram_distance(h) > 2 * SL_MAX_M ? 1 : 0) : 0) | (tsplit ? 2 : 0);
         // a launch that may overlap its neighbours (late wait) is planned as half a wave; one that waits at its start fills the SMs
         const bool may_overlap = h->use_pdl && h->stateless && nb == 1 && (h->stream_exclusive || own_prev || b0 > 0);
-        if (h->plan_key.ns == ns && h->plan_key.align == align && h->plan_key.deep == deep && h->plan_key.n_blk == nb && h->plan_key.wave == (int)may_overlap) L = h->plan;
+        if (tr_sl) {}                                              // (its geometry is decided at the launch)
+        else if (h->plan_key.ns == ns && h->plan_key.align == align && h->plan_key.deep == deep && h->plan_key.n_blk == nb && h->plan_key.wave == (int)may_overlap) L = h->plan;
         else {
             L.M = 0;
             const int rc = (h->sl_ok && h->use_sl && !h->trace_mode) ? plan_stateless(h, ins[b0], outs[b0], align, ns, nb, may_overlap, tsplit, L)
@@ -1138,15 +1144,16 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
         }
         // the kernel family that will run this launch (each keeps its own constant-memory copy of the program)
         const Family fam = L.M > 0 ? sl_family(L.K) : ((use_short_kernel(h)) ? FAM_SHORT : FAM_GENERIC);
-        const bool reencode = h->encode_dirty || h->enc_K != L.K || h->enc_B != L.B || h->sl_M != L.M || (L.M == 0 && h->enc_chunk != L.chunk) || h->enc_family != (int)fam;
+        const bool reencode = !tr_sl && (h->encode_dirty || h->enc_K != L.K || h->enc_B != L.B || h->sl_M != L.M || (L.M == 0 && h->enc_chunk != L.chunk) || h->enc_family != (int)fam);
         if (reencode) {
             // the previous upload must have left the pinned buffer before it is rewritten
             FX_CUDA(h, cudaStreamSynchronize(st));
             if (L.M > 0) encode_stateless(h, L.K, L.B, L.M); else encode(h, L.K, L.B, L.chunk);
         }
-        std::lock_guard<std::mutex> lk(g_dev_mutex[h->device]);       // residency check -> launch
+        std::unique_lock<std::mutex> lk(g_dev_mutex[h->device], std::defer_lock);       // residency check -> launch
         bool fresh = false;
-        {
+        if (!tr_sl) {
+            lk.lock();
             const int rc = arena_acquire(h, (int)fam, (L.M > 0 ? 4 : 2) * (h->n_exec + 1), fresh);
             if (rc) return rc;
         }
@@ -1193,7 +1200,11 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
         attrs[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attrs; cfg.numAttrs = h->use_pdl ? 1 : 0;
         const float* in = ins[b0]; float* out = outs[b0];
-        if (L.M > 0) {
+        if (tr_sl) {
+            const int rc = tr_sl_launch(h, ins + b0, outs + b0, nb, in_cs, out_cs, ns, st, late_wait, L);
+            if (rc) return rc;
+            h->info.last_tma = 0;
+        } else if (L.M > 0) {
             SLParams p = {};
             p.gpr = h->d_gpr; p.acc = h->d_acc; p.latch = h->d_latch; p.counts = h->d_counts; p.rt_flags = h->d_flags;
             p.tabs = h->d_tabs; p.load_list = h->d_sl_load; p.wb_list = h->d_sl_wb;
@@ -1267,14 +1278,14 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
             FX_CUDA(h, cudaLaunchKernelEx(&cfg, fn, p));
         }
         bool pairs = false;
-        if (L.M > 0) for (uint8_t f : h->sl_fuse) pairs = pairs || f;
+        if (L.M > 0 && !tr_sl) for (uint8_t f : h->sl_fuse) pairs = pairs || f;
         if (!late_wait) h->chain.clear();          // this launch waited at its start: everything before it is complete
         h->chain.push_back(sp); h->chain_stream = st;
         h->info.kernel_launches++;
         h->info.last_grid = L.grid_x * L.n_seg * (L.M > 0 ? nb : 1); h->info.last_block = L.B * L.P; h->info.last_time_split = L.n_seg;
         h->info.last_smem_bytes = (int)L.smem;
         h->info.last_late_wait = late_wait; h->info.last_fused_blocks = nb;
-        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | ((L.M == 0 && use_short_kernel(h)) ? 32 : 0) | (pairs ? 64 : 0) | (L.K << 8) | (L.M << 16);
+        h->info.kernel_variant = (h->has_skip ? 1 : 0) | (h->has_ext ? 2 : 0) | (h->stateless ? 4 : 0) | (L.M > 0 ? 8 : 0) | ((L.M == 0 && use_short_kernel(h)) ? 32 : 0) | (pairs ? 64 : 0) | (tr_sl ? 128 : 0) | (L.K << 8) | (L.M << 16);
         b0 += nb;
     }
     return FX8010_OK;
@@ -1357,7 +1368,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     if (h->tune_chunk & (h->tune_chunk - 1) || h->tune_chunk > MAX_CHUNK) h->tune_chunk = 0;
     if (h->tune_M != 1 && h->tune_M != 2 && h->tune_M != 4 && h->tune_M != 8 && h->tune_M != 16 && h->tune_M != 32 && h->tune_M != 64) h->tune_M = 0;
     if (h->tune_K != 1 && h->tune_K != 2 && h->tune_K != 4) h->tune_K = 0;
-    if (h->tune_B != 32 && h->tune_B != 64 && h->tune_B != 128) h->tune_B = 0;
+    if (h->tune_B != 32 && h->tune_B != 64 && h->tune_B != 128 && h->tune_B != 256) h->tune_B = 0;
     *out = h;
     return FX8010_OK;
 }
@@ -1990,9 +2001,9 @@ long long fx8010_translate_source(const fx8010_program_image* im, int n_channels
     for (int r = 0; r < im->n_regs; ++r) tmp.reg_value[r] = im->regs[r].init_value;
     tmp.tr_volatile.assign(im->n_regs, 0);
     analyse(&tmp);
-    if (!tr_eligible(&tmp)) return -2;
+    if (!tmp.stateless && !tr_eligible(&tmp)) return -2;
     std::vector<uint8_t> folded;
-    const std::string src = tr_generate(&tmp, folded);
+    const std::string src = tmp.stateless ? tr_generate_sl(&tmp, folded) : tr_generate(&tmp, folded);
     if (buf && cap) { strncpy(buf, src.c_str(), cap - 1); buf[cap - 1] = 0; }
     if (compile_check) {                                     // NVRTC -> sm_100a CUBIN (works without a GPU)
         std::vector<char> cubin; std::string log;

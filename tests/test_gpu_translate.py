@@ -155,3 +155,72 @@ def test_translated_matches_interpreter_device_path(fx, po):
     assert_bits_equal(outs[0][0], outs[1][0], "outputs")
     assert_bits_equal(outs[0][1], outs[1][1], "registers")
     assert_bits_equal(outs[0][2], outs[1][2], "counters")
+
+
+# ---- stateless programs: the translated streaming kernel (fx_translated_sl) ----------------------------------------
+
+@pytest.mark.parametrize("n", [4096, 1000, 332])
+def test_cfg2_translated_streaming(fx, po, n):
+    rng = np.random.default_rng(progs.SEED)
+    vol = rng.random(n).astype(np.float32)
+    st, info = run_translated(fx, po, progs.CFG2_LOG_GAIN, n, [1024, 40, 3], rng, controls={"volume": vol}, amp=0.99, what=f"cfg2 translated n={n}")
+    assert st["state"] == 2, st
+    assert info.kernel_variant & 128 and info.kernel_variant & 4
+
+
+def test_stateless_odd_instance_count_keeps_the_interpreter(fx, po):
+    rng = np.random.default_rng(2)
+    n = 333                                      # not a multiple of 4: no 16-byte accesses
+    vol = rng.random(n).astype(np.float32)
+    st, info = run_translated(fx, po, progs.CFG2_LOG_GAIN, n, [100], rng, controls={"volume": vol}, what="cfg2 n=333")
+    assert not (info.kernel_variant & 128)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "logtube", "two_channels"])
+def test_stateless_programs_translated(fx, po, name):
+    rng = np.random.default_rng(31)
+    n = 512
+    ch = 2 if name == "two_channels" else 1
+    text = {"cfg1": progs.CFG1A_TESTCODE, "logtube": progs.CFG1B_LOGTUBE,
+            "two_channels": "\n".join(["input in_l 0", "input in_r 1", "output out_l 0", "output out_r 1", "static t", "control g = 0.5",
+                                       "macs t, in_l, in_r, g", "log t, t, 7, 0", "macs out_l, t, in_r, 0.25", "macsn out_r, in_r, in_l, g", "end"])}[name]
+    prog = fx.Program(text, channels=ch)
+    ctl = {nm: rng.random(n).astype(np.float32) for nm in prog.controls()}
+    st, info = run_translated(fx, po, text, n, [257, 64, 1], rng, channels=ch, controls=ctl, what=name)
+    assert st["state"] == 2 and (info.kernel_variant & 128), (st, hex(info.kernel_variant))
+
+
+def test_fused_blocks_rotating_buffers_translated(fx, po):
+    """fx8010_gpu_process_blocks on the translated streaming kernel: 7 blocks over 3 rotating buffer pairs in one call, then
+    one block per call with FX8010_OPT_STREAM_EXCLUSIVE (launches overlap through the postponed wait)."""
+    import torch
+    rng = np.random.default_rng(41)
+    n, s = 4096, 256
+    prog, img, orc, gpu = make_pair(fx, po, progs.CFG2_LOG_GAIN, n)
+    try:
+        gpu.set_option(fx.OPT_TRANSLATE, 2)
+        vol = rng.random(n).astype(np.float32)
+        gpu.set_controls(prog.reg_index("volume"), vol); orc.set_register(prog.reg_index("volume"), vol)
+        xs = [(1.98 * rng.random((s, n)) - 0.99).astype(np.float32) for _ in range(3)]
+        d_in = [torch.from_numpy(x).cuda() for x in xs]
+        d_out = [torch.zeros_like(d_in[0]) for _ in range(3)]
+        st = torch.cuda.current_stream().cuda_stream
+        order = [b % 3 for b in range(7)]
+        gpu.process_blocks([d_in[b] for b in order], [d_out[b] for b in order], s, st)
+        gpu.synchronize(st)
+        assert gpu.launch_info().kernel_variant & 128
+        want = {}
+        for b in order:
+            want[b] = orc.process(xs[b].reshape(1, s, n))[0]
+        for b in range(3):
+            assert_bits_equal(d_out[b].cpu().numpy(), want[b], f"fused block buffer {b}")
+        gpu.set_option(fx.OPT_STREAM_EXCLUSIVE, 1)
+        for b in order:
+            gpu.process_device(d_in[b], d_out[b], s, st)
+            want[b] = orc.process(xs[b].reshape(1, s, n))[0]
+        gpu.synchronize(st)
+        for b in range(3):
+            assert_bits_equal(d_out[b].cpu().numpy(), want[b], f"per-call block buffer {b}")
+        compare_state(gpu, orc, img, "fused translated")
+    finally:
+        gpu.close()

@@ -47,7 +47,8 @@ def check(po, text, n, blocks, rng, channels=1, controls=None, amp=0.9, what="ca
     for which, size in ((0, prog.itram_size), (1, prog.xtram_size)):
         if size:
             for i in sorted({0, n - 1}):
-                assert_bits_equal(ht.tram(which, i), orc.tram(which, i), f"{what} tram{which}[{i}]")
+                if orc.tram(which, i).size:          # (a declared size without any TRAM instruction allocates nothing)
+                    assert_bits_equal(ht.tram(which, i), orc.tram(which, i), f"{what} tram{which}[{i}]")
     assert int(ht.flags[0]) == orc.flags, what + " runtime flags"
     return ht
 
@@ -110,6 +111,47 @@ def test_noise_macmv_tram(po):
                       "idelay write, a, at, 0", "idelay read, d, at, 36", "xdelay write, d, at, 3", "xdelay read, m, at, 40",
                       "skip ccr, ccr, 2, 1", "macs d, d, m, 0.5", "macs out_l, d, a, 0.5", "end"])
     check(po, text, 3, [90, 45], rng, what="noise/macmv/tram")
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "logtube", "random_stateless"])
+def test_stateless_programs_streaming_kernel(po, name):
+    """Stateless programs translate into the streaming kernel (fx_translated_sl): blocks x time segments x instance groups."""
+    rng = np.random.default_rng(21)
+    n = 12
+    if name == "random_stateless":
+        text = progs.random_program(rng, 24, skip=False, tram=False, noise=False, ops=progs.SAT_OPS + progs.TABLE_OPS + ["limit", "tstneg", "andxor"])
+        text = stateless_variant(text)
+    else:
+        text = {"cfg1": progs.CFG1A_TESTCODE, "cfg2": progs.CFG2_LOG_GAIN, "logtube": progs.CFG1B_LOGTUBE}[name]
+    prog = fx.Program(text)
+    assert prog.loaded, prog.errors()
+    ctl = {nm: rng.random(n).astype(np.float32) for nm in prog.controls()}
+    ht = check(po, text, n, [37, 8, 1], rng, controls=ctl, what=name)
+    assert "fx_translated_sl" in ht.src
+    # several blocks in one launch
+    img = po.Image(prog.instructions(), prog.registers(), prog.itram_size, prog.xtram_size, prog.controls(), prog.tables())
+    orc = po.Oracle(img, n, 1)
+    ht = HostTranslated(prog, n, 1)
+    for nm, v in ctl.items():
+        orc.set_register(prog.reg_index(nm), v); ht.registers[prog.reg_index(nm), :] = v
+    xs = [(1.8 * rng.random((1, 21, n)) - 0.9).astype(np.float32) for _ in range(3)]
+    ys = ht.process_blocks(xs, 21, seg_len=4)
+    for b in range(3):
+        assert_bits_equal(ys[b], orc.process(xs[b]), f"{name} fused block {b}")
+    assert_bits_equal(ht.registers, orc.registers, name + " registers after fused blocks")
+    assert_bits_equal(ht.acc, orc.acc, name + " accumulator after fused blocks")
+    assert_bits_equal(ht.out_latch, orc.out_latch, name + " latch after fused blocks")
+    assert_bits_equal(ht.counts, orc.counts, name + " counters after fused blocks")
+
+
+def stateless_variant(text: str) -> str:
+    """Keeps a random program only if the product's analysis calls it stateless; otherwise falls back to a fixed one."""
+    prog = fx.Program(text)
+    src, _ = fx.translate_source(prog)
+    if src is not None and "fx_translated_sl" in src:
+        return text
+    return "\n".join(["static a", "static b", "control g = 0.5", "input in_l 0", "output out_l 0", "macs a, 0, in_l, g", "log b, a, 5, 0",
+                      "limit a, b, a, 0.25", "exp b, a, 3, 0", "macsn out_l, b, a, g", "end"])
 
 
 @pytest.mark.parametrize("name", ["cfg5", "random"])

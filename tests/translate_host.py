@@ -44,10 +44,18 @@ def compile_source(src: str) -> C.CDLL:
     open(cu, "w").write(src)
     subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-DFXT_HOST_CHECK", "-o", so, cu], check=True)
     lib = C.CDLL(so)
-    lib.fx_translated_host.restype = None
-    lib.fx_translated_host.argtypes = [C.c_int] + [C.c_void_p] * 12 + [C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]
+    if hasattr(lib, "fx_translated_host"):
+        lib.fx_translated_host.restype = None
+        lib.fx_translated_host.argtypes = [C.c_int] + [C.c_void_p] * 12 + [C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]
+    else:                       # stateless program: the streaming kernel, one call per (thread, blockIdx.y)
+        lib.fx_translated_sl_host.restype = None
+        lib.fx_translated_sl_host.argtypes = [C.c_int, C.c_int, FxtIo] + [C.c_void_p] * 6 + [C.c_size_t, C.c_size_t] + [C.c_int] * 6
     _cache[key] = lib
     return lib
+
+
+class FxtIo(C.Structure):
+    _fields_ = [("inp", C.c_void_p * 32), ("out", C.c_void_p * 32)]
 
 
 class HostTranslated:
@@ -81,6 +89,8 @@ class HostTranslated:
             s = x.shape[1]
         out = np.zeros((self.c, s, self.n), np.float32)
         cs = s * self.n
+        if hasattr(self.lib, "fx_translated_sl_host"):
+            return self.process_blocks([x], s)[0]
         for i in range(self.n):
             self.lib.fx_translated_host(i, self.registers.ctypes.data, self.acc.ctypes.data, self.lfsr.ctypes.data, self.out_latch.ctypes.data,
                                         self.tram_ptrs.ctypes.data, self.itram.ctypes.data, self.xtram.ctypes.data, self.counts.ctypes.data,
@@ -90,3 +100,23 @@ class HostTranslated:
 
     def tram(self, which: int, instance: int):
         return (self.itram if which == 0 else self.xtram)[: (self.isz if which == 0 else self.xsz), instance].copy()
+
+    def process_blocks(self, xs, s, seg_len=8):
+        """Stateless programs: consecutive blocks in ONE emulated launch (block x time segment x instance group work items)."""
+        assert self.n % 4 == 0
+        nb = len(xs)
+        xs = [None if x is None else np.ascontiguousarray(x, dtype=np.float32).reshape(self.c, s, self.n) for x in xs]
+        outs = [np.zeros((self.c, s, self.n), np.float32) for _ in xs]
+        io = FxtIo()
+        for b in range(nb):
+            io.inp[b] = xs[b].ctypes.data if xs[b] is not None else None
+            io.out[b] = outs[b].ctypes.data
+        cs = s * self.n
+        n_seg = -(-s // seg_len)
+        order = [(tx, by) for by in range(n_seg * nb) for tx in range(self.n // 4 + 1)]     # one thread past the end: the bounds check
+        rng = np.random.default_rng(0)
+        rng.shuffle(order)                                                                 # work items are independent: any order
+        for tx, by in order:
+            self.lib.fx_translated_sl_host(int(tx), int(by), io, self.registers.ctypes.data, self.acc.ctypes.data, self.out_latch.ctypes.data,
+                                           self.counts.ctypes.data, self.flags.ctypes.data, self.tabs.ctypes.data, cs, cs, s, seg_len, n_seg, nb, self.n, 0)
+        return outs
