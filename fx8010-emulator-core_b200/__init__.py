@@ -113,7 +113,7 @@ GPU_SYMBOLS = {
     "fx8010_gpu_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fx8010_gpu_get_launch_info": (C.c_int, [C.c_void_p, C.POINTER(CLaunchInfo)]),
     "fx8010_gpu_translate_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
-    "fx8010_translate_source": (C.c_longlong, [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_int)]),
+    "fx8010_translate_source": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_int)]),
 }
 
 MULTI_SYMBOLS = {
@@ -352,16 +352,16 @@ class Program:
         return self.L.fx8010_host_instruction_counter_total(self.h)
 
 
-def translate_source(prog: "Program", channels: int = 1, compile_check: bool = False):
+def translate_source(prog: "Program", channels: int = 1, compile_check: bool = False, instances: int = 1):
     """CUDA source the translator generates for a decoded program (no device needed).  Returns (source or None when the
     program is not eligible, CUBIN size when compile_check else None)."""
     L = gpu_lib()
-    n = L.fx8010_translate_source(prog.image_ptr(), channels, None, 0, 0, None)
+    n = L.fx8010_translate_source(prog.image_ptr(), instances, channels, None, 0, 0, None)
     if n < 0:
         return None, None
     buf = C.create_string_buffer(int(n) + 1)
     cub = C.c_int(0)
-    L.fx8010_translate_source(prog.image_ptr(), channels, buf, int(n) + 1, 1 if compile_check else 0, C.byref(cub))
+    L.fx8010_translate_source(prog.image_ptr(), instances, channels, buf, int(n) + 1, 1 if compile_check else 0, C.byref(cub))
     return buf.value.decode(), (cub.value if compile_check else None)
 
 

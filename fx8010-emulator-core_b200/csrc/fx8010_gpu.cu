@@ -20,6 +20,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <regex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -158,10 +159,13 @@ struct fx8010_gpu {
     // tuning overrides (0 = heuristic)
     int tune_K = 0, tune_B = 0, tune_seg = 0, tune_sub = 0, tune_P = 0, use_split = 1;
     // program translator (fx8010_translate.inc)
+    int tr_recurrences = 0;                      // FX8010_TR_RECUR: self-recurrence programs of the instruction-major kernel take the translated serial kernel too
     int use_translate = 1;                       // FX8010_OPT_TRANSLATE: 0 never, 1 background compile + switch when ready, 2 compile before the first launch
     int tr_state = 0;                            // 0 not looked at, 1 compiling, 2 kernel loaded, -1 not eligible / failed (tr_error says why)
     void* tr_fn = nullptr;                       // CUfunction of the translated kernel
     int tr_regs = 0, tr_local = 0;               // its registers per thread / local-memory bytes (spills)
+    int tr_lanes = 1;                            // (serial kernel) instances per thread
+    int tr_ring_floats = 0;                      // (serial kernel) floats of the shared-memory input ring per thread
     std::shared_ptr<void> tr_job;                // the running compilation
     std::string tr_error;
     std::vector<uint8_t> tr_folded;              // per register: its value is an immediate of the translated kernel ...
@@ -1103,7 +1107,8 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
         return FX8010_OK;
     }
     // Programs of the general interpreter run on their translated kernel once it exists (fx8010_translate.inc).
-    if (!h->stateless && !(h->sl_ok && h->use_sl) && !use_short_kernel(h) && !h->trace_mode && tr_ready(h)) {
+    const bool tr_recur = h->tr_recurrences && h->sl_ok && h->sl_serial && !h->sl_tram;      // self recurrences (cfg4): see FX8010_TR_RECUR
+    if (!h->stateless && (tr_recur || (!(h->sl_ok && h->use_sl) && !use_short_kernel(h))) && !h->trace_mode && tr_ready(h) && tr_aligned(h, ins, outs, n_blk, in_cs, out_cs, n_samples)) {
         for (int b = 0; b < n_blk; ++b) {
             const int rc = tr_launch(h, ins[b], outs[b], in_cs, out_cs, n_samples, st);
             if (rc) return rc;
@@ -1361,6 +1366,7 @@ int fx8010_gpu_create(int device, int n_instances, int n_channels, fx8010_gpu** 
     if (getenv("FX8010_NO_CARRY")) h->use_carry = 0;
     if (getenv("FX8010_NO_TRAM_IM")) h->use_tram_im = 0;
     if (getenv("FX8010_NO_SPLIT")) h->use_split = 0;
+    if (getenv("FX8010_TR_RECUR")) h->tr_recurrences = atoi(getenv("FX8010_TR_RECUR"));
     if (getenv("FX8010_TRANSLATE")) h->use_translate = std::min(2, std::max(0, atoi(getenv("FX8010_TRANSLATE"))));
     h->tune_P = env_int("FX8010_TUNE_P");
     h->tune_M = env_int("FX8010_TUNE_M");
@@ -1985,10 +1991,10 @@ int fx8010_gpu_translate_status(fx8010_gpu* h, int* state, int* regs_per_thread,
 }
 
 // Needs no device: analyses the image as load_program would and returns the CUDA source of its translated kernel.
-long long fx8010_translate_source(const fx8010_program_image* im, int n_channels, char* buf, size_t cap, int compile_check, int* regs_or_status) {
-    if (!im || !im->instrs || !im->regs || im->n_instrs <= 0 || im->n_regs <= 0 || n_channels <= 0) return -1;
+long long fx8010_translate_source(const fx8010_program_image* im, int n_instances, int n_channels, char* buf, size_t cap, int compile_check, int* regs_or_status) {
+    if (!im || !im->instrs || !im->regs || im->n_instrs <= 0 || im->n_regs <= 0 || n_channels <= 0 || n_instances <= 0) return -1;
     fx8010_gpu tmp;
-    tmp.C = n_channels; tmp.N = 1;
+    tmp.C = n_channels; tmp.N = n_instances;
     tmp.instrs.assign(im->instrs, im->instrs + im->n_instrs);
     tmp.regs.assign(im->regs, im->regs + im->n_regs);
     for (const fx8010_instr& in : tmp.instrs)

@@ -283,11 +283,11 @@ FX8010_API int fx8010_gpu_trace(fx8010_gpu* h, const float* in, float* out, int 
  * describe the loaded kernel.  Any pointer may be NULL. */
 FX8010_API int fx8010_gpu_translate_status(fx8010_gpu* h, int* state, int* regs_per_thread, int* local_bytes,
                                            char* message, size_t message_cap);
-/* The CUDA source the translator generates for an image (no device needed; a test and inspection aid — the generated
+/* The CUDA source the translator generates for an image on n_instances instances (no device needed; a test and inspection aid — the generated
  * source also compiles as plain C++ with -DFXT_HOST_CHECK, which is how tests/test_translate.py checks it on the CPU).
  * Returns the source length (copied, truncated, into buf when given), -1 for a bad image, -2 when the program is not
  * eligible.  compile_check != 0 also runs NVRTC for sm_100a and stores the CUBIN size (or -1) in *cubin_bytes. */
-FX8010_API long long fx8010_translate_source(const fx8010_program_image* image, int n_channels, char* buf, size_t cap,
+FX8010_API long long fx8010_translate_source(const fx8010_program_image* image, int n_instances, int n_channels, char* buf, size_t cap,
                                              int compile_check, int* cubin_bytes);
 
 /* Text of the last error on this handle (or of the last failed create when h == NULL). */

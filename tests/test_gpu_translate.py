@@ -224,3 +224,27 @@ def test_fused_blocks_rotating_buffers_translated(fx, po):
         compare_state(gpu, orc, img, "fused translated")
     finally:
         gpu.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_skip_free_programs_four_instances_per_thread(fx, po, seed, monkeypatch):
+    """SKIP-free programs with carried state (noise, MACMV, TRAM, cross-instruction recurrences): 4 / 2 / 1 instances per thread
+    (16- / 8- / 4-byte cp.async input ring)."""
+    monkeypatch.setenv("FX8010_TR_K", ["4", "2", "1", "4"][seed % 4])
+    rng = np.random.default_rng(5000 + seed)
+    ch = 1 + seed % 2
+    text = progs.random_program(rng, 28 + 11 * seed, channels=ch, skip=False, xtram=bool(seed % 2))
+    n = 256 + 64 * seed
+    st, info = run_translated(fx, po, text, n, [70, 33, 1], rng, channels=ch, what=f"translated K=4 random {seed}")
+    assert st["state"] == 2, st
+    assert info.kernel_variant & 128
+    assert (info.kernel_variant >> 8) & 0xff == [4, 2, 1, 4][seed % 4]
+
+
+def test_cfg4_translated_serial_kernel(fx, po, monkeypatch):
+    monkeypatch.setenv("FX8010_TR_RECUR", "1")
+    rng = np.random.default_rng(51)
+    n = 2048
+    ctl = {"filter_cutoff": (0.001 + 0.998 * np.arange(n) / (n - 1)).astype(np.float32)}
+    st, info = run_translated(fx, po, progs.CFG4_ONEPOLE, n, [300, 100, 37], rng, controls=ctl, amp=0.99, what="cfg4 translated")
+    assert st["state"] == 2 and (info.kernel_variant & 128), (st, hex(info.kernel_variant))

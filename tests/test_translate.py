@@ -60,6 +60,26 @@ def test_random_programs(po, seed):
     check(po, text, 5, [23, 9], rng, channels=1 + seed % 2, what=f"random {seed}")
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_random_programs_four_instances_per_thread(po, seed, monkeypatch):
+    """SKIP-free programs, several instances per thread in the serial kernel (the default above ~38 000 instances is 2; FX8010_TR_K forces it)."""
+    monkeypatch.setenv("FX8010_TR_K", "4" if seed % 3 else "2")
+    rng = np.random.default_rng(1500 + seed)
+    ch = 1 + seed % 2
+    text = progs.random_program(rng, 30 + 5 * seed, channels=ch, skip=False, xtram=bool(seed % 2))
+    ht = check(po, text, 8, [19, 6, 1], rng, channels=ch, what=f"random K=4 {seed}")
+    assert ("#define FXT_K 4" in ht.src or "#define FXT_K 2" in ht.src) and "fx_translated_host" in ht.src
+
+
+def test_cfg4_onepole_four_instances_per_thread(po, monkeypatch):
+    monkeypatch.setenv("FX8010_TR_K", "4")
+    rng = np.random.default_rng(17)
+    n = 8
+    ctl = {"filter_cutoff": (0.001 + 0.998 * np.arange(n) / (n - 1)).astype(np.float32)}
+    ht = check(po, progs.CFG4_ONEPOLE, n, [50, 33], rng, controls=ctl, what="cfg4")
+    assert "#define FXT_K 4" in ht.src
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_random_programs_unsafe(po, seed):
     rng = np.random.default_rng(2000 + seed)

@@ -61,7 +61,7 @@ class FxtIo(C.Structure):
 class HostTranslated:
     def __init__(self, prog, n: int, channels: int = 1):
         fx = importlib.import_module(PKG)
-        src, _ = fx.translate_source(prog, channels)
+        src, _ = fx.translate_source(prog, channels, instances=n)
         if src is None:
             raise ValueError("program is not eligible for translation")
         self.src = src
@@ -91,7 +91,9 @@ class HostTranslated:
         cs = s * self.n
         if hasattr(self.lib, "fx_translated_sl_host"):
             return self.process_blocks([x], s)[0]
-        for i in range(self.n):
+        import re
+        lanes = int(re.search(r"#define FXT_K (\d+)", self.src).group(1))
+        for i in range(-(-self.n // lanes) + 1):            # one thread past the end: the bounds check
             self.lib.fx_translated_host(i, self.registers.ctypes.data, self.acc.ctypes.data, self.lfsr.ctypes.data, self.out_latch.ctypes.data,
                                         self.tram_ptrs.ctypes.data, self.itram.ctypes.data, self.xtram.ctypes.data, self.counts.ctypes.data,
                                         self.flags.ctypes.data, self.tabs.ctypes.data, x.ctypes.data if x is not None else None, out.ctypes.data,
