@@ -244,8 +244,11 @@ def oracle_blocks(text: str, prog, idx, controls: dict, x_blocks: list):
 class Workload:
     """One BASELINE config on this rank: handle, controls, rotating device buffers; times blocks of 1 024 samples."""
 
-    def __init__(self, fx, torch, cfg: str, n_inst: int, local_rank: int, rank: int, itram: int = 1000):
+    def __init__(self, fx, torch, cfg: str, n_inst: int, local_rank: int, rank: int, itram: int = 1000, translate: int | None = None, share=None):
         self.fx, self.torch, self.cfg, self.n = fx, torch, cfg, n_inst
+        # FX8010_OPT_TRANSLATE for this workload's handles: 2 = the translated kernel, compiled before the first launch (what a long-running
+        # host gets from the default background mode after the first second); 0 = the interpreter kernels (FX8010_BENCH_TRANSLATE overrides)
+        self.translate = int(os.environ.get("FX8010_BENCH_TRANSLATE", "2")) if translate is None else translate
         self.text, _, self.bytes_per, self.label = workload(cfg)
         if cfg == "cfg3":
             self.text = progs.cfg3_delay(itram)
@@ -262,8 +265,11 @@ class Workload:
             self.host_in = [progs.impulse_noise(n_inst, BLOCK, rng) for _ in range(2)]
         else:
             self.host_in = [progs.sine_bank(n_inst, BLOCK, rng, start=b * BLOCK, amp_lo=amp[0], amp_hi=amp[1]) for b in range(2)]
-        self.d_in = [torch.from_numpy(self.host_in[b % 2]).cuda() for b in range(self.n_bufs)]
-        self.d_out = [torch.empty_like(self.d_in[0]) for _ in range(self.n_bufs)]
+        if share is not None:
+            self.d_in, self.d_out = share.d_in, share.d_out
+        else:
+            self.d_in = [torch.from_numpy(self.host_in[b % 2]).cuda() for b in range(self.n_bufs)]
+            self.d_out = [torch.empty_like(self.d_in[0]) for _ in range(self.n_bufs)]
         self.stream = torch.cuda.Stream()
         self.st = self.stream.cuda_stream
         self.gpu = self.new_handle()
@@ -271,8 +277,7 @@ class Workload:
     def new_handle(self):
         g = self.fx.Gpu(self.n, 1, self.local_rank)
         g.load_program(self.prog)
-        # general-interpreter programs (cfg5): translated kernel, compiled before the first launch (FX8010_BENCH_TRANSLATE=0: the interpreter)
-        g.set_option(self.fx.OPT_TRANSLATE, int(os.environ.get("FX8010_BENCH_TRANSLATE", "2")))
+        g.set_option(self.fx.OPT_TRANSLATE, self.translate)
         for name, v in self.controls.items():
             g.set_controls(self.prog.reg_index(name), v)
         return g
@@ -388,6 +393,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; the median is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-interpreter-leg", action="store_true", help="skip timing the same steps on the interpreter kernels")
     ap.add_argument("--no-sharded", action="store_true", help="skip the cfg4 / cfg5 records of the scaling line")
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
@@ -489,6 +495,17 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     info = W.gpu.launch_info()
     translated = W.gpu.translate_status()
+    # the same steps on the interpreter kernels (FX8010_OPT_TRANSLATE = 0): the number before translation, for comparison
+    interp = None
+    if W.translate and (info.kernel_variant & 128) and not args.no_interpreter_leg:
+        Wi = Workload(fx, torch, args.config, n_inst, local_rank, rank, args.itram, translate=0, share=W)
+        mi_all, li = Wi.timed(args.steps, args.warmup, 3, barrier)
+        mi = statistics.median([max_over_ranks(v) for v in mi_all])
+        ii = Wi.gpu.launch_info()
+        interp = {"what": "the same timed call with FX8010_OPT_TRANSLATE = 0 (interpreter kernels only)", "ms_per_step": mi / args.steps,
+                  "hbm_frac": bytes_per * n_inst * BLOCK * args.steps / (mi * 1e-3) / 1e9 / peak, "gpu_launches": li,
+                  "kernel_variant": hex(ii.kernel_variant)}
+        Wi.close()
     kernel_cfg = {"grid": info.last_grid, "block": info.last_block, "time_split": info.last_time_split, "blocks_per_launch": info.last_fused_blocks,
                   "smem_bytes": info.last_smem_bytes, "instances_per_thread": (info.kernel_variant >> 8) & 0xff, "samples_per_batch": info.kernel_variant >> 16,
                   "translated_kernel": bool(info.kernel_variant & 128)}
@@ -590,7 +607,8 @@ def main():
                        "kernel": kernel_cfg},
             "timed_regions_ms": ms_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.config), "peak_source": peak_src,
+                         "traffic": (ncu_traffic(args.config) or 0) * args.steps / max(1, launches) or None, "peak_source": peak_src,
+                         "traffic_source": "profiles/traffic.json: dram__bytes_read + dram__bytes_write per block from the committed ncu --set full capture, x blocks per launch",
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": 1e3 * launch_ms,
                          "blocks_per_launch": args.steps / max(1, launches)},
             "per_call": {"what": "the same steps as one fx8010_gpu_process_batch call per step from the Python loop",
@@ -598,11 +616,12 @@ def main():
                          "ms_per_step_stream_exclusive": per_call_excl_ms,
                          "hbm_frac_stream_exclusive": bytes_per * n_inst * BLOCK / (per_call_excl_ms * 1e-3) / 1e9 / peak,
                          "isolated_launch_us": isolated_us},
-            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "parity": parity}
+            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "parity": parity,
+            "translator": {"status": translated, "interpreter_kernels": interp,
+                           "what": "FX8010_OPT_TRANSLATE: the loaded DSP program compiled (NVRTC, sm_100a) into one straight-line kernel built from the same "
+                                   "hand-written arithmetic helpers as the interpreter kernels; bit-identical results (parity object above)"}}
     if sharded:
         line["sharded"] = sharded
-    if args.config == "cfg5":
-        line["translated"] = translated
     if args.config == "cfg5":        # compute-bound program: the arithmetic roofline of SURVEY.md §8d beside the HBM one
         line["compute_roofline"] = compute_roofline(text, instr_per_step / world, n_inst, 1e-3 * ms / args.steps,
                                                     (clocks or {}).get("sm_mhz"), bytes_per, peak)

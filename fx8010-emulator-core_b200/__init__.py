@@ -129,6 +129,7 @@ MULTI_SYMBOLS = {
     "fx8010_multi_process_batch_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fx8010_multi_process_batch_host_broadcast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "fx8010_multi_synchronize": (C.c_int, [C.c_void_p]),
+    "fx8010_multi_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "fx8010_multi_get_instruction_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
     "fx8010_multi_get_registers": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fx8010_multi_get_runtime_flags": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), C.c_int]),
@@ -626,6 +627,9 @@ class MultiGpu:
 
     def synchronize(self):
         self._check(self.L.fx8010_multi_synchronize(self.h))
+
+    def set_option(self, option: int, value: int):
+        self._check(self.L.fx8010_multi_set_option(self.h, option, value))
 
     def registers(self) -> np.ndarray:
         out = np.zeros((self.n_regs, self.n), dtype=np.float32)

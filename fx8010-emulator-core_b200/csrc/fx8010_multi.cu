@@ -172,6 +172,11 @@ int fx8010_multi_process_batch_host_broadcast(fx8010_multi* m, const float* in, 
     return run_all(m, [=](Shard& s) { return fx8010_gpu_process_batch_host_broadcast(s.h, in, out + s.lo, n_samples, N, wait); });
 }
 
+int fx8010_multi_set_option(fx8010_multi* m, int option, int value) {
+    if (!m) return FX8010_ERR_ARG;
+    return run_all(m, [option, value](Shard& s) { return fx8010_gpu_set_option(s.h, option, value); });
+}
+
 int fx8010_multi_synchronize(fx8010_multi* m) {
     if (!m) return FX8010_ERR_ARG;
     return run_all(m, [](Shard& s) { return fx8010_gpu_synchronize(s.h, nullptr); });

@@ -51,6 +51,8 @@ FX8010_API int fx8010_multi_process_batch_host_async(fx8010_multi* m, const floa
 /* One input signal for all instances: `in` is [n_channels][n_samples] (fx8010_gpu_process_batch_host_broadcast per shard). */
 FX8010_API int fx8010_multi_process_batch_host_broadcast(fx8010_multi* m, const float* in, float* out, int n_samples, int wait);
 FX8010_API int fx8010_multi_synchronize(fx8010_multi* m);
+/* fx8010_gpu_set_option on every shard (FX8010_OPT_STREAM_EXCLUSIVE, FX8010_OPT_TRANSLATE). */
+FX8010_API int fx8010_multi_set_option(fx8010_multi* m, int option, int value);
 
 /* Executed instructions summed over all instances (getInstructionCounter, source/FX8010.cpp:986-989). */
 FX8010_API int fx8010_multi_get_instruction_count(fx8010_multi* m, unsigned long long* total);
