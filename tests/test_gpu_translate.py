@@ -248,3 +248,13 @@ def test_cfg4_translated_serial_kernel(fx, po, monkeypatch):
     ctl = {"filter_cutoff": (0.001 + 0.998 * np.arange(n) / (n - 1)).astype(np.float32)}
     st, info = run_translated(fx, po, progs.CFG4_ONEPOLE, n, [300, 100, 37], rng, controls=ctl, amp=0.99, what="cfg4 translated")
     assert st["state"] == 2 and (info.kernel_variant & 128), (st, hex(info.kernel_variant))
+
+
+def test_if_converted_skips(fx, po, monkeypatch):
+    """Developer switch FX8010_TR_IFCONV=1: SKIPs over pure register instructions as predicates instead of branches."""
+    monkeypatch.setenv("FX8010_TR_IFCONV", "1")
+    rng = np.random.default_rng(61)
+    n = 512
+    ctl = {f"k{i}": rng.random(n).astype(np.float32) for i in range(4)}
+    st, info = run_translated(fx, po, progs.cfg5_allops(n_instr=160), n, [48, 17], rng, controls=ctl, what="if-converted cfg5-like")
+    assert st["state"] == 2 and (info.kernel_variant & 128)

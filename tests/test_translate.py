@@ -92,7 +92,7 @@ def test_cfg5_allops(po):
     n = 6
     ctl = {f"k{i}": rng.random(n).astype(np.float32) for i in range(4)}
     ht = check(po, progs.cfg5_allops(), n, [12, 5], rng, controls=ctl, what="cfg5")
-    assert "goto L" in ht.src
+    assert "goto L" in ht.src or "bool sk" in ht.src
 
 
 def test_skip_past_the_end_and_negative_count(po):
@@ -184,3 +184,14 @@ def test_source_compiles_for_sm_100a(name):
     if cubin == -1:
         pytest.skip("libnvrtc not loadable here")
     assert cubin > 1000
+
+
+def test_branch_free_table_index_matches_the_reference_rule(tmp_path):
+    """fxt_table_index (no branch, U6 clamp by clamping x) against the branchy rule of the interpreter kernels / the oracle, over every
+    5th binary32 bit pattern (tests/table_index_check.c; `table_index_check 1` sweeps all 2^32 and was run once: 0 mismatches)."""
+    import os, subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "table_index_check")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-o", exe, os.path.join(here, "table_index_check.c"), "-lm"], check=True)
+    r = subprocess.run([exe, "5"], capture_output=True, text=True)
+    assert r.returncode == 0 and "mismatches: 0" in r.stdout, r.stdout
