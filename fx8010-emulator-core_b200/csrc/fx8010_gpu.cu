@@ -1107,7 +1107,8 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
         return FX8010_OK;
     }
     // Programs of the general interpreter run on their translated kernel once it exists (fx8010_translate.inc).
-    const bool tr_recur = h->tr_recurrences && h->sl_ok && h->sl_serial && !h->sl_tram;      // self recurrences (cfg4): see FX8010_TR_RECUR
+    // FX8010_TR_RECUR (developer switch): bit 0 = self recurrences (cfg4), bit 1 = delay lines (cfg3) take the translated serial kernel
+    const bool tr_recur = h->sl_ok && h->sl_serial && (((h->tr_recurrences & 1) && !h->sl_tram) || ((h->tr_recurrences & 2) && h->sl_tram));
     if (!h->stateless && (tr_recur || (!(h->sl_ok && h->use_sl) && !use_short_kernel(h))) && !h->trace_mode && tr_ready(h) && tr_aligned(h, ins, outs, n_blk, in_cs, out_cs, n_samples)) {
         for (int b = 0; b < n_blk; ++b) {
             const int rc = tr_launch(h, ins[b], outs[b], in_cs, out_cs, n_samples, st);

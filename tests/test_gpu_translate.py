@@ -258,3 +258,61 @@ def test_if_converted_skips(fx, po, monkeypatch):
     ctl = {f"k{i}": rng.random(n).astype(np.float32) for i in range(4)}
     st, info = run_translated(fx, po, progs.cfg5_allops(n_instr=160), n, [48, 17], rng, controls=ctl, what="if-converted cfg5-like")
     assert st["state"] == 2 and (info.kernel_variant & 128)
+
+
+# ---- TRAM READ streams of the translated serial kernel (prefetched through the cp.async ring when the delay allows) ----------
+
+from test_gpu_parity import TRAM_CASES, _tram_prog
+
+
+@pytest.mark.parametrize("name", sorted(TRAM_CASES))
+@pytest.mark.parametrize("ring", ["32", "8"])
+def test_tram_streams_translated(fx, po, name, ring, monkeypatch):
+    """The delay-line programs of test_tram_instruction_major on the translated serial kernel (FX8010_TR_RECUR=3 routes them there):
+    delays shorter and longer than the prefetch depth, write-before-read taps, offsets, per-instance offsets, both rings."""
+    monkeypatch.setenv("FX8010_TR_RECUR", "3")
+    monkeypatch.setenv("FX8010_TR_RING", ring)
+    rng = np.random.default_rng(31)
+    n = 136
+    text = _tram_prog(**TRAM_CASES[name])
+    ctl = {"dly": rng.integers(70, 390, n).astype(np.float32)} if name == "ctl_off" else None
+    prog, img, orc, gpu = make_pair(fx, po, text, n)
+    try:
+        gpu.set_option(fx.OPT_TRANSLATE, 2)
+        for nm, v in (ctl or {}).items():
+            gpu.set_controls(prog.reg_index(nm), v); orc.set_register(prog.reg_index(nm), v)
+        x = progs.impulse_noise(n, 700, rng)
+        start = 0
+        for k in [1, 150, 33, 64, 2, 450]:
+            xb = x[start:start + k].reshape(1, k, n)
+            assert_bits_equal(gpu.process_host(xb), orc.process(xb), f"tram {name} block at {start}")
+            start += k
+        compare_state(gpu, orc, img, f"tram {name}", (0, n // 2, n - 1))
+        assert gpu.launch_info().kernel_variant & 128, gpu.translate_status()
+    finally:
+        gpu.close()
+
+
+def test_tram_streams_per_instance_pointers(fx, po, monkeypatch):
+    """Pointers that differ per instance (set through fx8010_gpu_set_scalars): some threads of a warp can prefetch, others cannot."""
+    monkeypatch.setenv("FX8010_TR_RECUR", "3")
+    rng = np.random.default_rng(77)
+    n, size = 96, 120
+    text = _tram_prog(size=size, order="wr", roff="0", woff="0")
+    prog, img, orc, gpu = make_pair(fx, po, text, n)
+    try:
+        gpu.set_option(fx.OPT_TRANSLATE, 2)
+        acc, lfsr, latch, ptrs = gpu.scalars()
+        ptrs = ptrs.copy()
+        ptrs[0] = rng.integers(0, size, n)        # iw
+        ptrs[1] = rng.integers(0, size, n)        # ir: read-after-write distances from 0 to size - 1 across the instances
+        gpu.set_scalars(ptrs=ptrs)
+        orc.tram_ptrs[:] = ptrs
+        x = progs.impulse_noise(n, 400, rng)
+        for a, k in ((0, 130), (130, 270)):
+            xb = x[a:a + k].reshape(1, k, n)
+            assert_bits_equal(gpu.process_host(xb), orc.process(xb), f"per-instance pointers, block at {a}")
+        compare_state(gpu, orc, img, "per-instance pointers", tuple(range(0, n, 7)))
+        assert gpu.launch_info().kernel_variant & 128
+    finally:
+        gpu.close()
