@@ -163,6 +163,7 @@ struct fx8010_gpu {
     int use_translate = 1;                       // FX8010_OPT_TRANSLATE: 0 never, 1 background compile + switch when ready, 2 compile before the first launch
     int tr_state = 0;                            // 0 not looked at, 1 compiling, 2 kernel loaded, -1 not eligible / failed (tr_error says why)
     void* tr_fn = nullptr;                       // CUfunction of the translated kernel
+    unsigned long long tr_key = 0; bool tr_attached = false;     // its entry in the per-process kernel cache (reference-counted)
     int tr_regs = 0, tr_local = 0;               // its registers per thread / local-memory bytes (spills)
     int tr_lanes = 1;                            // (serial kernel) instances per thread
     int tr_ring_floats = 0;                      // (serial kernel) floats of the shared-memory input ring per thread
@@ -1384,6 +1385,7 @@ void fx8010_gpu_destroy(fx8010_gpu* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     sync_all(h);
+    tr_reset(h);
     free_state(h);
     cudaFree(h->d_flags); cudaFree(h->d_tabs); cudaFree(h->d_events); cudaFree(h->d_planar_in); cudaFree(h->d_planar_out);
     if (h->ev_events) cudaEventDestroy(h->ev_events);

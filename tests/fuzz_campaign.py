@@ -1,6 +1,6 @@
 """Developer tool (GPU box): a longer differential fuzz than the test suite runs — random programs of both generator
 families over random instance counts, block splits and forced geometries, GPU against the oracle, all state compared.
-usage: fuzz_campaign.py [seconds]   (prints the first failing case, exit code 1)"""
+usage: fuzz_campaign.py [seconds] [translate]   (prints the first failing case, exit code 1; `translate`: only the translator's cases)"""
 import importlib, os, sys, time, traceback
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,7 +23,14 @@ def nan_tolerant_equal(a, b, what=""):
 fx = importlib.import_module("fx8010-emulator-core_b200")
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 ENVS = [{}, {}, {}, {"FX8010_TUNE_K": "1"}, {"FX8010_TUNE_K": "2"}, {"FX8010_TUNE_M": "4"}, {"FX8010_NO_PAIRS": "1"}, {"FX8010_NO_TSPLIT": "1"},
-        {"FX8010_USE_TMA": "2"}, {"FX8010_USE_TMA": "0"}, {"FX8010_TUNE_M": "16", "FX8010_TUNE_K": "2"}, {"FX8010_NO_STATELESS": "1"}, {"FX8010_TUNE_SEG": "3"}]
+        {"FX8010_USE_TMA": "2"}, {"FX8010_USE_TMA": "0"}, {"FX8010_TUNE_M": "16", "FX8010_TUNE_K": "2"}, {"FX8010_NO_STATELESS": "1"}, {"FX8010_TUNE_SEG": "3"},
+        # the program translator (NVRTC-compiled kernels, compiled before the first launch): general programs, stateless ones on the streaming
+        # kernel, recurrences and delay lines routed to the serial kernel, 1 / 2 / 4 instances per thread, short input rings
+        {"FX8010_TRANSLATE": "2"}, {"FX8010_TRANSLATE": "2", "FX8010_TR_RECUR": "3"}, {"FX8010_TRANSLATE": "2", "FX8010_TR_RECUR": "3", "FX8010_TR_RING": "8"},
+        {"FX8010_TRANSLATE": "2", "FX8010_TR_K": "4", "FX8010_TR_RECUR": "1"}, {"FX8010_TRANSLATE": "2", "FX8010_TR_K": "2"}, {"FX8010_TRANSLATE": "2", "FX8010_TR_G": "1", "FX8010_TR_RECUR": "3"},
+        {"FX8010_TRANSLATE": "2", "FX8010_TR_IFCONV": "1"}, {"FX8010_TRANSLATE": "2", "FX8010_TR_RECUR": "3", "FX8010_TR_G": "4", "FX8010_TR_RING": "16"}]
+if len(sys.argv) > 2 and sys.argv[2] == "translate":
+    ENVS = [e for e in ENVS if "FX8010_TRANSLATE" in e]
 t0, seed, n_ok = time.time(), 0, 0
 while time.time() - t0 < budget:
     seed += 1
@@ -32,6 +39,7 @@ while time.time() - t0 < budget:
     for k in list(os.environ):
         if k.startswith("FX8010_"):
             del os.environ[k]
+    os.environ["FX8010_TRANSLATE"] = "0"          # (the interpreter kernels unless the case says otherwise: the default mode switches kernels when NVRTC is done)
     os.environ.update(env)
     kind = seed % 3
     ch = 2 if seed % 11 == 5 else 1

@@ -316,3 +316,31 @@ def test_tram_streams_per_instance_pointers(fx, po, monkeypatch):
         assert gpu.launch_info().kernel_variant & 128
     finally:
         gpu.close()
+
+
+def test_kernel_cache_is_shared_between_handles(fx, po):
+    """A second handle with the same program (and the same folded values) finds the loaded kernel: no second compilation."""
+    rng = np.random.default_rng(81)
+    text = progs.random_program(rng, 120)
+    prog = fx.Program(text)
+    n = 128
+    x = torch_free_input(rng, 24, n)
+    first = None
+    for k in range(2):
+        gpu = fx.Gpu(n, 1)
+        gpu.load_program(prog)
+        gpu.set_option(fx.OPT_TRANSLATE, 2)
+        t0 = time.time()
+        y = gpu.process_host(x)
+        dt = time.time() - t0
+        assert gpu.translate_status()["state"] == 2
+        if first is None:
+            first = (y, dt)
+        else:
+            assert_bits_equal(y, first[0], "second handle")
+            assert dt < 0.5 * first[1] or dt < 0.05, (dt, first[1])
+        gpu.close()
+
+
+def torch_free_input(rng, s, n):
+    return (1.8 * rng.random((1, s, n)) - 0.9).astype(np.float32)
