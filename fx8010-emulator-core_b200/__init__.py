@@ -145,6 +145,7 @@ HOST_SYMBOLS = {
     "fx8010_host_load_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "fx8010_host_ready": (C.c_int, [C.c_void_p]),
     "fx8010_host_set_relaxed": (None, [C.c_void_p, C.c_int]),
+    "fx8010_host_set_translation": (C.c_int, [C.c_void_p, C.c_int]),
     "fx8010_host_num_registers": (C.c_int, [C.c_void_p]),
     "fx8010_host_register_info": (None, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float),
                                          C.POINTER(C.c_int), C.c_char_p, C.c_int]),
@@ -234,6 +235,11 @@ class Program:
             self.h = None
 
     __del__ = close
+
+    def set_translation(self, mode: int):
+        """FX8010::setTranslation — the program translator's mode for this object's device handle(s)."""
+        if self.L.fx8010_host_set_translation(self.h, mode):
+            raise ValueError("translation mode must be 0, 1 or 2")
 
     def load(self, text=None, path=None) -> bool:
         if path is not None:

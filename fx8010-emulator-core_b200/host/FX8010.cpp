@@ -40,6 +40,7 @@ void FX8010::ensureUploaded() {
                 throw std::runtime_error(msg);
             }
         }
+        if (translate_mode_ >= 0) check(fx8010_multi_set_option(multi_, FX8010_OPT_TRANSLATE, translate_mode_), "set_option");
         if (!uploaded_ || uploaded_generation_ != front_.generation()) {
             check(fx8010_multi_load_program(multi_, front_.image()), "load_program");
             uploaded_ = true;
@@ -58,6 +59,7 @@ void FX8010::ensureUploaded() {
     // The image the device holds is stale after ANY later loadFile/loadText/initialize (they append, like the
     // reference, source/FX8010.cpp:777-875 — but an edit that keeps the counts equal must be noticed too).  A reload
     // puts every instance back into the state of a freshly loaded object (see FX8010.h).
+    if (translate_mode_ >= 0) check(fx8010_gpu_set_option(gpu_, FX8010_OPT_TRANSLATE, translate_mode_), "set_option");
     if (!uploaded_ || uploaded_generation_ != front_.generation()) {
         check(fx8010_gpu_load_program(gpu_, front_.image()), "load_program");
         uploaded_ = true;
@@ -69,6 +71,11 @@ fx8010_gpu* FX8010::gpuHandle() {
     ensureUploaded();
     if (multi_) throw std::runtime_error("FX8010 (B200): this object drives several GPUs; there is no single device handle");
     return gpu_;
+}
+
+void FX8010::setTranslation(int mode) {
+    if (mode < 0 || mode > 2) throw std::invalid_argument("FX8010 (B200): setTranslation takes 0, 1 or 2");
+    translate_mode_ = mode;                                     // applied by the next process* call (ensureUploaded)
 }
 
 std::vector<float> FX8010::process(const std::vector<float>& inputSamples) {

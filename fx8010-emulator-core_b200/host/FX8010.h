@@ -73,6 +73,9 @@ public:
                                         const std::vector<ControlChange>& changes, void* stream);
     // DEVICE buffers laid out [channel][instance][sample] (planar audio), asynchronous on `stream`
     void processBlockDevicePlanar(const float* d_in, float* d_out, int n_samples, void* stream);
+    // program translator (include/fx8010_gpu.h, FX8010_OPT_TRANSLATE): 0 interpreter kernels only, 1 compile in the background and switch
+    // over when the kernel is loaded (default), 2 compile before the first block
+    void setTranslation(int mode);
     unsigned long long getInstructionCounterTotal();           // summed over instances
     fx8010_gpu* gpuHandle();                                   // creates the handle / uploads the program if needed
     fx8010::Frontend& frontend() { return front_; }
@@ -87,6 +90,7 @@ private:
     fx8010_gpu* gpu_ = nullptr;
     std::vector<int> devices_;                                 // more than one entry: the multi-GPU executor below is used instead of gpu_
     fx8010_multi* multi_ = nullptr;
+    int translate_mode_ = -1;                                  // -1: the library's default
     bool uploaded_ = false;                                    // the device holds the image of generation uploaded_generation_
     unsigned long uploaded_generation_ = 0;
     std::vector<float> in_block_, out_block_;

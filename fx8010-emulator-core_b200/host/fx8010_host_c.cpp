@@ -42,6 +42,9 @@ const char* fx8010_host_last_error(fx8010_host* h) { return h ? h->err.c_str() :
 int fx8010_host_load_file(fx8010_host* h, const char* path) { return h->fx.loadFile(path) ? 1 : 0; }
 int fx8010_host_load_text(fx8010_host* h, const char* text, size_t len) { return h->fx.loadText(std::string(text, len)) ? 1 : 0; }
 void fx8010_host_set_relaxed(fx8010_host* h, int on) { h->fx.setRelaxedSyntax(on != 0); }
+int fx8010_host_set_translation(fx8010_host* h, int mode) {
+    try { h->fx.setTranslation(mode); return 0; } catch (...) { return 1; }
+}
 int fx8010_host_ready(fx8010_host* h) { return h->fx.getReadyStatus() ? 1 : 0; }
 
 int fx8010_host_num_registers(fx8010_host* h) { return (int)h->fx.frontend().registers().size(); }

@@ -31,6 +31,8 @@ FX8010_API int fx8010_host_load_text(fx8010_host* h, const char* text, size_t le
 FX8010_API int fx8010_host_ready(fx8010_host* h);                      /* getReadyStatus */
 /* extension: relaxed syntax (accepts the reference README's `itramsize 100`, CR-LF files, blank lines after `end`) */
 FX8010_API void fx8010_host_set_relaxed(fx8010_host* h, int on);
+/* FX8010::setTranslation: the program translator's mode (FX8010_OPT_TRANSLATE of fx8010_gpu.h: 0, 1 or 2); 0 ok / 1 bad mode */
+FX8010_API int fx8010_host_set_translation(fx8010_host* h, int mode);
 
 /* decoded image (what loadFile leaves in the object) */
 FX8010_API int fx8010_host_num_registers(fx8010_host* h);

@@ -344,3 +344,20 @@ def test_kernel_cache_is_shared_between_handles(fx, po):
 
 def torch_free_input(rng, s, n):
     return (1.8 * rng.random((1, s, n)) - 0.9).astype(np.float32)
+
+
+def test_facade_set_translation(fx, po):
+    """Klangraum::FX8010::setTranslation through the facade's C view: a SKIP program on 64 instances, translated before the first block."""
+    rng = np.random.default_rng(91)
+    n, s = 64, 40
+    text = progs.random_program(rng, 60)
+    facade = fx.Program(text, channels=1, instances=n)
+    assert facade.loaded
+    facade.set_translation(2)
+    img = po.Image(facade.instructions(), facade.registers(), facade.itram_size, facade.xtram_size, facade.controls(), facade.tables())
+    orc = po.Oracle(img, n, 1)
+    x = (1.8 * rng.random((1, s, n)) - 0.9).astype(np.float32)
+    assert_bits_equal(facade.process_block(x), orc.process(x), "facade block")
+    with pytest.raises(ValueError):
+        facade.set_translation(7)
+    facade.close()
