@@ -120,6 +120,7 @@ struct fx8010_gpu {
     int sl_n_tr = 0;
     bool sl_tram = false;                        // the program has TRAM instructions (pointers are loaded and kept)
     int use_tram_im = 1;
+    unsigned long long tram_periods = 0;         // sample periods launched since load_program (a pristine delay line's pointers are this, modulo the ring size)
     bool tram_ptrs_pristine = true;              // TRAM pointers as load_program left them (read and write pointer of a ring move in lockstep)
     bool sl_ccr_live = false;                    // the uploaded stateless encoding keeps per-sample CCR stores
     bool sl_serial = false;                      // ... with self-carried operands: one time segment, state loaded and kept
@@ -165,6 +166,7 @@ struct fx8010_gpu {
     void* tr_fn = nullptr;                       // CUfunction of the translated kernel
     unsigned long long tr_key = 0; bool tr_attached = false;     // its entry in the per-process kernel cache (reference-counted)
     int tr_regs = 0, tr_local = 0;               // its registers per thread / local-memory bytes (spills)
+    int tr_kind = 0;                             // 0 serial kernel, 1 streaming kernel (stateless program), 2 streaming kernel with TRAM (time-cut delay line)
     int tr_lanes = 1;                            // (serial kernel) instances per thread
     int tr_ring_floats = 0;                      // (serial kernel) floats of the shared-memory input ring per thread
     std::shared_ptr<void> tr_job;                // the running compilation
@@ -1096,7 +1098,15 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
     const int span = (h->sl_ok && h->use_sl && !h->trace_mode && h->use_tsplit) ? known_tram_span(h) : 0;
     // (worth it when the block needs at most two launches — cfg3 at 16 384 instances x 1 024 periods: span 100, eleven launches,
     //  198 us against 139 us for the serial kernel with its sample split; span 1 000, two launches, 111 against 112; one launch, 82)
-    const bool tsplit = span >= MIN_TSPLIT_SPAN && 2L * span >= n_samples;
+    // ... or any number of launches when they run on the translated streaming kernel (fx8010_translate.inc, tr_kind 2): a stretch of 100 periods
+    // of cfg3 is a 6 us launch there (cfg3, ring of 100: 11 launches 66 us against 134 us serial)
+    bool tr_stretch = false;
+    if (span >= MIN_TSPLIT_SPAN && 2L * span < n_samples && tr_kind(h) == 2 && h->use_translate && h->N % 4 == 0 && (in_cs * 4) % 16 == 0 && (out_cs * 4) % 16 == 0) {
+        tr_stretch = true;
+        for (int b = 0; b < n_blk && tr_stretch; ++b) tr_stretch = (((uintptr_t)ins[b] | (uintptr_t)outs[b]) & 15u) == 0;
+        tr_stretch = tr_stretch && tr_ready(h);
+    }
+    const bool tsplit = span >= MIN_TSPLIT_SPAN && (2L * span >= n_samples || tr_stretch);
     if (tsplit && n_samples > span) {
         for (int b = 0; b < n_blk; ++b)
             for (int s0 = 0; s0 < n_samples; s0 += span) {
@@ -1114,6 +1124,7 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
         for (int b = 0; b < n_blk; ++b) {
             const int rc = tr_launch(h, ins[b], outs[b], in_cs, out_cs, n_samples, st);
             if (rc) return rc;
+            h->tram_periods += (unsigned long long)n_samples;
         }
         return FX8010_OK;
     }
@@ -1121,11 +1132,12 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
     const bool fusable = h->sl_ok && h->use_sl && !h->trace_mode && !h->sl_serial && h->use_fuse;
     // A stateless program runs on its translated streaming kernel once that exists (fx8010_translate.inc): 4 adjacent instances
     // per thread, so the instance count and every buffer must allow 16-byte accesses.
-    bool tr_sl = h->stateless && !h->trace_mode && h->N % 4 == 0 && (in_cs * 4) % 16 == 0 && (out_cs * 4) % 16 == 0 && ((size_t)ns * h->N * 4) % 16 == 0;
+    const bool tr_delay = !h->stateless && tsplit && ns <= span && tr_kind(h) == 2;       // a time-cut launch of a delay line
+    bool tr_sl = (h->stateless || tr_delay) && !h->trace_mode && h->N % 4 == 0 && (in_cs * 4) % 16 == 0 && (out_cs * 4) % 16 == 0 && ((size_t)ns * h->N * 4) % 16 == 0;
     for (int b = 0; b < n_blk && tr_sl; ++b) tr_sl = (((uintptr_t)ins[b] | (uintptr_t)outs[b]) & 15u) == 0;
     tr_sl = tr_sl && tr_ready(h);
     for (int b0 = 0; b0 < n_blk;) {
-        const int nb = (fusable || tr_sl) ? std::min(n_blk - b0, MAX_FUSED_BLOCKS) : 1;
+        const int nb = (fusable || (tr_sl && h->stateless)) ? std::min(n_blk - b0, MAX_FUSED_BLOCKS) : 1;
         if (h->encode_dirty && !tr_sl) { select_tables(h); h->plan_key.ns = -1; }
         Launch L = {};
         // the plan depends on the batch length and on how far the buffers are aligned
@@ -1286,6 +1298,7 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
         }
         bool pairs = false;
         if (L.M > 0 && !tr_sl) for (uint8_t f : h->sl_fuse) pairs = pairs || f;
+        h->tram_periods += (unsigned long long)ns * nb;
         if (!late_wait) h->chain.clear();          // this launch waited at its start: everything before it is complete
         h->chain.push_back(sp); h->chain_stream = st;
         h->info.kernel_launches++;
@@ -1513,7 +1526,7 @@ int fx8010_gpu_load_program(fx8010_gpu* h, const fx8010_program_image* im) {
     if (!h->wb.empty()) FX_CUDA(h, cudaMemcpy(h->d_wb, h->wb.data(), sizeof(uint32_t) * h->wb.size(), cudaMemcpyHostToDevice));
     FX_CUDA(h, cudaDeviceSynchronize());
     h->encode_dirty = true;
-    h->loaded = true; h->tram_ptrs_pristine = true; h->plan_key = PlanKey();
+    h->loaded = true; h->tram_ptrs_pristine = true; h->tram_periods = 0; h->plan_key = PlanKey();
     return FX8010_OK;
 }
 
@@ -2010,9 +2023,10 @@ long long fx8010_translate_source(const fx8010_program_image* im, int n_instance
     for (int r = 0; r < im->n_regs; ++r) tmp.reg_value[r] = im->regs[r].init_value;
     tmp.tr_volatile.assign(im->n_regs, 0);
     analyse(&tmp);
-    if (!tmp.stateless && !tr_eligible(&tmp)) return -2;
+    const int kind = (tr_kind(&tmp) == 2 && known_tram_span(&tmp) < MIN_TSPLIT_SPAN) ? 0 : tr_kind(&tmp);
+    if (kind == 0 && !tr_eligible(&tmp)) return -2;
     std::vector<uint8_t> folded;
-    const std::string src = tmp.stateless ? tr_generate_sl(&tmp, folded) : tr_generate(&tmp, folded);
+    const std::string src = kind ? tr_generate_sl(&tmp, folded, kind == 2) : tr_generate(&tmp, folded);
     if (buf && cap) { strncpy(buf, src.c_str(), cap - 1); buf[cap - 1] = 0; }
     if (compile_check) {                                     // NVRTC -> sm_100a CUBIN (works without a GPU)
         std::vector<char> cubin; std::string log;

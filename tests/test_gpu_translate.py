@@ -361,3 +361,38 @@ def test_facade_set_translation(fx, po):
     with pytest.raises(ValueError):
         facade.set_translation(7)
     facade.close()
+
+
+@pytest.mark.parametrize("name", sorted(TRAM_CASES))
+def test_delay_lines_time_cut_on_the_streaming_kernel(fx, po, name):
+    """Default routing with the translator on: the launches fx8010_gpu.cu cuts along time (independent periods over a stretch) run on
+    the translated streaming kernel with TRAM, everything else of these programs on the instruction-major kernel; same bits either way."""
+    rng = np.random.default_rng(31)
+    n = 136
+    text = _tram_prog(**TRAM_CASES[name])
+    ctl = {"dly": rng.integers(70, 390, n).astype(np.float32)} if name == "ctl_off" else None
+    prog, img, orc, gpu = make_pair(fx, po, text, n)
+    try:
+        gpu.set_option(fx.OPT_TRANSLATE, 2)
+        for nm, v in (ctl or {}).items():
+            gpu.set_controls(prog.reg_index(nm), v); orc.set_register(prog.reg_index(nm), v)
+        x = progs.impulse_noise(n, 1900, rng)
+        start, used = 0, False
+        for k in [1, 150, 33, 64, 2, 450, 1200]:
+            xb = x[start:start + k].reshape(1, k, n)
+            assert_bits_equal(gpu.process_host(xb), orc.process(xb), f"tram {name} block at {start}")
+            used = used or bool(gpu.launch_info().kernel_variant & 128)
+            start += k
+        compare_state(gpu, orc, img, f"tram {name}", (0, n // 2, n - 1))
+        if name in ("s1000", "xdelay", "wr_off", "s100", "s66"):
+            assert used, (name, gpu.translate_status())
+    finally:
+        gpu.close()
+
+
+@pytest.mark.parametrize("size", [1000, 8192])
+def test_cfg3_full_width_translated(fx, po, size):
+    rng = np.random.default_rng(33)
+    n = 2048
+    st, info = run_translated(fx, po, progs.cfg3_delay(size), n, [1024, 1024, 300], rng, amp=0.9, what=f"cfg3 {size} translated")
+    assert st["state"] == 2, st

@@ -23,12 +23,13 @@ def po():
     return pyoracle
 
 
-def check(po, text, n, blocks, rng, channels=1, controls=None, amp=0.9, what="case"):
+def check(po, text, n, blocks, rng, channels=1, controls=None, amp=0.9, what="case", span=None):
     prog = fx.Program(text, channels=channels)
     assert prog.loaded, prog.errors()
     img = po.Image(prog.instructions(), prog.registers(), prog.itram_size, prog.xtram_size, prog.controls(), prog.tables())
     orc = po.Oracle(img, n, channels)
     ht = HostTranslated(prog, n, channels)
+    ht.span = span
     for name, vals in (controls or {}).items():
         idx = prog.reg_index(name)
         orc.set_register(idx, vals)
@@ -172,6 +173,31 @@ def stateless_variant(text: str) -> str:
         return text
     return "\n".join(["static a", "static b", "control g = 0.5", "input in_l 0", "output out_l 0", "macs a, 0, in_l, g", "log b, a, 5, 0",
                       "limit a, b, a, 0.25", "exp b, a, 3, 0", "macsn out_l, b, a, g", "end"])
+
+
+@pytest.mark.parametrize("name", ["cfg3_200", "tap", "two_rings", "xdelay"])
+def test_delay_lines_streaming_kernel(po, name):
+    """Delay lines whose periods are independent over a stretch (ring positions shared by all instances): the streaming kernel with TRAM
+    READs loaded like inputs and WRITEs stored like outputs, one emulated launch per stretch, work items in random order."""
+    rng = np.random.default_rng(23)
+    n = 8
+    if name == "cfg3_200":
+        text, span = progs.cfg3_delay(200), 200
+    elif name == "tap":          # write first, read 150 periods later (write offset 3): read-after-write distance 153, write-after-read 347
+        text = "\n".join(["static a", "static rd", "input in_l 0", "output out_l 0", "itramsize 500 ", "idelay write, in_l, at, 3",
+                          "idelay read, rd, at, 150", "macs a, rd, 0.5, 0.5", "macs out_l, in_l, rd, 0.5", "end"])
+        span = 153
+    elif name == "two_rings":
+        text = "\n".join(["static a", "static a2", "static rd", "static rx", "input in_l 0", "output out_l 0", "itramsize 700 ", "xtramsize 300 ",
+                          "idelay read, rd, at, 0", "macs a, in_l, rd, 0.5", "idelay write, a, at, 0", "xdelay write, in_l, at, 0", "xdelay read, rx, at, 150",
+                          "macs a2, rx, 0.5, 0.5", "macs out_l, a2, rd, 0.5", "end"])
+        span = 150
+    else:
+        text = "\n".join(["static a", "static rd", "input in_l 0", "output out_l 0", "xtramsize 2000 ", "xdelay read, rd, at, 0", "macs a, in_l, rd, 0.5",
+                          "xdelay write, a, at, 0", "macs out_l, in_l, rd, 0.5", "end"])
+        span = 2000
+    ht = check(po, text, n, [70, 400, 33, 1, 250], rng, what=name, span=span)
+    assert "fx_translated_sl" in ht.src and "#define FXT_NTR 0" not in ht.src
 
 
 @pytest.mark.parametrize("name", ["cfg5", "random"])

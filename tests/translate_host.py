@@ -49,7 +49,7 @@ def compile_source(src: str) -> C.CDLL:
         lib.fx_translated_host.argtypes = [C.c_int] + [C.c_void_p] * 12 + [C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]
     else:                       # stateless program: the streaming kernel, one call per (thread, blockIdx.y)
         lib.fx_translated_sl_host.restype = None
-        lib.fx_translated_sl_host.argtypes = [C.c_int, C.c_int, FxtIo] + [C.c_void_p] * 6 + [C.c_size_t, C.c_size_t] + [C.c_int] * 6
+        lib.fx_translated_sl_host.argtypes = [C.c_int, C.c_int, FxtIo] + [C.c_void_p] * 6 + [C.c_size_t, C.c_size_t] + [C.c_int] * 6 + [C.c_void_p] * 3 + [C.c_int] * 6
     _cache[key] = lib
     return lib
 
@@ -65,6 +65,7 @@ class HostTranslated:
         if src is None:
             raise ValueError("program is not eligible for translation")
         self.src = src
+        self.span = None                    # delay lines: periods per emulated launch (the caller sets it from the ring geometry)
         self.lib = compile_source(src)
         self.n, self.c = n, channels
         regs = prog.registers()
@@ -90,7 +91,15 @@ class HostTranslated:
         out = np.zeros((self.c, s, self.n), np.float32)
         cs = s * self.n
         if hasattr(self.lib, "fx_translated_sl_host"):
-            return self.process_blocks([x], s)[0]
+            if "#define FXT_NTR 0" in self.src:
+                return self.process_blocks([x], s)[0]
+            # a delay line: one emulated launch per stretch of at most `span` periods (what fx8010_gpu.cu::launch_blocks does)
+            assert self.span and x is not None
+            outs = []
+            for a in range(0, s, self.span):
+                k = min(self.span, s - a)
+                outs.append(self.process_blocks([x[:, a:a + k]], k, seg_len=4)[0])
+            return np.concatenate(outs, axis=1)
         import re
         lanes = int(re.search(r"#define FXT_K (\d+)", self.src).group(1))
         for i in range(-(-self.n // lanes) + 1):            # one thread past the end: the bounds check
@@ -116,9 +125,11 @@ class HostTranslated:
         cs = s * self.n
         n_seg = -(-s // seg_len)
         order = [(tx, by) for by in range(n_seg * nb) for tx in range(self.n // 4 + 1)]     # one thread past the end: the bounds check
+        base = [int(v) for v in self.tram_ptrs[:, 0]]      # what the host passes: the (shared) ring pointers at the launch's first period
         rng = np.random.default_rng(0)
         rng.shuffle(order)                                                                 # work items are independent: any order
         for tx, by in order:
             self.lib.fx_translated_sl_host(int(tx), int(by), io, self.registers.ctypes.data, self.acc.ctypes.data, self.out_latch.ctypes.data,
-                                           self.counts.ctypes.data, self.flags.ctypes.data, self.tabs.ctypes.data, cs, cs, s, seg_len, n_seg, nb, self.n, 0)
+                                           self.counts.ctypes.data, self.flags.ctypes.data, self.tabs.ctypes.data, cs, cs, s, seg_len, n_seg, nb, self.n, 0,
+                                           self.tram_ptrs.ctypes.data, self.itram.ctypes.data, self.xtram.ctypes.data, self.isz, self.xsz, *base)
         return outs
