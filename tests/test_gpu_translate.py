@@ -396,3 +396,30 @@ def test_cfg3_full_width_translated(fx, po, size):
     n = 2048
     st, info = run_translated(fx, po, progs.cfg3_delay(size), n, [1024, 1024, 300], rng, amp=0.9, what=f"cfg3 {size} translated")
     assert st["state"] == 2, st
+
+
+def test_delay_line_background_compile_switches_over(fx, po):
+    """Mode 1 on a delay line: the instruction-major kernel runs the time-cut launches until NVRTC is done, then the translated streaming
+    kernel takes over in mid-stream; the ring positions it gets from the host continue where the other kernel left them."""
+    rng = np.random.default_rng(97)
+    n = 256
+    prog, img, orc, gpu = make_pair(fx, po, progs.cfg3_delay(300), n)
+    try:
+        gpu.set_option(fx.OPT_TRANSLATE, 1)
+        seen = set()
+        t0 = time.time()
+        while time.time() - t0 < 60:
+            k = int(rng.integers(1, 300))
+            x = (1.8 * rng.random((1, k, n)) - 0.9).astype(np.float32)
+            assert_bits_equal(gpu.process_host(x), orc.process(x), "delay line stream")
+            seen.add(bool(gpu.launch_info().kernel_variant & 128))
+            if len(seen) == 2:
+                break
+            time.sleep(0.02)
+        for k in (299, 7, 300):
+            x = (1.8 * rng.random((1, k, n)) - 0.9).astype(np.float32)
+            assert_bits_equal(gpu.process_host(x), orc.process(x), "delay line stream, after the switch")
+        assert True in seen, gpu.translate_status()
+        compare_state(gpu, orc, img, "delay line background")
+    finally:
+        gpu.close()
