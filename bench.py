@@ -557,12 +557,12 @@ def main():
         del pin, pout
     W.close()
 
-    # ---- the configs BASELINE.json shards over the GPUs, at their per-GPU share: cfg4 = 65 536 instances
-    # in total, cfg5 = 32 768 per GPU; same timing rules, fewer steps (one cfg5 block takes tens of milliseconds)
+    # ---- the other BASELINE.json configs at their per-GPU share: cfg3 = 16 384 instances per GPU (ring of 1 000), cfg4 =
+    # 65 536 instances in total, cfg5 = 32 768 per GPU; same timing rules, fewer steps
     sharded = None
     if not args.no_sharded and args.config == "cfg2":
         sharded = {}
-        for cfg, n_cfg, k_steps in (("cfg4", max(1, 65536 // world), 20), ("cfg5", 32768, 3)):
+        for cfg, n_cfg, k_steps in (("cfg3", 16384, 10), ("cfg4", max(1, 65536 // world), 20), ("cfg5", 32768, 3)):
             t_cfg, _, b_cfg, l_cfg = workload(cfg)
             Wc = Workload(fx, torch, cfg, n_cfg, local_rank, rank)
             m_all, l_n = Wc.timed(k_steps, 3, 3, barrier)
@@ -575,6 +575,7 @@ def main():
             rec = {"workload": l_cfg, "instances_per_gpu": n_cfg, "instances_total": n_cfg * world, "steps": k_steps, "ms_per_step": 1e3 * step_s,
                    "value": float(n_cfg) * BLOCK * world / step_s, "unit": "instance-samples/s", "dsp_instr_per_s": ex / step_s,
                    "hbm_frac": b_cfg * n_cfg * BLOCK / step_s / 1e9 / peak, "gpu_launches": l_n, "parity": par}
+            rec["translated_kernel"] = bool(Wc.gpu.launch_info().kernel_variant & 128)
             if cfg == "cfg5":
                 rec["translated"] = Wc.gpu.translate_status()      # FX8010_OPT_TRANSLATE: state 2 = the NVRTC-compiled kernel ran
                 rec["compute_roofline"] = compute_roofline(t_cfg, ex / world, n_cfg, step_s, (clocks or {}).get("sm_mhz") if clocks else None, b_cfg, peak)
