@@ -1998,7 +1998,7 @@ int fx8010_gpu_trace(fx8010_gpu* h, const float* in, float* out, int n_samples, 
 // ---- program translator: status and the host-only source generator (tests/test_translate.py) ----
 int fx8010_gpu_translate_status(fx8010_gpu* h, int* state, int* regs_per_thread, int* local_bytes, char* message, size_t message_cap) {
     if (!h) return FX8010_ERR_ARG;
-    if (h->tr_state == 1 && h->loaded) tr_ready(h);          // pick up a finished background compilation
+    if (h->tr_state == 1 && h->loaded && cudaSetDevice(h->device) == cudaSuccess) tr_ready(h);   // pick up a finished background compilation (the kernel loads into this device's context)
     if (state) *state = h->tr_state;
     if (regs_per_thread) *regs_per_thread = h->tr_regs;
     if (local_bytes) *local_bytes = h->tr_local;
