@@ -1257,6 +1257,16 @@ int launch_blocks(fx8010_gpu* h, const float* const* ins, float* const* outs, in
                 p.tr_wy[x] = t.w_yreg >= 0 ? (sl_word(h, t.w_yreg, L.B, L.K, L.M) & SL_OFF_MASK) : 0xffffffffu;
                 p.tr_wfirst[x] = t.w_first;
             }
+            // cut along time (the pointers are as load_program left them and have moved once per period launched since — known_tram_span):
+            // every segment starts from the host's copy of the pointers, not from the array the last segment's owner rewrites
+            p.tr_base_valid = 0;
+            if (h->sl_tram && tsplit && L.n_seg > 1 && h->tram_ptrs_pristine) {
+                p.tr_base_valid = 1;
+                for (int j = 0; j < 4; ++j) {
+                    const int size = j < 2 ? h->itram_size : h->xtram_size;
+                    p.tr_base[j] = (size > 0 && p.tr_ops[j]) ? (int)(h->tram_periods * (unsigned long long)p.tr_ops[j] % (unsigned long long)size) : 0;
+                }
+            }
             p.pdl_late_wait = late_wait;
             p.use_tma = 0;
             // Bulk tensor copies (TMA) for the input stage: one instruction per batch and channel instead of one cp.async per thread and

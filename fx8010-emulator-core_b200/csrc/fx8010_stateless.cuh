@@ -101,6 +101,8 @@ struct alignas(64) SLParams {
     uint32_t tr_y[2];           // byte offset of the row holding the READ's offset operand
     uint32_t tr_wy[2];          // ... of the same TRAM's WRITE (0xffffffff: no WRITE instruction)
     int tr_wfirst[2];           // the WRITE comes before the READ in program order
+    int tr_base_valid;          // a launch cut along time: the ring pointers at its first period come from the host (tr_base) — the owner of the
+    int tr_base[4];             // last period writes the new ones to `ptrs`, and a thread block scheduled after it must not start from those
     int pdl_late_wait;
 };
 
@@ -617,8 +619,11 @@ __global__ void __launch_bounds__(128, 3) fx_stateless_kernel(const __grid_const
     if (TRAM && p.has_tram) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            tp0[0][k] = p.ptrs[inst0 + k]; tp0[1][k] = p.ptrs[N + inst0 + k];
-            tp0[2][k] = p.ptrs[2 * N + inst0 + k]; tp0[3][k] = p.ptrs[3 * N + inst0 + k];
+            if (p.tr_base_valid) { tp0[0][k] = p.tr_base[0]; tp0[1][k] = p.tr_base[1]; tp0[2][k] = p.tr_base[2]; tp0[3][k] = p.tr_base[3]; }
+            else {
+                tp0[0][k] = p.ptrs[inst0 + k]; tp0[1][k] = p.ptrs[N + inst0 + k];
+                tp0[2][k] = p.ptrs[2 * N + inst0 + k]; tp0[3][k] = p.ptrs[3 * N + inst0 + k];
+            }
             if (s_begin) {          // a later time segment of a launch whose periods are independent (fx8010_gpu.cu::known_tram_span): pointers at its first period
 #pragma unroll
                 for (int j = 0; j < 4; ++j) if (p.tr_ops[j]) tp0[j][k] = ring_add(tp0[j][k], s_begin * p.tr_ops[j], cx.rsize[j >> 1]);
