@@ -338,7 +338,7 @@ def test_kernel_cache_is_shared_between_handles(fx, po):
             first = (y, dt)
         else:
             assert_bits_equal(y, first[0], "second handle")
-            assert dt < 0.5 * first[1] or dt < 0.05, (dt, first[1])
+            assert dt < max(0.5 * first[1], 0.25), (dt, first[1])      # (no second compilation: NVRTC takes 0.3 s and more for this program)
         gpu.close()
 
 
