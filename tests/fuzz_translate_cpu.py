@@ -23,7 +23,7 @@ def nan_tolerant_equal(a, b, what=""):
 
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
-t0, seed, n_ok, n_declined, n_sl = time.time(), 0, 0, 0, 0
+t0, seed, n_ok, n_declined, n_sl, n_delay = time.time(), 0, 0, 0, 0, 0
 while time.time() - t0 < budget:
     seed += 1
     rng = np.random.default_rng(991000 + seed)
@@ -50,6 +50,9 @@ while time.time() - t0 < budget:
     if src is None:
         n_declined += 1
         continue
+    if "fx_translated_sl" in src and "#define FXT_NTR 0" not in src:
+        n_delay += 1              # a delay line cut along time: needs the stretch length (tests/test_translate.py covers those with known spans)
+        continue
     n_sl += "fx_translated_sl" in src
     try:
         ctl = {nm: rng.random(n).astype(np.float32) for nm in prog.controls()}
@@ -60,4 +63,4 @@ while time.time() - t0 < budget:
         print(text)
         traceback.print_exc()
         sys.exit(1)
-print(f"translator fuzz (CPU check of the generated source): {n_ok} cases passed ({n_sl} on the streaming kernel), {n_declined} declined by the translator, {time.time() - t0:.0f} s")
+print(f"translator fuzz (CPU check of the generated source): {n_ok} cases passed ({n_sl} on the streaming kernel), {n_declined} declined by the translator, {n_delay} delay lines skipped, {time.time() - t0:.0f} s")

@@ -1,4 +1,4 @@
-"""Developer tool (GPU box): run one BASELINE config a few times for ncu. usage: probe_cfg.py cfgN instances samples [launches]"""
+"""Developer tool (GPU box): run one BASELINE config a few times for ncu. usage: probe_cfg.py cfgN instances samples [launches [itramsize]]"""
 import importlib, os, sys
 import numpy as np
 import torch
@@ -10,6 +10,8 @@ fx = importlib.import_module("fx8010-emulator-core_b200")
 cfg, N, S = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 L = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 text = bench.workload(cfg)[0]
+if cfg == "cfg3" and len(sys.argv) > 5:
+    text = progs.cfg3_delay(int(sys.argv[5]))
 p = fx.Program(text); assert p.loaded, p.errors()
 g = fx.Gpu(N, 1); g.load_program(p)
 rng = np.random.default_rng(1)
