@@ -120,7 +120,7 @@ def test_background_compile_switches_over(fx, po):
             x = (1.8 * rng.random((1, 16, n)) - 0.9).astype(np.float32)
             assert_bits_equal(gpu.process_host(x), orc.process(x), "stream")
             seen.add(bool(gpu.launch_info().kernel_variant & 128))
-            if True in seen and len(seen) == 2:
+            if True in seen:
                 break
             time.sleep(0.02)
         assert True in seen, gpu.translate_status()
@@ -403,7 +403,9 @@ def test_delay_line_background_compile_switches_over(fx, po):
     kernel takes over in mid-stream; the ring positions it gets from the host continue where the other kernel left them."""
     rng = np.random.default_rng(97)
     n = 256
-    prog, img, orc, gpu = make_pair(fx, po, progs.cfg3_delay(300), n)
+    # (a gain nobody else uses: the generated source — the kernel cache's key — does not depend on the ring size, and a cached kernel
+    #  would be in use from the first launch on)
+    prog, img, orc, gpu = make_pair(fx, po, progs.cfg3_delay(300).replace("0.5", "0.4921875"), n)
     try:
         gpu.set_option(fx.OPT_TRANSLATE, 1)
         seen = set()
@@ -413,13 +415,13 @@ def test_delay_line_background_compile_switches_over(fx, po):
             x = (1.8 * rng.random((1, k, n)) - 0.9).astype(np.float32)
             assert_bits_equal(gpu.process_host(x), orc.process(x), "delay line stream")
             seen.add(bool(gpu.launch_info().kernel_variant & 128))
-            if len(seen) == 2:
+            if True in seen:
                 break
             time.sleep(0.02)
         for k in (299, 7, 300):
             x = (1.8 * rng.random((1, k, n)) - 0.9).astype(np.float32)
             assert_bits_equal(gpu.process_host(x), orc.process(x), "delay line stream, after the switch")
-        assert True in seen, gpu.translate_status()
+        assert seen == {False, True}, (seen, gpu.translate_status())
         compare_state(gpu, orc, img, "delay line background")
     finally:
         gpu.close()
